@@ -1,0 +1,93 @@
+"""ctypes binding of include/a2m.h.  Fails loudly: there is no CPU or PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB, build
+
+_lib = None
+
+
+class A2mError(RuntimeError):
+    pass
+
+
+class LeafDesc(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("offset_bytes", C.c_uint64), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class MidiEvent(C.Structure):
+    _fields_ = [("attack_time", C.c_uint64), ("note", C.c_uint8), ("duration", C.c_uint64), ("velocity", C.c_uint8)]
+
+
+class MidiEventList(C.Structure):
+    _fields_ = [("ptr", C.POINTER(MidiEvent)), ("length", C.c_size_t), ("_capacity", C.c_size_t)]
+
+
+class MLMultiArrayWrapper3(C.Structure):
+    _fields_ = [("strides", C.c_uint64 * 3), ("dims", C.c_uint64 * 3), ("data", C.c_void_p)]
+
+
+EXPORTS = [
+    "a2m_create", "a2m_destroy", "a2m_last_error", "a2m_load_weights", "a2m_workspace_bytes", "a2m_forward",
+    "a2m_forward_host", "a2m_last_launch_count", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
+    "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
+]
+
+
+def lib() -> C.CDLL:
+    """Loads (building in-tree first if a compiler is present and the .so is stale) the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = LIB
+    if not os.path.exists(path) or os.environ.get("A2M_REBUILD") == "1":
+        path = build()
+    else:
+        try:
+            path = build()  # no-op when up to date
+        except RuntimeError:
+            pass  # no nvcc on this box: use the prebuilt library that travelled with the tree
+    L = C.CDLL(path)
+    vp, i32, u32, u64, sz, f64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_size_t, C.c_double
+    L.a2m_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.a2m_create.restype = C.c_int
+    L.a2m_destroy.argtypes = [vp]
+    L.a2m_destroy.restype = None
+    L.a2m_last_error.argtypes = [vp]
+    L.a2m_last_error.restype = C.c_char_p
+    L.a2m_load_weights.argtypes = [vp, vp, sz, C.POINTER(LeafDesc), i32]
+    L.a2m_load_weights.restype = C.c_int
+    L.a2m_workspace_bytes.argtypes = [vp, i32, i32]
+    L.a2m_workspace_bytes.restype = sz
+    L.a2m_forward.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz, vp]
+    L.a2m_forward.restype = C.c_int
+    L.a2m_forward_host.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+    L.a2m_forward_host.restype = C.c_int
+    L.a2m_last_launch_count.argtypes = [vp]
+    L.a2m_last_launch_count.restype = i32
+    L.a2m_set_use_graph.argtypes = [vp, i32]
+    L.a2m_set_use_graph.restype = C.c_int
+    L.a2m_debug_forward_tap.argtypes = [vp, vp, i32, vp, vp, i32, C.c_char_p, vp, sz, vp]
+    L.a2m_debug_forward_tap.restype = C.c_int
+    L.a2m_debug_gemm.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, u32, vp, vp, vp, vp, vp, vp]
+    L.a2m_debug_gemm.restype = C.c_int
+    L.a2m_stitch_probs.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, f64, f64, vp]
+    L.a2m_stitch_probs.restype = C.c_int64
+    L.a2m_extract_events.argtypes = [vp, C.c_int64, C.c_int64]
+    L.a2m_extract_events.restype = C.POINTER(MidiEventList)
+    L.extract_midi_events.argtypes = [MLMultiArrayWrapper3, f64, f64]
+    L.extract_midi_events.restype = C.POINTER(MidiEventList)
+    L.free_midi_events.argtypes = [C.POINTER(MidiEventList)]
+    L.free_midi_events.restype = None
+    L.a2m_to_frame_events.argtypes = [C.POINTER(MidiEvent), C.c_int64, C.c_int64, vp]
+    L.a2m_to_frame_events.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(handle, rc: int, what: str):
+    if rc != 0:
+        msg = lib().a2m_last_error(handle)
+        raise A2mError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,47 @@
+"""In-tree build of libaudio2midi_b200.so for sm_100a (explicit nvcc, no JIT cache)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libaudio2midi_b200.so")
+SOURCES = ["a2m_api.cu", "modelutil.cpp"]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "cnn_kernels.cuh", "attention.cuh", os.path.join("..", "..", "include", "a2m.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library if missing or older than its sources; returns its path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libaudio2midi_b200.so (there is no fallback path)")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,979 @@
+// C-ABI implementation: handle, weight re-packing, per-batch launch plan, forward orchestration.
+// See include/a2m.h for the contract and the reference interfaces each entry point replaces.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/a2m.h"
+#include "attention.cuh"
+#include "cnn_kernels.cuh"
+#include "gemm_tc.cuh"
+
+using namespace a2m;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ model constants
+constexpr int kStages = 7;
+constexpr int kDims[kStages] = {4, 8, 16, 32, 64, 128, 256};      // model.py:21
+constexpr int kDepths[kStages] = {3, 3, 3, 3, 3, 21, 3};          // model.py:22
+constexpr int kLens[kStages] = {16000, 8000, 4000, 2000, 1000, 500, 250};
+constexpr int kNumTL = 8;       // num_transformer_layers (each = local + global), model.py:25
+constexpr int kD = 256;         // transformer width
+constexpr int kQC = 320;        // q (256) || compressed kv (64)
+constexpr int kKV = 512;        // k (256) || v (256)
+constexpr int kFF = 512;        // FFN intermediate (model.py:732)
+constexpr int kRopeRows = 300;  // internal RoPE table rows (infer.py:38 uses 300)
+constexpr int kTP = ATT_TP;     // padded frames per window
+constexpr int kT = ATT_T;
+
+struct Err {
+  std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      h->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                  \
+      return A2M_ECUDA;                                                                             \
+    }                                                                                               \
+  } while (0)
+
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// Host image of the device weights arena.
+struct Arena {
+  std::vector<uint8_t> bytes;
+  size_t reserve(size_t n) {
+    const size_t off = (bytes.size() + 255) & ~size_t(255);
+    bytes.resize(off + n, 0);
+    return off;
+  }
+  size_t put_f32(const std::vector<float>& v) {
+    const size_t off = reserve(v.size() * 4);
+    std::memcpy(bytes.data() + off, v.data(), v.size() * 4);
+    return off;
+  }
+  size_t put_bf16(const std::vector<float>& v) {
+    const size_t off = reserve(v.size() * 2);
+    uint16_t* d = reinterpret_cast<uint16_t*>(bytes.data() + off);
+    for (size_t i = 0; i < v.size(); ++i) d[i] = f32_to_bf16(v[i]);
+    return off;
+  }
+};
+
+struct BigBlockW {   // Block with C >= 64 (tensor-core path)
+  size_t dwln;       // fp32: dw[7][C] | dwb[C] | lnw[C] | lnb[C]
+  size_t w1, b1;     // bf16 [2C, C], fp32 [2C]
+  size_t w2, b2;     // bf16 [C, 2C], fp32 [C]
+  size_t gamma;      // fp32 [C]
+};
+struct BigDownW {
+  size_t lnw, lnb;   // fp32 [Cin]
+  size_t w, b;       // bf16 [Cout, 2*Cin] (k = tap * Cin + c), fp32 [Cout]
+};
+struct TLayerW {
+  size_t ln1w, ln1b, wqc, wkv, wo, ln2w, ln2b, w1, b1, w2, b2;
+};
+
+struct Weights {
+  StemParams stem;
+  size_t small_block[4][3];
+  size_t small_down[5];           // index = output stage 1..4
+  BigBlockW big_block[kStages][21];
+  BigDownW big_down[kStages];     // stages 5, 6
+  size_t fnw, fnb;
+  TLayerW tl[2 * kNumTL];         // 2*i local, 2*i+1 global
+  size_t dlnw, dlnb, dw, db;      // decoder: bf16 [128, 256] zero padded, fp32 [128]
+};
+
+struct Workspace {
+  uint8_t* base = nullptr;
+  float* X[2];
+  __nv_bfloat16* A16;
+  __nv_bfloat16* H16;
+  float* Xt;
+  __nv_bfloat16* QC16;
+  __nv_bfloat16* KV16;
+  __nv_bfloat16* Vt16;
+  __nv_bfloat16* O16;
+};
+
+size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 1023) & ~size_t(1023);
+    return o;
+  };
+  const size_t b = static_cast<size_t>(B);
+  const size_t x0 = take(b * 64000 * 4), x1 = take(b * 64000 * 4);
+  const size_t a16 = take(b * 65536 * 2), h16 = take(b * 131072 * 2);
+  const size_t xt = take(b * 65536 * 4);
+  const size_t qc = take(b * kTP * kQC * 2), kv = take(b * kTP * kKV * 2);
+  const size_t vt = take(b * 65536 * 2), o16 = take(b * 65536 * 2);
+  if (ws) {
+    ws->base = base;
+    ws->X[0] = reinterpret_cast<float*>(base + x0);
+    ws->X[1] = reinterpret_cast<float*>(base + x1);
+    ws->A16 = reinterpret_cast<__nv_bfloat16*>(base + a16);
+    ws->H16 = reinterpret_cast<__nv_bfloat16*>(base + h16);
+    ws->Xt = reinterpret_cast<float*>(base + xt);
+    ws->QC16 = reinterpret_cast<__nv_bfloat16*>(base + qc);
+    ws->KV16 = reinterpret_cast<__nv_bfloat16*>(base + kv);
+    ws->Vt16 = reinterpret_cast<__nv_bfloat16*>(base + vt);
+    ws->O16 = reinterpret_cast<__nv_bfloat16*>(base + o16);
+  }
+  return off;
+}
+
+struct Step {
+  std::string label;  // non-empty: a tap point reached AFTER this step
+  const float* tap_ptr = nullptr;
+  size_t tap_elems = 0;
+  std::function<cudaError_t(cudaStream_t)> run;
+};
+
+struct Plan {
+  int B = 0;
+  uint8_t* ws_base = nullptr;
+  Workspace ws;
+  std::vector<Step> steps;       // everything between the stem and the decoder GEMM
+  CUtensorMap dec_tmA, dec_tmB;  // decoder GEMM operands
+  int cur_after_stem = 0;
+  cudaGraphExec_t graph = nullptr;
+};
+
+}  // namespace
+
+struct A2mHandle {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  bool loaded = false;
+  Weights w;
+  uint8_t* arena_dev = nullptr;
+  size_t arena_bytes = 0;
+  float* rope_dev = nullptr;  // cos [300,32] then sin [300,32]
+  uint8_t* own_ws = nullptr;
+  size_t own_ws_bytes = 0;
+  std::vector<std::unique_ptr<Plan>> plans;
+  bool use_graph = true;
+  int last_launches = 0;
+  // host staging for a2m_forward_host
+  float* pin_audio = nullptr;
+  float* pin_out = nullptr;
+  float* pin_rope = nullptr;
+  float* dev_audio = nullptr;
+  float* dev_out = nullptr;
+  float* dev_rope_in = nullptr;
+  int staged_B = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+template <class T>
+T* dev_ptr(const A2mHandle* h, size_t off) {
+  return reinterpret_cast<T*>(h->arena_dev + off);
+}
+
+// ------------------------------------------------------------------------------------------ tensor maps
+bool make_tmap(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+               uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u base=%p",
+                  static_cast<int>(r), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+                  static_cast<unsigned long long>(ld_elems), box_cols, box_rows, base);
+    h->err = buf;
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <int BN, int MODE>
+cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int num_sms, cudaStream_t s) {
+  constexpr size_t smem = gemm_smem_bytes<BN>();
+  const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
+  const int per_sm = (smem * 2 + 2048 <= 227 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;
+  const int grid = std::min(tiles, num_sms * per_sm);
+  gemm_tc_kernel<BN, MODE><<<grid, GEMM_THREADS, smem, s>>>(a, b, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(int BN, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int num_sms,
+                        cudaStream_t s) {
+  if (g.N % BN != 0 || g.K % GEMM_BK != 0 || g.M <= 0) return cudaErrorInvalidValue;
+  switch (mode * 1000 + BN) {
+    case GEMM_GENERIC * 1000 + 64: return launch_gemm_t<64, GEMM_GENERIC>(a, b, g, num_sms, s);
+    case GEMM_GENERIC * 1000 + 128: return launch_gemm_t<128, GEMM_GENERIC>(a, b, g, num_sms, s);
+    case GEMM_GENERIC * 1000 + 256: return launch_gemm_t<256, GEMM_GENERIC>(a, b, g, num_sms, s);
+    case GEMM_GLU * 1000 + 256: return launch_gemm_t<256, GEMM_GLU>(a, b, g, num_sms, s);
+    case GEMM_ROPE * 1000 + 64: return launch_gemm_t<64, GEMM_ROPE>(a, b, g, num_sms, s);
+    case GEMM_ROPE * 1000 + 128: return launch_gemm_t<128, GEMM_ROPE>(a, b, g, num_sms, s);
+    case GEMM_DECODER * 1000 + 128: return launch_gemm_t<128, GEMM_DECODER>(a, b, g, num_sms, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <class K>
+cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+
+template <int C>
+size_t small_block_smem() {
+  constexpr int RS = (C == 4) ? 4 : C + 4;
+  return (((SmallBlockLayout<C>::TOTAL + 3) & ~3) + (SB_TOK + 6) * RS) * sizeof(float);
+}
+
+cudaError_t configure_kernels() {
+  cudaError_t e;
+  if ((e = set_smem(gemm_tc_kernel<64, GEMM_GENERIC>, gemm_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<128, GEMM_GENERIC>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<256, GEMM_GENERIC>, gemm_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<256, GEMM_GLU>, gemm_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<64, GEMM_ROPE>, gemm_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<128, GEMM_ROPE>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc_kernel<128, GEMM_DECODER>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
+  if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+template <int C>
+cudaError_t launch_small_block(const float* in, float* out, int L, int M, const float* params, cudaStream_t s) {
+  block_small_kernel<C><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, small_block_smem<C>(), s>>>(in, out, L, M, params);
+  return cudaGetLastError();
+}
+template <int CIN>
+cudaError_t launch_small_down(const float* in, float* out, int M_out, const float* params, cudaStream_t s) {
+  downsample_small_kernel<CIN>
+      <<<(M_out + 127) / 128, 128, SmallDownLayout<CIN>::TOTAL * sizeof(float), s>>>(in, out, M_out, params);
+  return cudaGetLastError();
+}
+template <int C>
+cudaError_t launch_dwln(const float* X, __nv_bfloat16* A, int L, int M, const float* params, cudaStream_t s) {
+  dwconv_ln_kernel<C><<<(M + DW_TOK - 1) / DW_TOK, DW_THREADS, (DW_TOK + 6) * C * sizeof(float), s>>>(X, A, L, M, params);
+  return cudaGetLastError();
+}
+template <int C>
+cudaError_t launch_ln(const float* X, int rows, int Lin, int Lout, const float* w, const float* b,
+                      __nv_bfloat16* o16, float* o32, cudaStream_t s) {
+  ln_rows_kernel<C><<<(rows + 7) / 8, 256, 0, s>>>(X, rows, Lin, Lout, w, b, o16, o32);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct LeafView {
+  const float* p = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto d : shape) n *= static_cast<size_t>(d);
+    return n;
+  }
+};
+using LeafMap = std::map<std::string, LeafView>;
+
+struct PackError {
+  std::string msg;
+};
+
+const LeafView& leaf(const LeafMap& m, const std::string& path, std::initializer_list<int64_t> shape) {
+  auto it = m.find(path);
+  if (it == m.end()) throw PackError{"missing pytree leaf: " + path};
+  std::vector<int64_t> want(shape);
+  if (it->second.shape != want) {
+    std::string got;
+    for (auto d : it->second.shape) got += std::to_string(d) + ",";
+    throw PackError{"leaf " + path + " has shape (" + got + ") which is not the reference shape"};
+  }
+  return it->second;
+}
+
+std::vector<float> vec(const LeafView& l, size_t offset = 0, size_t n = 0) {
+  if (n == 0) n = l.numel() - offset;
+  return std::vector<float>(l.p + offset, l.p + offset + n);
+}
+
+void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
+  // ---- stem (model.py:84-100)
+  {
+    const std::string p = "layers.0.layers.0.";
+    const auto& cw = leaf(m, p + "conv.weight", {4, 2, 5});
+    const auto& cb = leaf(m, p + "conv.bias", {4, 1});
+    const auto& lw = leaf(m, p + "norm.weight", {4});
+    const auto& lb = leaf(m, p + "norm.bias", {4});
+    std::memcpy(w->stem.w, cw.p, sizeof(float) * 40);
+    std::memcpy(w->stem.b, cb.p, sizeof(float) * 4);
+    std::memcpy(w->stem.ln_w, lw.p, sizeof(float) * 4);
+    std::memcpy(w->stem.ln_b, lb.p, sizeof(float) * 4);
+  }
+  for (int s = 0; s < kStages; ++s) {
+    const int C = kDims[s], H = 2 * C;
+    const std::string sp = "layers." + std::to_string(s) + ".layers.";
+    // ---- downsample (model.py:102-118)
+    if (s >= 1) {
+      const int Cin = kDims[s - 1];
+      const auto& cw = leaf(m, sp + "0.conv.weight", {C, Cin, 2});
+      const auto& cb = leaf(m, sp + "0.conv.bias", {C, 1});
+      const auto& lw = leaf(m, sp + "0.norm.weight", {Cin});
+      const auto& lb = leaf(m, sp + "0.norm.bias", {Cin});
+      std::vector<float> wk(static_cast<size_t>(C) * 2 * Cin);  // [Cout][tap * Cin + c]
+      for (int o = 0; o < C; ++o)
+        for (int c = 0; c < Cin; ++c)
+          for (int t = 0; t < 2; ++t) wk[(static_cast<size_t>(o) * 2 + t) * Cin + c] = cw.p[(static_cast<size_t>(o) * Cin + c) * 2 + t];
+      if (s <= 4) {
+        std::vector<float> img;
+        auto a = vec(lw), b = vec(lb), bb = vec(cb);
+        img.insert(img.end(), a.begin(), a.end());
+        img.insert(img.end(), b.begin(), b.end());
+        img.insert(img.end(), wk.begin(), wk.end());
+        img.insert(img.end(), bb.begin(), bb.end());
+        w->small_down[s] = ar->put_f32(img);
+      } else {
+        w->big_down[s].lnw = ar->put_f32(vec(lw));
+        w->big_down[s].lnb = ar->put_f32(vec(lb));
+        w->big_down[s].w = ar->put_bf16(wk);
+        w->big_down[s].b = ar->put_f32(vec(cb));
+      }
+    }
+    // ---- blocks (model.py:120-167)
+    for (int j = 0; j < kDepths[s]; ++j) {
+      const std::string bp = sp + std::to_string(j + 1) + ".";
+      const auto& dw = leaf(m, bp + "depth_conv.weight", {C, 1, 7});
+      const auto& dwb = leaf(m, bp + "depth_conv.bias", {C, 1});
+      const auto& w1 = leaf(m, bp + "point_conv_1.weight", {H, C, 1});
+      const auto& b1 = leaf(m, bp + "point_conv_1.bias", {H, 1});
+      const auto& w2 = leaf(m, bp + "point_conv_2.weight", {C, H, 1});
+      const auto& b2 = leaf(m, bp + "point_conv_2.bias", {C, 1});
+      const auto& lw = leaf(m, bp + "norm.weight", {C});
+      const auto& lb = leaf(m, bp + "norm.bias", {C});
+      const auto& gm = leaf(m, bp + "gamma", {C});
+      std::vector<float> dwt(static_cast<size_t>(7) * C);  // [tap][C]
+      for (int c = 0; c < C; ++c)
+        for (int t = 0; t < 7; ++t) dwt[static_cast<size_t>(t) * C + c] = dw.p[c * 7 + t];
+      if (s <= 3) {
+        std::vector<float> img;
+        auto app = [&](const std::vector<float>& v) { img.insert(img.end(), v.begin(), v.end()); };
+        app(dwt); app(vec(dwb)); app(vec(lw)); app(vec(lb)); app(vec(w1)); app(vec(b1));
+        std::vector<float> w2t(static_cast<size_t>(H) * C);  // [H][C] = point_conv_2 transposed
+        for (int c = 0; c < C; ++c)
+          for (int hh = 0; hh < H; ++hh) w2t[static_cast<size_t>(hh) * C + c] = w2.p[static_cast<size_t>(c) * H + hh];
+        app(w2t); app(vec(b2)); app(vec(gm));
+        w->small_block[s][j] = ar->put_f32(img);
+      } else {
+        BigBlockW& bw = w->big_block[s][j];
+        std::vector<float> img;
+        auto app = [&](const std::vector<float>& v) { img.insert(img.end(), v.begin(), v.end()); };
+        app(dwt); app(vec(dwb)); app(vec(lw)); app(vec(lb));
+        bw.dwln = ar->put_f32(img);
+        bw.w1 = ar->put_bf16(vec(w1));
+        bw.b1 = ar->put_f32(vec(b1));
+        bw.w2 = ar->put_bf16(vec(w2));
+        bw.b2 = ar->put_f32(vec(b2));
+        bw.gamma = ar->put_f32(vec(gm));
+      }
+    }
+  }
+  w->fnw = ar->put_f32(vec(leaf(m, "norm.weight", {kD})));
+  w->fnb = ar->put_f32(vec(leaf(m, "norm.bias", {kD})));
+
+  // ---- transformer (model.py:474-670); leaves stacked on a leading axis of 8
+  for (int i = 0; i < kNumTL; ++i) {
+    for (int g = 0; g < 2; ++g) {
+      const std::string lp = std::string("transformer.layers.") + (g == 0 ? "local_attention." : "global_attention.");
+      const std::string ap = lp + (g == 0 ? "attention_block.self_attention." : "attention_block.");
+      TLayerW& t = w->tl[2 * i + g];
+      const size_t li = static_cast<size_t>(i);
+      const auto& n1w = leaf(m, lp + "attention_norm.weight", {kNumTL, kD});
+      const auto& n1b = leaf(m, lp + "attention_norm.bias", {kNumTL, kD});
+      const auto& n2w = leaf(m, lp + "feed_forward_norm.weight", {kNumTL, kD});
+      const auto& n2b = leaf(m, lp + "feed_forward_norm.bias", {kNumTL, kD});
+      const auto& wq = leaf(m, ap + "query_up_proj.weight", {kNumTL, 256, kD});
+      const auto& wc = leaf(m, ap + "kv_down_proj.weight", {kNumTL, 64, kD});
+      const auto& wk = leaf(m, ap + "key_up_proj.weight", {kNumTL, 256, 64});
+      const auto& wv = leaf(m, ap + "value_up_proj.weight", {kNumTL, 256, 64});
+      const auto& wo = leaf(m, ap + "output_proj.weight", {kNumTL, kD, 256});
+      const auto& f1w = leaf(m, lp + "feed_forward_block.attention_to_intermediate_proj.weight", {kNumTL, 2 * kFF, kD});
+      const auto& f1b = leaf(m, lp + "feed_forward_block.attention_to_intermediate_proj.bias", {kNumTL, 2 * kFF});
+      const auto& f2w = leaf(m, lp + "feed_forward_block.intermediate_to_attention_proj.weight", {kNumTL, kD, kFF});
+      const auto& f2b = leaf(m, lp + "feed_forward_block.intermediate_to_attention_proj.bias", {kNumTL, kD});
+      t.ln1w = ar->put_f32(vec(n1w, li * kD, kD));
+      t.ln1b = ar->put_f32(vec(n1b, li * kD, kD));
+      t.ln2w = ar->put_f32(vec(n2w, li * kD, kD));
+      t.ln2b = ar->put_f32(vec(n2b, li * kD, kD));
+      std::vector<float> qc = vec(wq, li * 256 * kD, 256 * kD);
+      auto c = vec(wc, li * 64 * kD, 64 * kD);
+      qc.insert(qc.end(), c.begin(), c.end());
+      t.wqc = ar->put_bf16(qc);  // [320, 256]
+      std::vector<float> kv = vec(wk, li * 256 * 64, 256 * 64);
+      auto v = vec(wv, li * 256 * 64, 256 * 64);
+      kv.insert(kv.end(), v.begin(), v.end());
+      t.wkv = ar->put_bf16(kv);  // [512, 64]
+      t.wo = ar->put_bf16(vec(wo, li * kD * 256, kD * 256));
+      // FFN-1 rows re-ordered so each 256-row tile holds 128 "gelu" rows followed by their 128 "gate" rows
+      // (model.py:233-234: x1, x2 = split(x, 2); h = gelu(x1) * x2)
+      std::vector<float> w1p(static_cast<size_t>(2 * kFF) * kD), b1p(2 * kFF);
+      for (int tb = 0; tb < 2 * kFF / 256; ++tb)
+        for (int r = 0; r < 256; ++r) {
+          const int src = (r < 128) ? tb * 128 + r : kFF + tb * 128 + (r - 128);
+          std::memcpy(&w1p[(static_cast<size_t>(tb) * 256 + r) * kD], f1w.p + (li * 2 * kFF + src) * kD, sizeof(float) * kD);
+          b1p[tb * 256 + r] = f1b.p[li * 2 * kFF + src];
+        }
+      t.w1 = ar->put_bf16(w1p);
+      t.b1 = ar->put_f32(b1p);
+      t.w2 = ar->put_bf16(vec(f2w, li * kD * kFF, kD * kFF));
+      t.b2 = ar->put_f32(vec(f2b, li * kD, kD));
+    }
+  }
+  // ---- decoder (model.py:169-198): N = 90 padded to 128 with zero rows
+  {
+    const auto& dwt = leaf(m, "decoder.decoder_pooling.weight", {A2M_VOCAB, kD});
+    const auto& dbs = leaf(m, "decoder.decoder_pooling.bias", {A2M_VOCAB});
+    std::vector<float> wp(static_cast<size_t>(128) * kD, 0.f), bp(128, 0.f);
+    std::memcpy(wp.data(), dwt.p, sizeof(float) * A2M_VOCAB * kD);
+    std::memcpy(bp.data(), dbs.p, sizeof(float) * A2M_VOCAB);
+    w->dw = ar->put_bf16(wp);
+    w->db = ar->put_f32(bp);
+    w->dlnw = ar->put_f32(vec(leaf(m, "decoder.norm.weight", {kD})));
+    w->dlnb = ar->put_f32(vec(leaf(m, "decoder.norm.bias", {kD})));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ plan
+GemmArgs gemm_args(int M, int N, int K) {
+  GemmArgs g;
+  std::memset(&g, 0, sizeof g);
+  g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+// Adds one tcgen05 GEMM step.  A: [M, K] bf16 with row stride lda; W: [N, K] bf16 in the arena.
+bool add_gemm(A2mHandle* h, Plan* p, int BN, int mode, const __nv_bfloat16* A, int lda, size_t w_off, GemmArgs g,
+              const std::string& label = "", const float* tap = nullptr, size_t tap_elems = 0) {
+  CUtensorMap ta, tb;
+  if (!make_tmap(h, &ta, A, g.M, g.K, lda, GEMM_BK, GEMM_BM)) return false;
+  if (!make_tmap(h, &tb, dev_ptr<__nv_bfloat16>(h, w_off), g.N, g.K, g.K, GEMM_BK, BN)) return false;
+  const int sms = h->num_sms;
+  Step st;
+  st.label = label; st.tap_ptr = tap; st.tap_elems = tap_elems;
+  st.run = [=](cudaStream_t s) { return launch_gemm(BN, mode, ta, tb, g, sms, s); };
+  p->steps.push_back(std::move(st));
+  return true;
+}
+
+void add_step(Plan* p, std::function<cudaError_t(cudaStream_t)> fn, const std::string& label = "",
+              const float* tap = nullptr, size_t tap_elems = 0) {
+  Step st;
+  st.label = label; st.tap_ptr = tap; st.tap_elems = tap_elems;
+  st.run = std::move(fn);
+  p->steps.push_back(std::move(st));
+}
+
+bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
+  p->B = B;
+  p->ws_base = ws_base;
+  ws_carve(B, ws_base, &p->ws);
+  Workspace& ws = p->ws;
+  const Weights& w = h->w;
+  int cur = 0;  // stem writes X[0]
+  p->cur_after_stem = 0;
+
+  for (int s = 0; s < kStages; ++s) {
+    const int C = kDims[s], L = kLens[s], M = B * L;
+    if (s >= 1) {
+      const float* in = ws.X[cur];
+      float* out = ws.X[cur ^ 1];
+      if (s <= 4) {
+        const float* prm = dev_ptr<float>(h, w.small_down[s]);
+        switch (s) {
+          case 1: add_step(p, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); }); break;
+          case 2: add_step(p, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); }); break;
+          case 3: add_step(p, [=](cudaStream_t st) { return launch_small_down<16>(in, out, M, prm, st); }); break;
+          default: add_step(p, [=](cudaStream_t st) { return launch_small_down<32>(in, out, M, prm, st); }); break;
+        }
+      } else {
+        // LN over the input channels -> bf16 [2M, Cin] == [M, 2*Cin]; conv k2 s2 == GEMM with K = 2*Cin
+        const int Cin = kDims[s - 1], Min = 2 * M;
+        const float* lw = dev_ptr<float>(h, w.big_down[s].lnw);
+        const float* lb = dev_ptr<float>(h, w.big_down[s].lnb);
+        __nv_bfloat16* a16 = ws.A16;
+        if (Cin == 64) add_step(p, [=](cudaStream_t st) { return launch_ln<64>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
+        else add_step(p, [=](cudaStream_t st) { return launch_ln<128>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
+        GemmArgs g = gemm_args(M, C, 2 * Cin);
+        g.flags = GF_BIAS | GF_OUT32;
+        g.bias = dev_ptr<float>(h, w.big_down[s].b);
+        g.out32 = out; g.ld32 = C;
+        if (!add_gemm(h, p, 128, GEMM_GENERIC, a16, 2 * Cin, w.big_down[s].w, g)) return false;
+      }
+      cur ^= 1;
+    }
+    for (int j = 0; j < kDepths[s]; ++j) {
+      const bool last = (j == kDepths[s] - 1);
+      const std::string label = last ? "stage" + std::to_string(s) : "";
+      if (s <= 3) {
+        const float* in = ws.X[cur];
+        float* out = ws.X[cur ^ 1];
+        const float* prm = dev_ptr<float>(h, w.small_block[s][j]);
+        const size_t te = static_cast<size_t>(M) * C;
+        switch (s) {
+          case 0: add_step(p, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te); break;
+          case 1: add_step(p, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te); break;
+          case 2: add_step(p, [=](cudaStream_t st) { return launch_small_block<16>(in, out, L, M, prm, st); }, label, out, te); break;
+          default: add_step(p, [=](cudaStream_t st) { return launch_small_block<32>(in, out, L, M, prm, st); }, label, out, te); break;
+        }
+        cur ^= 1;
+      } else {
+        const BigBlockW& bw = w.big_block[s][j];
+        float* X = ws.X[cur];
+        __nv_bfloat16* a16 = ws.A16;
+        __nv_bfloat16* h16 = ws.H16;
+        const float* prm = dev_ptr<float>(h, bw.dwln);
+        if (C == 64) add_step(p, [=](cudaStream_t st) { return launch_dwln<64>(X, a16, L, M, prm, st); });
+        else if (C == 128) add_step(p, [=](cudaStream_t st) { return launch_dwln<128>(X, a16, L, M, prm, st); });
+        else add_step(p, [=](cudaStream_t st) { return launch_dwln<256>(X, a16, L, M, prm, st); });
+        GemmArgs g1 = gemm_args(M, 2 * C, C);
+        g1.flags = GF_BIAS | GF_GELU | GF_OUT16;
+        g1.bias = dev_ptr<float>(h, bw.b1);
+        g1.out16 = h16; g1.ld16 = 2 * C;
+        if (!add_gemm(h, p, (2 * C >= 256) ? 256 : 128, GEMM_GENERIC, a16, C, bw.w1, g1)) return false;
+        GemmArgs g2 = gemm_args(M, C, 2 * C);
+        g2.flags = GF_BIAS | GF_GAMMA | GF_RESID | GF_OUT32;
+        g2.bias = dev_ptr<float>(h, bw.b2);
+        g2.gamma = dev_ptr<float>(h, bw.gamma);
+        g2.resid = X; g2.ldr = C;
+        g2.out32 = X; g2.ld32 = C;
+        if (!add_gemm(h, p, (C >= 128) ? 128 : 64, GEMM_GENERIC, h16, 2 * C, bw.w2, g2, label, X, static_cast<size_t>(M) * C)) return false;
+      }
+    }
+  }
+  // ---- final CNN norm (model.py:759) + transpose (free in token-major layout) into the padded layout
+  const int Mt = B * kTP;
+  {
+    const float* in = ws.X[cur];
+    float* xt = ws.Xt;
+    const float* lw = dev_ptr<float>(h, w.fnw);
+    const float* lb = dev_ptr<float>(h, w.fnb);
+    const int rows = B * kT;
+    add_step(p, [=](cudaStream_t st) { return launch_ln<256>(in, rows, kT, kTP, lw, lb, nullptr, xt, st); }, "cnn_out", xt,
+             static_cast<size_t>(Mt) * kD);
+  }
+  // ---- transformer stack (model.py:649-670): per scan step a local then a global TransformerLayer
+  const float* rope_cos = h->rope_dev;
+  const float* rope_sin = h->rope_dev + kRopeRows * A2M_ROPE_DIM;
+  for (int i = 0; i < 2 * kNumTL; ++i) {
+    const bool local = (i % 2 == 0);
+    const TLayerW& t = w.tl[i];
+    float* xt = ws.Xt;
+    __nv_bfloat16 *a16 = ws.A16, *qc = ws.QC16, *kv = ws.KV16, *vt = ws.Vt16, *o16 = ws.O16, *h16 = ws.H16;
+    {
+      const float* lw = dev_ptr<float>(h, t.ln1w);
+      const float* lb = dev_ptr<float>(h, t.ln1b);
+      add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+    }
+    if (local) {
+      GemmArgs g = gemm_args(Mt, kQC, kD);
+      g.flags = GF_OUT16; g.out16 = qc; g.ld16 = kQC;
+      if (!add_gemm(h, p, 64, GEMM_GENERIC, a16, kD, t.wqc, g)) return false;
+      GemmArgs g2 = gemm_args(Mt, kKV, 64);
+      g2.flags = GF_OUT16; g2.out16 = kv; g2.ld16 = kKV;
+      if (!add_gemm(h, p, 128, GEMM_GENERIC, qc + 256, kQC, t.wkv, g2)) return false;
+      const int total_warps = B * ATT_HEADS * 32;
+      add_step(p, [=](cudaStream_t st) {
+        attn_local_kernel<<<(total_warps + AL_WARPS - 1) / AL_WARPS, AL_WARPS * 32, 0, st>>>(
+            qc, kQC, kv, kv + 256, kKV, o16, kD, rope_cos, rope_sin, total_warps);
+        return cudaGetLastError();
+      });
+    } else {
+      GemmArgs g = gemm_args(Mt, kQC, kD);
+      g.out16 = qc; g.ld16 = kQC;
+      g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.rope_cols = 256; g.rows_per_window = kTP;
+      g.vt_out = nullptr; g.vt_col0 = 1 << 30;
+      if (!add_gemm(h, p, 64, GEMM_ROPE, a16, kD, t.wqc, g)) return false;
+      GemmArgs g2 = gemm_args(Mt, kKV, 64);
+      g2.out16 = kv; g2.ld16 = kKV;
+      g2.rope_cos = rope_cos; g2.rope_sin = rope_sin; g2.rope_cols = 256; g2.rows_per_window = kTP;
+      g2.vt_out = vt; g2.vt_col0 = 256;
+      if (!add_gemm(h, p, 128, GEMM_ROPE, qc + 256, kQC, t.wkv, g2)) return false;
+      CUtensorMap tq, tk, tv;
+      if (!make_tmap(h, &tq, qc, Mt, 256, kQC, 64, 128)) return false;
+      if (!make_tmap(h, &tk, kv, Mt, 256, kKV, 64, 256)) return false;
+      if (!make_tmap(h, &tv, vt, static_cast<uint64_t>(B) * ATT_HEADS * ATT_HD, kTP, kTP, 64, 64)) return false;
+      add_step(p, [=](cudaStream_t st) {
+        attn_global_kernel<<<dim3(2, ATT_HEADS, B), AG_THREADS, AG_SMEM, st>>>(tq, tk, tv, o16, kD);
+        return cudaGetLastError();
+      });
+    }
+    {
+      GemmArgs g = gemm_args(Mt, kD, 256);
+      g.flags = GF_RESID | GF_OUT32;
+      g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
+      if (!add_gemm(h, p, 128, GEMM_GENERIC, o16, kD, t.wo, g)) return false;
+    }
+    {
+      const float* lw = dev_ptr<float>(h, t.ln2w);
+      const float* lb = dev_ptr<float>(h, t.ln2b);
+      add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+    }
+    {
+      GemmArgs g = gemm_args(Mt, 2 * kFF, kD);
+      g.bias = dev_ptr<float>(h, t.b1);
+      g.out16 = h16; g.ld16 = kFF;
+      if (!add_gemm(h, p, 256, GEMM_GLU, a16, kD, t.w1, g)) return false;
+    }
+    {
+      GemmArgs g = gemm_args(Mt, kD, kFF);
+      g.flags = GF_BIAS | GF_RESID | GF_OUT32;
+      g.bias = dev_ptr<float>(h, t.b2);
+      g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
+      const std::string label = "tl" + std::to_string(i / 2) + (local ? "_local" : "_global");
+      if (!add_gemm(h, p, 128, GEMM_GENERIC, h16, kFF, t.w2, g, label, xt, static_cast<size_t>(Mt) * kD)) return false;
+    }
+  }
+  // ---- decoder norm (model.py:190); the decoder GEMM itself is launched per call (user output pointers)
+  {
+    float* xt = ws.Xt;
+    __nv_bfloat16* a16 = ws.A16;
+    const float* lw = dev_ptr<float>(h, w.dlnw);
+    const float* lb = dev_ptr<float>(h, w.dlnb);
+    add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+  }
+  if (!make_tmap(h, &p->dec_tmA, ws.A16, Mt, kD, kD, GEMM_BK, GEMM_BM)) return false;
+  if (!make_tmap(h, &p->dec_tmB, dev_ptr<__nv_bfloat16>(h, w.dw), 128, kD, kD, GEMM_BK, 128)) return false;
+  return true;
+}
+
+Plan* get_plan(A2mHandle* h, int B, uint8_t* ws_base) {
+  for (auto& p : h->plans)
+    if (p->B == B && p->ws_base == ws_base) return p.get();
+  auto p = std::make_unique<Plan>();
+  if (!build_plan(h, p.get(), B, ws_base)) return nullptr;
+  if (h->plans.size() >= 8) {
+    if (h->plans.front()->graph) cudaGraphExecDestroy(h->plans.front()->graph);
+    h->plans.erase(h->plans.begin());
+  }
+  h->plans.push_back(std::move(p));
+  return h->plans.back().get();
+}
+
+int ensure_own_ws(A2mHandle* h, int B) {
+  const size_t need = ws_carve(B, nullptr, nullptr);
+  if (h->own_ws_bytes >= need) return A2M_OK;
+  // plans built on the old buffer are stale
+  for (auto& p : h->plans)
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+  h->plans.clear();
+  if (h->own_ws) cudaFree(h->own_ws);
+  h->own_ws = nullptr;
+  h->own_ws_bytes = 0;
+  CUDA_TRY(cudaMalloc(&h->own_ws, need));
+  CUDA_TRY(cudaMemset(h->own_ws, 0, need));
+  h->own_ws_bytes = need;
+  return A2M_OK;
+}
+
+int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, const float* sin_in, int max_pos,
+                float* logits, float* probs, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                const char* tap_label, float* tap_out, size_t tap_elems) {
+  if (!h->loaded) { h->err = "a2m_forward before a2m_load_weights"; return A2M_ESTATE; }
+  if (B <= 0 || !audio || !cos_in || !sin_in) { h->err = "bad forward arguments"; return A2M_EINVAL; }
+  if (max_pos < kT) { h->err = "rope table needs at least 250 positions"; return A2M_EINVAL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  uint8_t* ws_base;
+  if (workspace) {
+    if (ws_bytes < ws_carve(B, nullptr, nullptr) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
+      h->err = "workspace too small or not 1024-byte aligned";
+      return A2M_EINVAL;
+    }
+    ws_base = static_cast<uint8_t*>(workspace);
+  } else {
+    int rc = ensure_own_ws(h, B);
+    if (rc) return rc;
+    ws_base = h->own_ws;
+  }
+  Plan* p = get_plan(h, B, ws_base);
+  if (!p) return A2M_ECUDA;
+
+  int launches = 0;
+  // RoPE table is an input of the call (rope.py:5-22): copy the rows the model can address
+  const int rows = std::min(max_pos, kRopeRows);
+  CUDA_TRY(cudaMemcpyAsync(h->rope_dev, cos_in, sizeof(float) * rows * A2M_ROPE_DIM, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(h->rope_dev + kRopeRows * A2M_ROPE_DIM, sin_in, sizeof(float) * rows * A2M_ROPE_DIM,
+                           cudaMemcpyDeviceToDevice, stream));
+  {
+    const int total = B * kLens[0];
+    stem_kernel<<<(total + 255) / 256, 256, 0, stream>>>(audio, p->ws.X[0], A2M_WINDOW_SAMPLES, kLens[0], total, h->w.stem);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  if (tap_label) {
+    bool found = false;
+    for (auto& st : p->steps) {
+      CUDA_TRY(st.run(stream));
+      if (st.label == tap_label) {
+        if (tap_elems != st.tap_elems) { h->err = "tap size mismatch for " + st.label; return A2M_EINVAL; }
+        CUDA_TRY(cudaMemcpyAsync(tap_out, st.tap_ptr, sizeof(float) * tap_elems, cudaMemcpyDeviceToDevice, stream));
+        found = true;
+        break;
+      }
+    }
+    if (!found) { h->err = std::string("unknown tap label ") + tap_label; return A2M_EINVAL; }
+    return A2M_OK;
+  }
+  if (h->use_graph) {
+    if (!p->graph) {
+      cudaStream_t cs;
+      CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        for (auto& st : p->steps) {
+          e = st.run(cs);
+          if (e != cudaSuccess) break;
+        }
+        cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
+        if (e == cudaSuccess) e = e2;
+      }
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&p->graph, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+      if (e != cudaSuccess) {
+        p->graph = nullptr;
+        h->err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(e);
+        return A2M_ECUDA;
+      }
+    }
+    CUDA_TRY(cudaGraphLaunch(p->graph, stream));
+  } else {
+    for (auto& st : p->steps) CUDA_TRY(st.run(stream));
+  }
+  launches += static_cast<int>(p->steps.size());
+  {
+    GemmArgs g = gemm_args(B * kTP, 128, kD);
+    g.bias = dev_ptr<float>(h, h->w.db);
+    g.rows_per_window = kTP; g.valid_rows = kT; g.valid_cols = A2M_VOCAB;
+    g.logits = logits; g.probs = probs;
+    CUDA_TRY(launch_gemm(128, GEMM_DECODER, p->dec_tmA, p->dec_tmB, g, h->num_sms, stream));
+    ++launches;
+  }
+  h->last_launches = launches;
+  return A2M_OK;
+}
+
+}  // namespace
+
+// ============================================================================================= C ABI
+extern "C" {
+
+int a2m_create(int device, A2mHandle** out) {
+  if (!out) return A2M_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return A2M_ENODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return A2M_ECUDA;
+  if (prop.major != 10) return A2M_ENODEVICE;  // tcgen05 / TMEM kernels: sm_100 family only, no fallback
+  auto* h = new A2mHandle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return A2M_ECUDA; }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    h->err = "cuTensorMapEncodeTiled not available from the driver";
+    return A2M_ECUDA;
+  }
+  h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  CUDA_TRY(configure_kernels());
+  CUDA_TRY(cudaMalloc(&h->rope_dev, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
+  CUDA_TRY(cudaMemset(h->rope_dev, 0, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  return A2M_OK;
+}
+
+void a2m_destroy(A2mHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& p : h->plans)
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+  if (h->arena_dev) cudaFree(h->arena_dev);
+  if (h->rope_dev) cudaFree(h->rope_dev);
+  if (h->own_ws) cudaFree(h->own_ws);
+  if (h->pin_audio) cudaFreeHost(h->pin_audio);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->pin_rope) cudaFreeHost(h->pin_rope);
+  if (h->dev_audio) cudaFree(h->dev_audio);
+  if (h->dev_out) cudaFree(h->dev_out);
+  if (h->dev_rope_in) cudaFree(h->dev_rope_in);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+const char* a2m_last_error(const A2mHandle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int a2m_load_weights(A2mHandle* h, const void* blob, size_t blob_bytes, const A2mLeafDesc* table, int32_t n) {
+  if (!h) return A2M_EINVAL;
+  if (!blob || !table || n <= 0) { h->err = "bad load_weights arguments"; return A2M_EINVAL; }
+  LeafMap m;
+  for (int i = 0; i < n; ++i) {
+    LeafView v;
+    if (!table[i].path || table[i].ndim < 0 || table[i].ndim > 4) { h->err = "bad leaf descriptor"; return A2M_EINVAL; }
+    v.shape.assign(table[i].shape, table[i].shape + table[i].ndim);
+    if (table[i].offset_bytes % 4 != 0 || table[i].offset_bytes + v.numel() * 4 > blob_bytes) {
+      h->err = std::string("leaf outside blob: ") + table[i].path;
+      return A2M_EINVAL;
+    }
+    v.p = reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob) + table[i].offset_bytes);
+    m[table[i].path] = v;
+  }
+  Arena ar;
+  try {
+    pack_weights(m, &h->w, &ar);
+  } catch (const PackError& e) {
+    h->err = e.msg;
+    return A2M_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (h->arena_bytes != ar.bytes.size()) {
+    for (auto& p : h->plans)
+      if (p->graph) cudaGraphExecDestroy(p->graph);
+    h->plans.clear();  // tensor maps point into the old arena
+    if (h->arena_dev) cudaFree(h->arena_dev);
+    h->arena_dev = nullptr;
+    CUDA_TRY(cudaMalloc(&h->arena_dev, ar.bytes.size()));
+    h->arena_bytes = ar.bytes.size();
+  }
+  CUDA_TRY(cudaMemcpy(h->arena_dev, ar.bytes.data(), ar.bytes.size(), cudaMemcpyHostToDevice));
+  h->loaded = true;
+  return A2M_OK;
+}
+
+size_t a2m_workspace_bytes(const A2mHandle*, int32_t batch, int32_t) {
+  return batch > 0 ? ws_carve(batch, nullptr, nullptr) : 0;
+}
+
+int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev, const float* rope_sin_dev,
+                int32_t rope_max_pos, float* logits_dev, float* probs_dev, void* workspace_dev, size_t workspace_bytes,
+                void* stream) {
+  if (!h) return A2M_EINVAL;
+  if (!logits_dev || !probs_dev) { h->err = "null output"; return A2M_EINVAL; }
+  return run_forward(h, audio_dev, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, logits_dev, probs_dev, workspace_dev,
+                     workspace_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0);
+}
+
+int a2m_debug_forward_tap(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
+                          const float* rope_sin_dev, int32_t rope_max_pos, const char* label, float* out_dev,
+                          size_t out_elems, void* stream) {
+  if (!h) return A2M_EINVAL;
+  if (!label || !out_dev) { h->err = "null tap argument"; return A2M_EINVAL; }
+  return run_forward(h, audio_dev, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, nullptr, nullptr, nullptr, 0,
+                     static_cast<cudaStream_t>(stream), label, out_dev, out_elems);
+}
+
+int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                     const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
+  if (!h) return A2M_EINVAL;
+  if (batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !logits_host || !probs_host || rope_max_pos < kT) {
+    h->err = "bad forward_host arguments";
+    return A2M_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t a_elems = static_cast<size_t>(batch) * 2 * A2M_WINDOW_SAMPLES;
+  const size_t o_elems = static_cast<size_t>(batch) * A2M_FRAMES * A2M_VOCAB;
+  const int rows = std::min(rope_max_pos, kRopeRows);
+  const size_t r_elems = static_cast<size_t>(rows) * A2M_ROPE_DIM;
+  if (h->staged_B < batch) {
+    if (h->pin_audio) cudaFreeHost(h->pin_audio);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->dev_audio) cudaFree(h->dev_audio);
+    if (h->dev_out) cudaFree(h->dev_out);
+    h->pin_audio = h->pin_out = h->dev_audio = h->dev_out = nullptr;
+    h->staged_B = 0;
+    CUDA_TRY(cudaMallocHost(&h->pin_audio, a_elems * 4));
+    CUDA_TRY(cudaMallocHost(&h->pin_out, 2 * o_elems * 4));
+    CUDA_TRY(cudaMalloc(&h->dev_audio, a_elems * 4));
+    CUDA_TRY(cudaMalloc(&h->dev_out, 2 * o_elems * 4));
+    h->staged_B = batch;
+  }
+  if (!h->pin_rope) {
+    CUDA_TRY(cudaMallocHost(&h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4));
+    CUDA_TRY(cudaMalloc(&h->dev_rope_in, 2 * kRopeRows * A2M_ROPE_DIM * 4));
+  }
+  cudaStream_t s = h->own_stream;
+  std::memcpy(h->pin_audio, audio_host, a_elems * 4);
+  std::memcpy(h->pin_rope, rope_cos_host, r_elems * 4);
+  std::memcpy(h->pin_rope + kRopeRows * A2M_ROPE_DIM, rope_sin_host, r_elems * 4);
+  CUDA_TRY(cudaMemcpyAsync(h->dev_audio, h->pin_audio, a_elems * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice, s));
+  int rc = run_forward(h, h->dev_audio, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, h->dev_out,
+                       h->dev_out + o_elems, nullptr, 0, s, nullptr, nullptr, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->pin_out, h->dev_out, 2 * o_elems * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  std::memcpy(logits_host, h->pin_out, o_elems * 4);
+  std::memcpy(probs_host, h->pin_out + o_elems, o_elems * 4);
+  return A2M_OK;
+}
+
+int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }
+
+int a2m_set_use_graph(A2mHandle* h, int32_t enable) {
+  if (!h) return A2M_EINVAL;
+  h->use_graph = enable != 0;
+  return A2M_OK;
+}
+
+int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t K, const void* A, int32_t lda,
+                   const void* W, uint32_t flags, const float* bias, const float* gamma, const float* resid, float* out32,
+                   void* out16, void* stream) {
+  if (!h) return A2M_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUtensorMap ta, tb;
+  if (!make_tmap(h, &ta, A, M, K, lda, GEMM_BK, GEMM_BM)) return A2M_ECUDA;
+  if (!make_tmap(h, &tb, W, N, K, K, GEMM_BK, block_n)) return A2M_ECUDA;
+  GemmArgs g = gemm_args(M, N, K);
+  g.flags = flags;
+  g.bias = bias; g.gamma = gamma;
+  g.resid = resid; g.ldr = N;
+  g.out32 = out32; g.ld32 = N;
+  g.out16 = static_cast<__nv_bfloat16*>(out16); g.ld16 = N;
+  CUDA_TRY(launch_gemm(block_n, GEMM_GENERIC, ta, tb, g, h->num_sms, static_cast<cudaStream_t>(stream)));
+  return A2M_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,407 @@
+// CUDA-core kernels of the ConvNeXt-style frontend (model.py:84-167, 756-759).
+//
+// Internal activation layout is TOKEN-MAJOR: X[b * L + l][c] fp32 (the reference's (C, L) transposed),
+// so LayerNorm over channels is a contiguous row reduction and every 1x1 conv is a plain GEMM.
+// C * L = 64 000 elements per window at every stage.
+//
+//   stem_kernel              Stem: conv k5 s5 (2->4) + LN(4)                       model.py:98-100
+//   block_small_kernel<C>    whole Block for C in {4, 8, 16, 32} on CUDA cores      model.py:160-167
+//   downsample_small_kernel  LN(Cin) + conv k2 s2 for Cin in {4, 8, 16, 32}         model.py:116-118
+//   dwconv_ln_kernel<C>      depthwise k7 + LN -> bf16 GEMM operand, C in {64,128,256}  model.py:161-162
+//   ln_rows_kernel<C>        LN over a row -> bf16 and/or fp32 (Downsample norm for Cin >= 64,
+//                            final norm model.py:759, transformer/decoder norms model.py:190,539,546)
+// All are HBM/L2-bound glue: coalesced 128-bit accesses, warp-shuffle reductions, no atomics.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace a2m {
+
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float gelu_tanh_cc(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ Stem
+struct StemParams {
+  float w[4][2][5];  // conv weight (out, in, k)
+  float b[4];
+  float ln_w[4], ln_b[4];
+};
+
+// audio [B, 2, n_samples] fp32 -> X [B * L0, 4] fp32, L0 = n_samples / 5.  One thread per output token.
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ audio, float* __restrict__ out,
+                                                   int n_samples, int L0, int total_tokens, const StemParams p) {
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= total_tokens) return;
+  const int b = tok / L0, l = tok - b * L0;
+  const float* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
+  const float* a1 = a0 + n_samples;
+  float x[2][5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    x[0][k] = __ldg(a0 + k);
+    x[1][k] = __ldg(a1 + k);
+  }
+  float y[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float acc = p.b[o];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc = fmaf(p.w[o][c][k], x[c][k], acc);
+    y[o] = acc;
+  }
+  const float mean = 0.25f * (y[0] + y[1] + y[2] + y[3]);
+  float var = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) var += (y[o] - mean) * (y[o] - mean);
+  const float inv = rsqrtf(0.25f * var + kLnEps);
+  float4 r;
+  r.x = (y[0] - mean) * inv * p.ln_w[0] + p.ln_b[0];
+  r.y = (y[1] - mean) * inv * p.ln_w[1] + p.ln_b[1];
+  r.z = (y[2] - mean) * inv * p.ln_w[2] + p.ln_b[2];
+  r.w = (y[3] - mean) * inv * p.ln_w[3] + p.ln_b[3];
+  reinterpret_cast<float4*>(out)[tok] = r;
+}
+
+// ------------------------------------------------------------------------------------------ small Block
+// Packed fp32 parameter image of one Block for the CUDA-core kernel (built on the host):
+//   dw[7][C] | dwb[C] | lnw[C] | lnb[C] | w1[H][C] | b1[H] | w2t[H][C] (= point_conv_2 transposed) | b2[C] | gamma[C]
+template <int C>
+struct SmallBlockLayout {
+  static constexpr int H = 2 * C;
+  static constexpr int DW = 0;
+  static constexpr int DWB = DW + 7 * C;
+  static constexpr int LNW = DWB + C;
+  static constexpr int LNB = LNW + C;
+  static constexpr int W1 = LNB + C;
+  static constexpr int B1 = W1 + H * C;
+  static constexpr int W2T = B1 + H;
+  static constexpr int B2 = W2T + H * C;
+  static constexpr int GAMMA = B2 + C;
+  static constexpr int TOTAL = GAMMA + C;
+};
+
+constexpr int SB_TOK = 128;  // tokens (= threads) per CTA
+
+template <int C>
+__global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* __restrict__ Xin, float* __restrict__ Xout,
+                                                             int L, int M, const float* __restrict__ params) {
+  using Lay = SmallBlockLayout<C>;
+  constexpr int H = Lay::H;
+  constexpr int RS = (C == 4) ? 4 : C + 4;  // padded row stride (floats): conflict-free 128-bit row reads
+  extern __shared__ __align__(16) float smem_f[];
+  float* sp = smem_f;                          // parameters
+  float* sx = smem_f + ((Lay::TOTAL + 3) & ~3);  // (SB_TOK + 6) rows of input
+
+  for (int i = threadIdx.x; i < Lay::TOTAL; i += SB_TOK) sp[i] = __ldg(params + i);
+  const int tile0 = blockIdx.x * SB_TOK;
+  // rows tile0-3 .. tile0+SB_TOK+2, zero outside [0, M)
+  constexpr int V = C / 4;
+  for (int i = threadIdx.x; i < (SB_TOK + 6) * V; i += SB_TOK) {
+    const int r = i / V, q = i - r * V;
+    const int g = tile0 - 3 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];
+    reinterpret_cast<float4*>(sx + r * RS)[q] = v;
+  }
+  __syncthreads();
+
+  const int tok = tile0 + threadIdx.x;
+  if (tok >= M) return;
+  const int l = tok % L;
+
+  // depthwise conv k7, zero "SAME" padding at the WINDOW boundary (not the tile/batch boundary)
+  float y[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) y[c] = sp[Lay::DWB + c];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const int ll = l + t - 3;
+    if (ll >= 0 && ll < L) {
+      const float* row = sx + (threadIdx.x + t) * RS;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 xv = reinterpret_cast<const float4*>(row)[q];
+        const float4 wv = reinterpret_cast<const float4*>(sp + Lay::DW + t * C)[q];
+        y[4 * q] = fmaf(wv.x, xv.x, y[4 * q]);
+        y[4 * q + 1] = fmaf(wv.y, xv.y, y[4 * q + 1]);
+        y[4 * q + 2] = fmaf(wv.z, xv.z, y[4 * q + 2]);
+        y[4 * q + 3] = fmaf(wv.w, xv.w, y[4 * q + 3]);
+      }
+    }
+  }
+  // LayerNorm over channels (fp32, biased variance)
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) mean += y[c];
+  mean *= (1.0f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) var += (y[c] - mean) * (y[c] - mean);
+  const float inv = rsqrtf(var * (1.0f / C) + kLnEps);
+#pragma unroll
+  for (int c = 0; c < C; ++c) y[c] = (y[c] - mean) * inv * sp[Lay::LNW + c] + sp[Lay::LNB + c];
+
+  // pointwise C -> H, GELU, pointwise H -> C, one hidden unit at a time (weights broadcast from smem)
+  float o[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) o[c] = sp[Lay::B2 + c];
+#pragma unroll 2
+  for (int h = 0; h < H; ++h) {
+    float a = sp[Lay::B1 + h];
+    const float4* w1 = reinterpret_cast<const float4*>(sp + Lay::W1 + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w1[q];
+      a = fmaf(w.x, y[4 * q], a);
+      a = fmaf(w.y, y[4 * q + 1], a);
+      a = fmaf(w.z, y[4 * q + 2], a);
+      a = fmaf(w.w, y[4 * q + 3], a);
+    }
+    const float gl = gelu_tanh_cc(a);
+    const float4* w2 = reinterpret_cast<const float4*>(sp + Lay::W2T + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w2[q];
+      o[4 * q] = fmaf(w.x, gl, o[4 * q]);
+      o[4 * q + 1] = fmaf(w.y, gl, o[4 * q + 1]);
+      o[4 * q + 2] = fmaf(w.z, gl, o[4 * q + 2]);
+      o[4 * q + 3] = fmaf(w.w, gl, o[4 * q + 3]);
+    }
+  }
+  // layer scale + residual.  Out of place: neighbouring CTAs read rows of this tile as their halo.
+  const float* xr = sx + (threadIdx.x + 3) * RS;
+  float* dst = Xout + static_cast<size_t>(tok) * C;
+#pragma unroll
+  for (int q = 0; q < V; ++q) {
+    float4 r;
+    r.x = fmaf(sp[Lay::GAMMA + 4 * q], o[4 * q], xr[4 * q]);
+    r.y = fmaf(sp[Lay::GAMMA + 4 * q + 1], o[4 * q + 1], xr[4 * q + 1]);
+    r.z = fmaf(sp[Lay::GAMMA + 4 * q + 2], o[4 * q + 2], xr[4 * q + 2]);
+    r.w = fmaf(sp[Lay::GAMMA + 4 * q + 3], o[4 * q + 3], xr[4 * q + 3]);
+    reinterpret_cast<float4*>(dst)[q] = r;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ small Downsample
+// Packed parameters: lnw[Cin] | lnb[Cin] | w[Cout][2*Cin] (k index = tap * Cin + c) | b[Cout]
+template <int CIN>
+struct SmallDownLayout {
+  static constexpr int COUT = 2 * CIN;
+  static constexpr int LNW = 0;
+  static constexpr int LNB = CIN;
+  static constexpr int W = 2 * CIN;
+  static constexpr int B = W + COUT * 2 * CIN;
+  static constexpr int TOTAL = B + COUT;
+};
+
+// X [M_in, CIN] fp32 -> Y [M_in / 2, 2*CIN] fp32.  One thread per OUTPUT token (two adjacent input tokens;
+// L_in is even at every stage so a pair never straddles a window).
+template <int CIN>
+__global__ void __launch_bounds__(128) downsample_small_kernel(const float* __restrict__ X, float* __restrict__ Y,
+                                                               int M_out, const float* __restrict__ params) {
+  using Lay = SmallDownLayout<CIN>;
+  constexpr int COUT = Lay::COUT;
+  constexpr int K = 2 * CIN;
+  extern __shared__ __align__(16) float smem_f[];
+  for (int i = threadIdx.x; i < Lay::TOTAL; i += blockDim.x) smem_f[i] = __ldg(params + i);
+  __syncthreads();
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= M_out) return;
+
+  float n[K];
+  const float4* src = reinterpret_cast<const float4*>(X + static_cast<size_t>(tok) * K);
+#pragma unroll
+  for (int q = 0; q < K / 4; ++q) {
+    const float4 v = src[q];
+    n[4 * q] = v.x; n[4 * q + 1] = v.y; n[4 * q + 2] = v.z; n[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    float mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) mean += n[t * CIN + c];
+    mean *= (1.0f / CIN);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) var += (n[t * CIN + c] - mean) * (n[t * CIN + c] - mean);
+    const float inv = rsqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+      n[t * CIN + c] = (n[t * CIN + c] - mean) * inv * smem_f[Lay::LNW + c] + smem_f[Lay::LNB + c];
+  }
+  float* dst = Y + static_cast<size_t>(tok) * COUT;
+#pragma unroll 1
+  for (int o = 0; o < COUT; o += 4) {
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a = smem_f[Lay::B + o + u];
+      const float4* w = reinterpret_cast<const float4*>(smem_f + Lay::W + (o + u) * K);
+#pragma unroll
+      for (int q = 0; q < K / 4; ++q) {
+        const float4 wv = w[q];
+        a = fmaf(wv.x, n[4 * q], a);
+        a = fmaf(wv.y, n[4 * q + 1], a);
+        a = fmaf(wv.z, n[4 * q + 2], a);
+        a = fmaf(wv.w, n[4 * q + 3], a);
+      }
+      acc[u] = a;
+    }
+    reinterpret_cast<float4*>(dst)[o / 4] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ lane <-> channel map
+// A warp owns one row of C channels.  Lane `lane` holds G groups of VW contiguous channels:
+//   channel(g, j) = g * 32 * VW + lane * VW + j,   VW = min(4, C / 32),  G = C / (32 * VW)
+// so every warp-wide access is one contiguous 32*VW*4-byte segment (coalesced in global memory,
+// bank-conflict free in shared memory).
+template <int C>
+struct RowMap {
+  static constexpr int VW = (C / 32 >= 4) ? 4 : C / 32;
+  static constexpr int G = C / (32 * VW);
+  static constexpr int PER = VW * G;
+  static_assert(C % 64 == 0 && VW >= 2, "row kernels need C in {64, 128, 256}");
+  __device__ static __forceinline__ int chan(int lane, int g) { return g * 32 * VW + lane * VW; }
+  __device__ static __forceinline__ void load(const float* row, int lane, float* x) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if constexpr (VW == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(row + chan(lane, g));
+        x[4 * g] = v.x; x[4 * g + 1] = v.y; x[4 * g + 2] = v.z; x[4 * g + 3] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(row + chan(lane, g));
+        x[2 * g] = v.x; x[2 * g + 1] = v.y;
+      }
+    }
+  }
+  __device__ static __forceinline__ void store_f32(float* row, int lane, const float* x) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if constexpr (VW == 4)
+        *reinterpret_cast<float4*>(row + chan(lane, g)) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+      else
+        *reinterpret_cast<float2*>(row + chan(lane, g)) = make_float2(x[2 * g], x[2 * g + 1]);
+    }
+  }
+  __device__ static __forceinline__ void store_bf16(__nv_bfloat16* row, int lane, const float* x) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if constexpr (VW == 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(x[4 * g], x[4 * g + 1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(x[4 * g + 2], x[4 * g + 3]);
+        uint2 q;
+        q.x = *reinterpret_cast<uint32_t*>(&a);
+        q.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(row + chan(lane, g)) = q;
+      } else {
+        *reinterpret_cast<__nv_bfloat162*>(row + chan(lane, g)) = __floats2bfloat162_rn(x[2 * g], x[2 * g + 1]);
+      }
+    }
+  }
+  // LayerNorm of the row held across the warp (fp32 statistics, biased variance, eps inside the sqrt)
+  __device__ static __forceinline__ void layer_norm(float* x, const float* lw, const float* lb) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) s += x[j];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) v += (x[j] - mean) * (x[j] - mean);
+    const float inv = rsqrtf(warp_sum(v) * (1.0f / C) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) x[j] = (x[j] - mean) * inv * lw[j] + lb[j];
+  }
+};
+
+// ------------------------------------------------------------------------------------------ dwconv + LN (C >= 64)
+// Packed parameters: dw[7][C] | dwb[C] | lnw[C] | lnb[C]
+constexpr int DW_TOK = 32;       // tokens per CTA
+constexpr int DW_THREADS = 256;  // 8 warps, 4 tokens each
+
+template <int C>
+__global__ void __launch_bounds__(DW_THREADS) dwconv_ln_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ A,
+                                                               int L, int M, const float* __restrict__ params) {
+  using RM = RowMap<C>;
+  constexpr int PER = RM::PER;
+  extern __shared__ __align__(16) float smem_f[];
+  float* sx = smem_f;  // (DW_TOK + 6) x C
+  const int tile0 = blockIdx.x * DW_TOK;
+  constexpr int V = C / 4;
+  for (int i = threadIdx.x; i < (DW_TOK + 6) * V; i += DW_THREADS) {
+    const int r = i / V, q = i - r * V;
+    const int g = tile0 - 3 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= 0 && g < M) v = __ldg(reinterpret_cast<const float4*>(X + static_cast<size_t>(g) * C) + q);
+    reinterpret_cast<float4*>(sx + r * C)[q] = v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float w[7][PER], bias[PER], lw[PER], lb[PER];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) RM::load(params + t * C, lane, w[t]);
+  RM::load(params + 7 * C, lane, bias);
+  RM::load(params + 8 * C, lane, lw);
+  RM::load(params + 9 * C, lane, lb);
+  __syncthreads();
+
+#pragma unroll 1
+  for (int i = 0; i < DW_TOK / 8; ++i) {
+    const int lt = warp * (DW_TOK / 8) + i;
+    const int tok = tile0 + lt;
+    if (tok >= M) break;
+    const int l = tok % L;
+    float y[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) y[j] = bias[j];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int ll = l + t - 3;
+      if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary
+        float xr[PER];
+        RM::load(sx + (lt + t) * C, lane, xr);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) y[j] = fmaf(w[t][j], xr[j], y[j]);
+      }
+    }
+    RM::layer_norm(y, lw, lb);
+    RM::store_bf16(A + static_cast<size_t>(tok) * C, lane, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ row LayerNorm
+// One warp per row of C fp32 -> bf16 (GEMM operand) and/or fp32.  Rows may be re-mapped from a compact
+// [B * Lin] layout into a padded [B * Lout] layout (final CNN norm -> transformer buffers, T = 250 -> 256).
+template <int C>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ X, int rows, int Lin, int Lout,
+                                                      const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                      __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+  using RM = RowMap<C>;
+  constexpr int PER = RM::PER;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float x[PER], lw[PER], lb[PER];
+  RM::load(X + static_cast<size_t>(row) * C, lane, x);
+  RM::load(lnw, lane, lw);
+  RM::load(lnb, lane, lb);
+  RM::layer_norm(x, lw, lb);
+  const int orow = (row / Lin) * Lout + (row % Lin);
+  if (out32 != nullptr) RM::store_f32(out32 + static_cast<size_t>(orow) * C, lane, x);
+  if (out16 != nullptr) RM::store_bf16(out16 + static_cast<size_t>(orow) * C, lane, x);
+}
+
+}  // namespace a2m

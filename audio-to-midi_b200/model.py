@@ -1,0 +1,400 @@
+"""Host-side mirror of the reference model interface (reference model.py), backed by the CUDA library.
+
+Same class names, field names, field ORDER and leaf shapes as the reference's equinox modules, so the
+flattened pytree (``tree_leaves_with_path``) lines up leaf-for-leaf with the reference's checkpoint
+pytree (model.py:673-678 and the classes below it).  Same call signatures:
+
+    model = OutputSequenceGenerator(model_config, key)
+    (logits, probs), state = model(samples, state, rope_freqs, key=None, enable_dropout=False)   # model.py:740-769
+    logits, probs = model.predict(state, samples, rope_freqs)                                     # model.py:771-773
+
+The reference model is unbatched and callers ``jax.vmap`` it (infer.py:40).  JAX does not exist in this
+image, so the batch axis is native here: ``samples`` may be (2, N) or (B, 2, N); ``vmap(model.predict,
+in_axes=(None, 0, None))`` is provided as a thin adapter that forwards the batched array unchanged.
+
+Arrays: numpy in -> numpy out (host path, copies inside the C call); torch CUDA tensors in -> torch CUDA
+tensors out (device path, enqueued on the current torch stream, no host sync).  No CPU compute path
+exists: without the CUDA library / an sm_100 GPU every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .rope import RopeFreqs
+
+MIDI_EVENT_VOCCAB_SIZE = 90       # audio_to_midi_dataset.py:26
+MODEL_AUDIO_LENGTH = 5.0          # audio_to_midi_dataset.py:28
+SAMPLE_RATE = 16000               # audio_to_midi_dataset.py:111
+
+model_config = {                   # model.py:20-34
+    "dims": [4 * (2 ** i) for i in range(7)],
+    "depths": [3, 3, 3, 3, 3, 21, 3],
+    "cnn_hidden_expansion": 2.0,
+    "num_transformer_layers": 8,
+    "num_transformer_heads": 4,
+    "attention_size": 64,
+    "compressed_attention_q_size": 64,
+    "compressed_attention_kv_size": 64,
+    "transformer_dropout_rate": 0.1,
+    "transformer_hidden_expansion": 2.0,
+    "sdd_rate": 0.1,
+}
+
+
+def get_model_metadata():         # model.py:36-41
+    return {"model": model_config,
+            "data_prep": {"sample_rate": SAMPLE_RATE, "audio_length": MODEL_AUDIO_LENGTH}}
+
+
+# ----------------------------------------------------------------------------------------------- pytree
+class Module:
+    """Minimal stand-in for eqx.Module: ordered fields, leaves are numpy arrays (or None)."""
+    _fields: tuple = ()
+
+    def tree_leaves_with_path(self, prefix=""):
+        out = []
+        for name in self._fields:
+            out.extend(_flatten(getattr(self, name), f"{prefix}{name}"))
+        return out
+
+
+def _flatten(v, path):
+    if v is None:
+        return []
+    if isinstance(v, Module):
+        return v.tree_leaves_with_path(path + ".")
+    if isinstance(v, (list, tuple)):
+        out = []
+        for i, x in enumerate(v):
+            out.extend(_flatten(x, f"{path}.{i}"))
+        return out
+    if isinstance(v, (np.ndarray, np.floating)):
+        return [(path, v)]
+    return []  # static fields (ints, bools)
+
+
+def _set_by_path(obj, path, value):
+    parts = path.split(".")
+    for p in parts[:-1]:
+        obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+    last = parts[-1]
+    cur = obj[int(last)] if last.isdigit() else getattr(obj, last)
+    value = np.asarray(value, dtype=np.float32)
+    if np.shape(cur) != value.shape:
+        raise ValueError(f"leaf {path}: shape {value.shape} does not match {np.shape(cur)}")
+    if last.isdigit():
+        obj[int(last)] = value
+    else:
+        setattr(obj, last, value)
+
+
+class _Rng:
+    def __init__(self, key):
+        seed = 0 if key is None else int(np.asarray(key).ravel()[-1])
+        self.g = np.random.Generator(np.random.PCG64(seed))
+
+    def uniform(self, shape, fan_in):
+        lim = 1.0 / np.sqrt(fan_in)
+        return self.g.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+class Conv1d(Module):              # eqx.nn.Conv1d: weight (out, in/groups, k), bias (out, 1)
+    _fields = ("weight", "bias")
+
+    def __init__(self, rng, cin, cout, k, groups=1, lead=()):
+        fan_in = (cin // groups) * k
+        self.weight = rng.uniform(lead + (cout, cin // groups, k), fan_in)
+        self.bias = rng.uniform(lead + (cout, 1), fan_in)
+
+
+class Linear(Module):              # eqx.nn.Linear: weight (out, in), bias (out,)
+    _fields = ("weight", "bias")
+
+    def __init__(self, rng, cin, cout, use_bias=True, lead=()):
+        self.weight = rng.uniform(lead + (cout, cin), cin)
+        self.bias = rng.uniform(lead + (cout,), cin) if use_bias else None
+
+
+class LayerNorm(Module):           # eqx.nn.LayerNorm: weight, bias
+    _fields = ("weight", "bias")
+
+    def __init__(self, n, lead=()):
+        self.weight = np.ones(lead + (n,), np.float32)
+        self.bias = np.zeros(lead + (n,), np.float32)
+
+
+class StochasticDepthDropout(Module):   # model.py:49-81; p is an array leaf in the reference (model.py:694,710)
+    _fields = ("p",)
+
+    def __init__(self, p):
+        self.p = np.float32(p)
+        self.inference = False
+
+
+class Stem(Module):                # model.py:84-100
+    _fields = ("conv", "norm")
+
+    def __init__(self, rng, channels, kernel_size=5):
+        self.conv = Conv1d(rng, 2, channels, kernel_size)
+        self.norm = LayerNorm(channels)
+
+
+class Downsample(Module):          # model.py:102-118
+    _fields = ("conv", "norm")
+
+    def __init__(self, rng, cin, cout):
+        self.conv = Conv1d(rng, cin, cout, 2)
+        self.norm = LayerNorm(cin)
+
+
+class Block(Module):               # model.py:120-167
+    _fields = ("depth_conv", "point_conv_1", "point_conv_2", "stochastic_depth_dropout", "norm", "gamma")
+
+    def __init__(self, rng, channels, hidden_dim, sdd_rate, kernel_size=7):
+        self.depth_conv = Conv1d(rng, channels, channels, kernel_size, groups=channels)
+        self.norm = LayerNorm(channels)
+        self.point_conv_1 = Conv1d(rng, channels, hidden_dim, 1)
+        self.point_conv_2 = Conv1d(rng, hidden_dim, channels, 1)
+        self.stochastic_depth_dropout = StochasticDepthDropout(sdd_rate)
+        self.gamma = np.full((channels,), 1e-6, np.float32)   # layer scale, model.py:157-158
+
+
+class Sequential(Module):          # eqx.nn.Sequential: field `layers`
+    _fields = ("layers",)
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+
+
+class Decoder(Module):             # model.py:169-198
+    _fields = ("decoder_pooling", "norm")
+
+    def __init__(self, rng, dim):
+        self.decoder_pooling = Linear(rng, dim, MIDI_EVENT_VOCCAB_SIZE)
+        self.norm = LayerNorm(dim)
+
+
+class FeedForwardBlock(Module):    # model.py:200-238 (dropout has no array leaves)
+    _fields = ("attention_to_intermediate_proj", "intermediate_to_attention_proj")
+
+    def __init__(self, rng, hidden, inter, lead):
+        self.attention_to_intermediate_proj = Linear(rng, hidden, 2 * inter, lead=lead)
+        self.intermediate_to_attention_proj = Linear(rng, inter, hidden, lead=lead)
+
+
+class SelfAttention(Module):       # model.py:260-374; query_down_proj is None in the default config
+    _fields = ("query_down_proj", "query_up_proj", "kv_down_proj", "key_up_proj", "value_up_proj", "output_proj")
+
+    def __init__(self, rng, d, heads, hd, ckv, lead):
+        self.query_down_proj = None
+        self.query_up_proj = Linear(rng, d, heads * hd, use_bias=False, lead=lead)
+        self.kv_down_proj = Linear(rng, d, ckv, use_bias=False, lead=lead)
+        self.key_up_proj = Linear(rng, ckv, heads * hd, use_bias=False, lead=lead)
+        self.value_up_proj = Linear(rng, ckv, heads * hd, use_bias=False, lead=lead)
+        self.output_proj = Linear(rng, heads * hd, d, use_bias=False, lead=lead)
+        self.num_heads = heads
+
+
+class LocalSelfAttention(Module):  # model.py:377-471
+    _fields = ("self_attention",)
+
+    def __init__(self, rng, context_length, d, heads, hd, ckv, lead):
+        self.context_length = context_length
+        self.self_attention = SelfAttention(rng, d, heads, hd, ckv, lead)
+
+
+class TransformerLayer(Module):    # model.py:474-556
+    _fields = ("attention_norm", "attention_block", "feed_forward_norm", "feed_forward_block")
+
+    def __init__(self, rng, d, heads, hd, ckv, inter, lead, context_window=None):
+        if context_window is not None:
+            self.attention_block = LocalSelfAttention(rng, context_window, d, heads, hd, ckv, lead)
+        else:
+            self.attention_block = SelfAttention(rng, d, heads, hd, ckv, lead)
+        self.attention_norm = LayerNorm(d, lead)
+        self.feed_forward_block = FeedForwardBlock(rng, d, inter, lead)
+        self.feed_forward_norm = LayerNorm(d, lead)
+
+
+class AlternatingLocalAndGlobalAttention(Module):   # model.py:559-612
+    _fields = ("local_attention", "global_attention")
+
+    def __init__(self, rng, d, heads, hd, ckv, inter, lead):
+        self.local_attention = TransformerLayer(rng, d, heads, hd, ckv, inter, lead, context_window=16)
+        self.global_attention = TransformerLayer(rng, d, heads, hd, ckv, inter, lead)
+
+
+class TransformerStack(Module):    # model.py:615-670: `layers` is ONE module whose leaves carry a leading axis
+    _fields = ("layers",)
+
+    def __init__(self, rng, d, num_layers, heads, hd, ckv, inter):
+        self.num_layers = num_layers
+        self.layers = AlternatingLocalAndGlobalAttention(rng, d, heads, hd, ckv, inter, lead=(num_layers,))
+
+
+# ----------------------------------------------------------------------------------------------- engine
+class _Engine:
+    """One C handle per CUDA device; owns the uploaded weights."""
+    _by_device: Dict[int, "_Engine"] = {}
+
+    def __init__(self, device: int):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        rc = self.L.a2m_create(device, C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.L.a2m_last_error(h).decode() if h else ""
+            if h:
+                self.L.a2m_destroy(h)
+            raise _lib.A2mError(f"a2m_create(device={device}) failed with code {rc} {msg}: an sm_100 (B200) GPU and "
+                                "the CUDA library are required; there is no CPU fallback")
+        self.device = device
+        self.weights_token = None
+
+    @classmethod
+    def get(cls, device: int) -> "_Engine":
+        if device not in cls._by_device:
+            cls._by_device[device] = cls(device)
+        return cls._by_device[device]
+
+    def load(self, model: "OutputSequenceGenerator"):
+        leaves = model.tree_leaves_with_path()
+        n = len(leaves)
+        table = (_lib.LeafDesc * n)()
+        chunks, off = [], 0
+        for i, (path, arr) in enumerate(leaves):
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            table[i].path = path.encode()
+            table[i].offset_bytes = off
+            table[i].ndim = a.ndim
+            for d in range(a.ndim):
+                table[i].shape[d] = a.shape[d]
+            chunks.append(a.reshape(-1))
+            off += a.size * 4
+        blob = np.concatenate(chunks)
+        _lib.check(self.h, self.L.a2m_load_weights(self.h, blob.ctypes.data, blob.nbytes, table, n), "a2m_load_weights")
+        self.weights_token = model._version
+
+
+class OutputSequenceGenerator(Module):   # model.py:673-773
+    _fields = ("layers", "norm", "transformer_projection", "transformer", "decoder")
+
+    def __init__(self, conf: Dict[str, Any], key=None):
+        rng = _Rng(key)
+        dims, depths = conf["dims"], conf["depths"]
+        if list(dims) != model_config["dims"] or list(depths) != model_config["depths"] or \
+                conf.get("transformer_hidden_dim", dims[-1]) != dims[-1]:
+            raise NotImplementedError("the CUDA kernels are specialised for the reference's default model_config")
+        hidden = [int(d * conf["cnn_hidden_expansion"]) for d in dims]
+        sdd = np.linspace(0.0, conf["sdd_rate"], sum(depths))
+        self.layers, k = [], 0
+        for i in range(len(dims)):
+            first = Stem(rng, dims[0]) if i == 0 else Downsample(rng, dims[i - 1], dims[i])
+            blocks = [Block(rng, dims[i], hidden[i], sdd[k + j]) for j in range(depths[i])]
+            k += depths[i]
+            self.layers.append(Sequential([first, *blocks]))
+        self.norm = LayerNorm(dims[-1])
+        self.transformer_projection = None
+        d = dims[-1]
+        self.transformer = TransformerStack(rng, d, conf["num_transformer_layers"], conf["num_transformer_heads"],
+                                            conf["attention_size"], conf["compressed_attention_kv_size"],
+                                            int(d * conf["transformer_hidden_expansion"]))
+        self.decoder = Decoder(rng, d)
+        self._version = 0
+        self._rope_cache = {}
+
+    # -- pytree helpers (what eqx.tree_at / tree_deserialise_leaves would be used for)
+    def load_leaves(self, leaves: Dict[str, np.ndarray]):
+        """Overwrite parameters from {dotted key path: array}; every leaf of the pytree must be present."""
+        mine = [p for p, _ in self.tree_leaves_with_path()]
+        missing = [p for p in mine if p not in leaves]
+        if missing:
+            raise KeyError(f"missing leaves: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        for p in mine:
+            _set_by_path(self, p, leaves[p])
+        self._version += 1
+        return self
+
+    def invalidate(self):
+        """Call after mutating leaves in place so the next forward re-uploads the weights."""
+        self._version += 1
+
+    # -- forward
+    def _engine(self, device: int) -> _Engine:
+        eng = _Engine.get(device)
+        if eng.weights_token != self._version or getattr(eng, "owner", None) is not self:
+            eng.load(self)
+            eng.owner = self
+        return eng
+
+    def __call__(self, samples, state, rope_freqs: RopeFreqs, key=None, enable_dropout: bool = False):
+        if enable_dropout:
+            raise NotImplementedError("training-mode forward (dropout) is not built yet; see DESIGN.md scope table")
+        logits, probs = self._forward(samples, rope_freqs)
+        return (logits, probs), state
+
+    def predict(self, state, samples, rope_freqs: RopeFreqs):
+        (logits, probs), _ = self(samples, state, rope_freqs, None)
+        return logits, probs
+
+    def _forward(self, samples, rope_freqs):
+        is_torch = type(samples).__module__.startswith("torch")
+        shape = tuple(samples.shape)
+        single = len(shape) == 2
+        if (len(shape) not in (2, 3)) or shape[-2:] != (2, 80000):
+            raise ValueError(f"samples must be (2, 80000) or (B, 2, 80000), got {shape}")
+        B = 1 if single else shape[0]
+        if is_torch:
+            import torch
+            if not samples.is_cuda:
+                raise _lib.A2mError("torch input must live on a CUDA device (no CPU path); pass numpy for the host API")
+            dev = samples.device.index if samples.device.index is not None else torch.cuda.current_device()
+            eng = self._engine(dev)
+            x = samples.to(torch.float32).contiguous()
+            ck = (dev, id(rope_freqs))
+            if ck not in self._rope_cache:
+                cos = torch.as_tensor(np.ascontiguousarray(rope_freqs.cos_freq, np.float32)).to(samples.device)
+                sin = torch.as_tensor(np.ascontiguousarray(rope_freqs.sin_freq, np.float32)).to(samples.device)
+                self._rope_cache = {ck: (cos, sin, rope_freqs)}
+            cos, sin, _ = self._rope_cache[ck]
+            logits = torch.empty((B, 250, 90), dtype=torch.float32, device=samples.device)
+            probs = torch.empty_like(logits)
+            stream = torch.cuda.current_stream(samples.device).cuda_stream
+            rc = eng.L.a2m_forward(eng.h, x.data_ptr(), B, cos.data_ptr(), sin.data_ptr(), cos.shape[0],
+                                   logits.data_ptr(), probs.data_ptr(), None, 0, C.c_void_p(stream))
+            _lib.check(eng.h, rc, "a2m_forward")
+            return (logits[0], probs[0]) if single else (logits, probs)
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        eng = self._engine(_default_device())
+        cos = np.ascontiguousarray(rope_freqs.cos_freq, np.float32)
+        sin = np.ascontiguousarray(rope_freqs.sin_freq, np.float32)
+        logits = np.empty((B, 250, 90), np.float32)
+        probs = np.empty((B, 250, 90), np.float32)
+        rc = eng.L.a2m_forward_host(eng.h, x.ctypes.data, B, cos.ctypes.data, sin.ctypes.data, cos.shape[0],
+                                    logits.ctypes.data, probs.ctypes.data)
+        _lib.check(eng.h, rc, "a2m_forward_host")
+        return (logits[0], probs[0]) if single else (logits, probs)
+
+    def last_launch_count(self, device: Optional[int] = None) -> int:
+        eng = _Engine.get(_default_device() if device is None else device)
+        return int(eng.L.a2m_last_launch_count(eng.h))
+
+
+def _default_device() -> int:
+    import os
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("A2M_DEVICE", "0")))
+
+
+def vmap(fn, in_axes=(None, 0, None)):
+    """Adapter for the reference call shape jax.vmap(model.predict, in_axes=(None, 0, None)) (infer.py:40):
+    the kernels are natively batched, so the mapped axis is simply passed through."""
+    if tuple(in_axes) != (None, 0, None):
+        raise NotImplementedError("only in_axes=(None, 0, None) (state, samples, rope_freqs) is supported")
+
+    def mapped(state, samples, rope_freqs):
+        return fn(state, samples, rope_freqs)
+    return mapped

@@ -1,0 +1,137 @@
+/* libaudio2midi_b200 -- C ABI of the B200-native audio-to-midi hot path.
+ *
+ * Drop-in boundary for the reference's batched model forward
+ *     jax.vmap(model.predict, in_axes=(None, 0, None))(state, samples[B,2,80000], rope_freqs)
+ * (reference infer.py:40; OutputSequenceGenerator.__call__ / predict, model.py:740-773) and for the
+ * Rust `modelutil` post-processing that consumes its output (rust-plugins/src/common.rs:13-144,
+ * python.rs:423-447, and the reference's only existing C ABI, cbinds.rs:9-91).
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returning int returns 0 on success and a negative A2M_E* code on failure, in which
+ *     case a2m_last_error(handle) describes it; nothing aborts or throws across the boundary;
+ *   - the caller owns every buffer it passes; the library owns its weights arena and workspace;
+ *   - one handle per device; a handle is not thread-safe, distinct handles are independent;
+ *   - *_dev pointers are device memory on the handle's device, *_host pointers are host memory;
+ *   - nothing here falls back to the CPU: without an sm_100 device a2m_create fails.
+ */
+#ifndef A2M_H_
+#define A2M_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A2M_OK 0
+#define A2M_EINVAL (-1)    /* bad argument / shape / missing leaf */
+#define A2M_ECUDA (-2)     /* CUDA runtime or driver error */
+#define A2M_ENODEVICE (-3) /* no sm_100 device */
+#define A2M_ESTATE (-4)    /* call order (e.g. forward before load_weights) */
+
+#define A2M_WINDOW_SAMPLES 80000 /* audio_to_midi_dataset.py:28,111: 5.0 s x 16 kHz */
+#define A2M_FRAMES 250           /* model output frames per window */
+#define A2M_VOCAB 90             /* audio_to_midi_dataset.py:26 MIDI_EVENT_VOCCAB_SIZE */
+#define A2M_ROPE_DIM 32          /* rope.py:12-22 with dim = attention_size = 64 */
+
+typedef struct A2mHandle A2mHandle;
+
+/* One leaf of the reference parameter pytree (model.py:673-678 and below), fp32, C-contiguous, in the
+ * reference's own layout (eqx.nn.Conv1d weight (out, in/groups, k), bias (out, 1); eqx.nn.Linear weight
+ * (out, in); transformer leaves stacked on a leading axis of num_transformer_layers, model.py:646-647).
+ * `path` is the dotted pytree key path, e.g. "layers.5.layers.3.point_conv_1.weight" or
+ * "transformer.layers.local_attention.attention_block.self_attention.kv_down_proj.weight". */
+typedef struct {
+  const char* path;
+  uint64_t offset_bytes; /* into the blob passed to a2m_load_weights */
+  int32_t ndim;
+  int64_t shape[4];
+} A2mLeafDesc;
+
+/* Creates a handle on CUDA device `device`.  Replaces OutputSequenceGenerator.__init__ (model.py:680-738)
+ * for the default model_config (model.py:20-34); weights arrive through a2m_load_weights. */
+int a2m_create(int device, A2mHandle** out);
+void a2m_destroy(A2mHandle* h);
+const char* a2m_last_error(const A2mHandle* h);
+
+/* Loads (and re-packs for the kernels) a full parameter pytree from a host blob.  Replaces the
+ * checkpoint-restore -> pytree hand-off of infer.py:172-236 / change_fp_precision (infer.py:27-32).
+ * May be called again to swap weights. */
+int a2m_load_weights(A2mHandle* h, const void* blob_host, size_t blob_bytes, const A2mLeafDesc* table,
+                     int32_t n_leaves);
+
+/* Bytes of device scratch a forward of `batch` windows needs.  The handle allocates and caches this
+ * itself when a2m_forward is called with workspace_dev == NULL. */
+size_t a2m_workspace_bytes(const A2mHandle* h, int32_t batch, int32_t training);
+
+/* Batched forward; everything is enqueued on `stream`, no host synchronisation.
+ *   audio_dev   [batch, 2, 80000] fp32           (samples of infer.py:40)
+ *   rope_cos_dev / rope_sin_dev [rope_max_pos, 32] fp32, rope_max_pos >= 250   (RopeFreqs, rope.py:5-22)
+ *   logits_dev, probs_dev [batch, 250, 90] fp32   (return value of model.predict, model.py:771-773)
+ *   workspace_dev: NULL, or >= a2m_workspace_bytes(h, batch, 0) bytes, 1024-byte aligned, zero-initialised
+ *                  once by the caller before its first use. */
+int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
+                const float* rope_sin_dev, int32_t rope_max_pos, float* logits_dev, float* probs_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers: stages through pinned memory, copies in, runs, copies out and waits.
+ * This is the end-to-end path a Python caller without device arrays uses. */
+int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                     const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host);
+
+/* Number of kernels of this library launched by the last a2m_forward on this handle. */
+int32_t a2m_last_launch_count(const A2mHandle* h);
+/* Use a CUDA graph for the steady-state forward (default 1). */
+int a2m_set_use_graph(A2mHandle* h, int32_t enable);
+
+/* ---- test hooks (used by tests/ only) ------------------------------------------------------------ */
+/* Runs the forward up to and including the step labelled `label` ("stage0".."stage6", "cnn_out",
+ * "tl<i>_local", "tl<i>_global") and copies the fp32 residual stream at that point to out_dev:
+ * stage taps are [batch * L_stage, C_stage]; the others are [batch * 256, 256] (rows 250..255 padding). */
+int a2m_debug_forward_tap(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
+                          const float* rope_sin_dev, int32_t rope_max_pos, const char* label, float* out_dev,
+                          size_t out_elems, void* stream);
+/* One tcgen05 GEMM: D[M,N] = A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16), generic epilogue
+ * (flags: 1 bias, 2 gelu, 4 gamma, 8 residual, 16 fp32 out, 32 bf16 out).  block_n in {64,128,256}. */
+int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t K, const void* A_bf16_dev,
+                   int32_t lda, const void* W_bf16_dev, uint32_t flags, const float* bias_dev,
+                   const float* gamma_dev, const float* resid_dev, float* out32_dev, void* out16_dev, void* stream);
+
+/* ---- modelutil: post-processing of the probabilities (host code, like the reference's Rust) ------- */
+/* stitch_probs (common.rs:13-45).  probs [windows, frames, cats] fp32 -> out [out_frames, cats];
+ * returns out_frames (= windows*frames - trunc(overlap/dpf)*(windows-1)); out may be NULL to query. */
+int64_t a2m_stitch_probs(const float* probs, int64_t windows, int64_t frames, int64_t cats, double overlap,
+                         double duration_per_frame, float* out);
+
+typedef struct { /* cbinds.rs:9-15 */
+  uint64_t attack_time;
+  uint8_t note;
+  uint64_t duration;
+  uint8_t velocity;
+} MidiEvent;
+typedef struct { /* cbinds.rs:17-22 */
+  MidiEvent* ptr;
+  size_t length;
+  size_t _capacity;
+} MidiEventList;
+typedef struct { /* cbinds.rs:24-29, N = 3; strides in ELEMENTS, data is IEEE binary16 */
+  uint64_t strides[3];
+  uint64_t dims[3];
+  const uint8_t* data;
+} MLMultiArrayWrapper3;
+
+/* extract_events (common.rs:47-144) over probs [frames, notes] fp32; caller frees with free_midi_events. */
+MidiEventList* a2m_extract_events(const float* probs, int64_t frames, int64_t notes);
+/* The reference's iOS entry points (cbinds.rs:51-91): f16 strided windows -> stitch -> extract. */
+MidiEventList* extract_midi_events(MLMultiArrayWrapper3 data, double overlap, double duration_per_frame);
+void free_midi_events(MidiEventList* ptr);
+/* convert_to_frame_events (python.rs:423-447) as called by to_frame_events (python.rs:980-1005):
+ * events -> out [frame_count, 90] fp32 (zero-filled first). */
+int a2m_to_frame_events(const MidiEvent* events, int64_t n_events, int64_t frame_count, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A2M_H_ */

@@ -112,7 +112,8 @@ def to_frame_events(events, frame_count: int, num_event_types: int = 90) -> np.n
             frames[start - 1, key] = 0.0
         for fr in range(max(start, 0), min(end, frame_count)):
             t = f32(fr) - f32(start)
-            frames[fr, key] = max(f32(np.exp(f32(-0.05) * t)), f32(0.6))
+            # f32 exp as a correctly rounded libm expf gives it (Rust f32::exp -> expf): evaluate in f64, round once
+            frames[fr, key] = max(f32(np.exp(np.float64(f32(-0.05) * t))), f32(0.6))
     return frames
 
 

@@ -1,0 +1,65 @@
+"""tcgen05 GEMM kernel (csrc/gemm_tc.cuh) against a float64 reference on the same bf16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * x ** 3)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from gpu_util import engine, make_model
+    m, _ = make_model(1)
+    return engine(m)
+
+
+@pytest.mark.parametrize("bn,M,N,K", [
+    (64, 128, 64, 64), (64, 1000, 320, 256), (128, 128, 128, 64), (128, 4096, 256, 512),
+    (128, 333, 128, 128), (256, 256, 256, 128), (256, 20000, 512, 256), (128, 16384, 256, 256),
+])
+def test_gemm_plain(eng, bn, M, N, K):
+    from gpu_util import debug_gemm
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(torch.bfloat16).cuda()
+    out32, _ = debug_gemm(eng, bn, a, w, 16)
+    ref = a.double().cpu().numpy() @ w.double().cpu().numpy().T
+    err = np.abs(out32.cpu().numpy() - ref).max()
+    assert err < 2e-4 * np.sqrt(K), f"max abs err {err}"       # fp32 accumulation of exact bf16 products
+
+
+def test_gemm_fused_epilogue(eng):
+    from gpu_util import debug_gemm
+    M, N, K = 1500, 256, 128
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(torch.bfloat16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    gamma = torch.rand(N, generator=g).cuda() + 0.5
+    resid = torch.randn(M, N, generator=g).cuda()
+    acc = a.double().cpu().numpy() @ w.double().cpu().numpy().T + bias.double().cpu().numpy()
+    # bias + gelu -> bf16
+    _, o16 = debug_gemm(eng, 128, a, w, 1 | 2 | 32, bias=bias, want32=False, want16=True)
+    ref = _gelu(acc)
+    assert np.abs(o16.float().cpu().numpy() - ref).max() < 2e-2          # bf16 output rounding (|x| < 6)
+    # bias + gamma + residual -> fp32 (the pw2 / ffn2 / out-proj epilogue)
+    o32, _ = debug_gemm(eng, 256, a, w, 1 | 4 | 8 | 16, bias=bias, gamma=gamma, resid=resid)
+    ref = resid.double().cpu().numpy() + gamma.double().cpu().numpy() * acc
+    assert np.abs(o32.cpu().numpy() - ref).max() < 1e-3
+
+
+def test_gemm_strided_a(eng):
+    """A operand read through a row stride (K = 64 slice of a [M, 320] buffer, as the kv projection does)."""
+    from gpu_util import debug_gemm
+    M, N, K = 700, 128, 64
+    g = torch.Generator(device="cpu").manual_seed(9)
+    full = torch.randn(M, 320, generator=g).to(torch.bfloat16).cuda()
+    a = full[:, 256:]
+    w = (torch.randn(N, K, generator=g) / 8).to(torch.bfloat16).cuda()
+    o32, _ = debug_gemm(eng, 128, a, w, 16)
+    ref = a.double().cpu().numpy() @ w.double().cpu().numpy().T
+    assert np.abs(o32.cpu().numpy() - ref).max() < 2e-3
