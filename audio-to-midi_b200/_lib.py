@@ -25,13 +25,17 @@ class MidiEventList(C.Structure):
     _fields_ = [("ptr", C.POINTER(MidiEvent)), ("length", C.c_size_t), ("_capacity", C.c_size_t)]
 
 
+class StepProfile(C.Structure):
+    _fields_ = [("kernel", C.c_char * 32), ("ms", C.c_float), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 class MLMultiArrayWrapper3(C.Structure):
     _fields_ = [("strides", C.c_uint64 * 3), ("dims", C.c_uint64 * 3), ("data", C.c_void_p)]
 
 
 EXPORTS = [
     "a2m_create", "a2m_destroy", "a2m_last_error", "a2m_load_weights", "a2m_workspace_bytes", "a2m_forward",
-    "a2m_forward_host", "a2m_last_launch_count", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
+    "a2m_forward_host", "a2m_last_launch_count", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
 ]
 
@@ -67,6 +71,8 @@ def lib() -> C.CDLL:
     L.a2m_forward_host.restype = C.c_int
     L.a2m_last_launch_count.argtypes = [vp]
     L.a2m_last_launch_count.restype = i32
+    L.a2m_profile_steps.argtypes = [vp, i32, i32, i32, C.POINTER(StepProfile)]
+    L.a2m_profile_steps.restype = i32
     L.a2m_set_use_graph.argtypes = [vp, i32]
     L.a2m_set_use_graph.restype = C.c_int
     L.a2m_debug_forward_tap.argtypes = [vp, vp, i32, vp, vp, i32, C.c_char_p, vp, sz, vp]

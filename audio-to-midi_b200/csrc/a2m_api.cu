@@ -150,6 +150,9 @@ struct Step {
   std::string label;  // non-empty: a tap point reached AFTER this step
   const float* tap_ptr = nullptr;
   size_t tap_elems = 0;
+  const char* kernel = "";  // kernel family, for the per-step profile
+  double flops = 0.0;       // algorithmic matmul/conv FLOPs of this launch (2 * MACs)
+  double bytes = 0.0;       // algorithmic bytes this launch must move (operands in + results out)
   std::function<cudaError_t(cudaStream_t)> run;
 };
 
@@ -489,15 +492,35 @@ bool add_gemm(A2mHandle* h, Plan* p, int BN, int mode, const __nv_bfloat16* A, i
   const int sms = h->num_sms;
   Step st;
   st.label = label; st.tap_ptr = tap; st.tap_elems = tap_elems;
+  st.kernel = "gemm_tc_kernel";
+  st.flops = 2.0 * g.M * g.N * g.K;
+  {
+    const double out_cols = (mode == GEMM_GLU) ? g.N / 2 : g.N;
+    double out_b = 0.0;
+    if (mode == GEMM_GENERIC) {
+      if (g.flags & GF_OUT32) out_b += 4.0;
+      if (g.flags & GF_OUT16) out_b += 2.0;
+      if (g.flags & GF_RESID) out_b += 4.0;
+    } else {
+      out_b = 2.0;
+    }
+    st.bytes = 2.0 * g.M * g.K + 2.0 * g.N * g.K + out_b * g.M * out_cols;
+  }
   st.run = [=](cudaStream_t s) { return launch_gemm(BN, mode, ta, tb, g, sms, s); };
   p->steps.push_back(std::move(st));
   return true;
 }
 
-void add_step(Plan* p, std::function<cudaError_t(cudaStream_t)> fn, const std::string& label = "",
+struct Meta {
+  const char* kernel;
+  double flops, bytes;
+};
+
+void add_step(Plan* p, Meta meta, std::function<cudaError_t(cudaStream_t)> fn, const std::string& label = "",
               const float* tap = nullptr, size_t tap_elems = 0) {
   Step st;
   st.label = label; st.tap_ptr = tap; st.tap_elems = tap_elems;
+  st.kernel = meta.kernel; st.flops = meta.flops; st.bytes = meta.bytes;
   st.run = std::move(fn);
   p->steps.push_back(std::move(st));
 }
@@ -518,11 +541,12 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       float* out = ws.X[cur ^ 1];
       if (s <= 4) {
         const float* prm = dev_ptr<float>(h, w.small_down[s]);
+        const Meta md{"downsample_small_kernel", 2.0 * M * C * C, 8.0 * M * C};
         switch (s) {
-          case 1: add_step(p, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); }); break;
-          case 2: add_step(p, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); }); break;
-          case 3: add_step(p, [=](cudaStream_t st) { return launch_small_down<16>(in, out, M, prm, st); }); break;
-          default: add_step(p, [=](cudaStream_t st) { return launch_small_down<32>(in, out, M, prm, st); }); break;
+          case 1: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); }); break;
+          case 2: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); }); break;
+          case 3: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<16>(in, out, M, prm, st); }); break;
+          default: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<32>(in, out, M, prm, st); }); break;
         }
       } else {
         // LN over the input channels -> bf16 [2M, Cin] == [M, 2*Cin]; conv k2 s2 == GEMM with K = 2*Cin
@@ -530,8 +554,9 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         const float* lw = dev_ptr<float>(h, w.big_down[s].lnw);
         const float* lb = dev_ptr<float>(h, w.big_down[s].lnb);
         __nv_bfloat16* a16 = ws.A16;
-        if (Cin == 64) add_step(p, [=](cudaStream_t st) { return launch_ln<64>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
-        else add_step(p, [=](cudaStream_t st) { return launch_ln<128>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
+        const Meta ml{"ln_rows_kernel", 0.0, 6.0 * Min * Cin};
+        if (Cin == 64) add_step(p, ml, [=](cudaStream_t st) { return launch_ln<64>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
+        else add_step(p, ml, [=](cudaStream_t st) { return launch_ln<128>(in, Min, Min, Min, lw, lb, a16, nullptr, st); });
         GemmArgs g = gemm_args(M, C, 2 * Cin);
         g.flags = GF_BIAS | GF_OUT32;
         g.bias = dev_ptr<float>(h, w.big_down[s].b);
@@ -548,11 +573,12 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         float* out = ws.X[cur ^ 1];
         const float* prm = dev_ptr<float>(h, w.small_block[s][j]);
         const size_t te = static_cast<size_t>(M) * C;
+        const Meta mb{"block_small_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
         switch (s) {
-          case 0: add_step(p, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te); break;
-          case 1: add_step(p, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te); break;
-          case 2: add_step(p, [=](cudaStream_t st) { return launch_small_block<16>(in, out, L, M, prm, st); }, label, out, te); break;
-          default: add_step(p, [=](cudaStream_t st) { return launch_small_block<32>(in, out, L, M, prm, st); }, label, out, te); break;
+          case 0: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te); break;
+          case 1: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te); break;
+          case 2: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<16>(in, out, L, M, prm, st); }, label, out, te); break;
+          default: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<32>(in, out, L, M, prm, st); }, label, out, te); break;
         }
         cur ^= 1;
       } else {
@@ -561,9 +587,10 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         __nv_bfloat16* a16 = ws.A16;
         __nv_bfloat16* h16 = ws.H16;
         const float* prm = dev_ptr<float>(h, bw.dwln);
-        if (C == 64) add_step(p, [=](cudaStream_t st) { return launch_dwln<64>(X, a16, L, M, prm, st); });
-        else if (C == 128) add_step(p, [=](cudaStream_t st) { return launch_dwln<128>(X, a16, L, M, prm, st); });
-        else add_step(p, [=](cudaStream_t st) { return launch_dwln<256>(X, a16, L, M, prm, st); });
+        const Meta mdw{"dwconv_ln_kernel", 14.0 * M * C, 6.0 * M * C};
+        if (C == 64) add_step(p, mdw, [=](cudaStream_t st) { return launch_dwln<64>(X, a16, L, M, prm, st); });
+        else if (C == 128) add_step(p, mdw, [=](cudaStream_t st) { return launch_dwln<128>(X, a16, L, M, prm, st); });
+        else add_step(p, mdw, [=](cudaStream_t st) { return launch_dwln<256>(X, a16, L, M, prm, st); });
         GemmArgs g1 = gemm_args(M, 2 * C, C);
         g1.flags = GF_BIAS | GF_GELU | GF_OUT16;
         g1.bias = dev_ptr<float>(h, bw.b1);
@@ -586,8 +613,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     float* xt = ws.Xt;
     const float* lw = dev_ptr<float>(h, w.fnw);
     const float* lb = dev_ptr<float>(h, w.fnb);
-    const int rows = B * kT;
-    add_step(p, [=](cudaStream_t st) { return launch_ln<256>(in, rows, kT, kTP, lw, lb, nullptr, xt, st); }, "cnn_out", xt,
+    add_step(p, Meta{"ln_rows_kernel", 0.0, 8.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(in, Mt, kT, kTP, lw, lb, nullptr, xt, st); }, "cnn_out", xt,
              static_cast<size_t>(Mt) * kD);
   }
   // ---- transformer stack (model.py:649-670): per scan step a local then a global TransformerLayer
@@ -601,7 +627,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     {
       const float* lw = dev_ptr<float>(h, t.ln1w);
       const float* lb = dev_ptr<float>(h, t.ln1b);
-      add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+      add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
     }
     if (local) {
       GemmArgs g = gemm_args(Mt, kQC, kD);
@@ -611,7 +637,8 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       g2.flags = GF_OUT16; g2.out16 = kv; g2.ld16 = kKV;
       if (!add_gemm(h, p, 128, GEMM_GENERIC, qc + 256, kQC, t.wkv, g2)) return false;
       const int total_warps = B * ATT_HEADS * 32;
-      add_step(p, [=](cudaStream_t st) {
+      // as written in the reference: 31 windows x 4 heads x (QK^T + PV) of 16 x 16 x 64
+      add_step(p, Meta{"attn_local_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * (256 + 512 + 256)}, [=](cudaStream_t st) {
         attn_local_kernel<<<(total_warps + AL_WARPS - 1) / AL_WARPS, AL_WARPS * 32, 0, st>>>(
             qc, kQC, kv, kv + 256, kKV, o16, kD, rope_cos, rope_sin, total_warps);
         return cudaGetLastError();
@@ -631,7 +658,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (!make_tmap(h, &tq, qc, Mt, 256, kQC, 64, 128)) return false;
       if (!make_tmap(h, &tk, kv, Mt, 256, kKV, 64, 256)) return false;
       if (!make_tmap(h, &tv, vt, static_cast<uint64_t>(B) * ATT_HEADS * ATT_HD, kTP, kTP, 64, 64)) return false;
-      add_step(p, [=](cudaStream_t st) {
+      add_step(p, Meta{"attn_global_kernel", 2.0 * B * ATT_HEADS * (2.0 * kT * kT * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
         attn_global_kernel<<<dim3(2, ATT_HEADS, B), AG_THREADS, AG_SMEM, st>>>(tq, tk, tv, o16, kD);
         return cudaGetLastError();
       });
@@ -645,7 +672,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     {
       const float* lw = dev_ptr<float>(h, t.ln2w);
       const float* lb = dev_ptr<float>(h, t.ln2b);
-      add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+      add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
     }
     {
       GemmArgs g = gemm_args(Mt, 2 * kFF, kD);
@@ -668,7 +695,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     __nv_bfloat16* a16 = ws.A16;
     const float* lw = dev_ptr<float>(h, w.dlnw);
     const float* lb = dev_ptr<float>(h, w.dlnb);
-    add_step(p, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+    add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
   }
   if (!make_tmap(h, &p->dec_tmA, ws.A16, Mt, kD, kD, GEMM_BK, GEMM_BM)) return false;
   if (!make_tmap(h, &p->dec_tmB, dev_ptr<__nv_bfloat16>(h, w.dw), 128, kD, kD, GEMM_BK, 128)) return false;
@@ -951,6 +978,39 @@ int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const
 }
 
 int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }
+
+int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t max_steps, A2mStepProfile* out) {
+  if (!h || batch <= 0 || repeats <= 0) return A2M_EINVAL;
+  if (!h->loaded) { h->err = "a2m_profile_steps before a2m_load_weights"; return A2M_ESTATE; }
+  if (cudaSetDevice(h->device) != cudaSuccess) return A2M_ECUDA;
+  int rc = ensure_own_ws(h, batch);
+  if (rc) return rc;
+  Plan* p = get_plan(h, batch, h->own_ws);
+  if (!p) return A2M_ECUDA;
+  const int n = static_cast<int>(p->steps.size());
+  if (!out) return n;
+  cudaStream_t s = h->own_stream;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  for (int i = 0; i < n && i < max_steps; ++i) {
+    Step& st = p->steps[i];
+    CUDA_TRY(st.run(s));  // warm-up
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int r = 0; r < repeats; ++r) CUDA_TRY(st.run(s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    std::snprintf(out[i].kernel, sizeof out[i].kernel, "%s", st.kernel);
+    out[i].ms = ms / repeats;
+    out[i].flops = st.flops;
+    out[i].bytes = st.bytes;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return std::min(n, max_steps);
+}
 
 int a2m_set_use_graph(A2mHandle* h, int32_t enable) {
   if (!h) return A2M_EINVAL;

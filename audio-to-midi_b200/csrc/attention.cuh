@@ -300,9 +300,11 @@ attn_local_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloa
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     const int j = 8 * w + jj;
-    if (j < ATT_T)
-      *reinterpret_cast<__nv_bfloat162*>(O + (rowbase + j) * ldo + h * ATT_HD + 2 * lane) =
-          __floats2bfloat162_rn(o[jj][0] * inv, o[jj][1] * inv);
+    // pad rows 250..255 are written as zeros: they feed the output projection of the padded rows and must
+    // stay finite (stale memory there could be NaN/Inf)
+    const bool real = j < ATT_T;
+    *reinterpret_cast<__nv_bfloat162*>(O + (rowbase + j) * ldo + h * ATT_HD + 2 * lane) =
+        __floats2bfloat162_rn(real ? o[jj][0] * inv : 0.f, real ? o[jj][1] * inv : 0.f);
   }
 }
 

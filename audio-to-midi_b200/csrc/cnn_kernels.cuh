@@ -383,23 +383,31 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_ln_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------ row LayerNorm
-// One warp per row of C fp32 -> bf16 (GEMM operand) and/or fp32.  Rows may be re-mapped from a compact
-// [B * Lin] layout into a padded [B * Lout] layout (final CNN norm -> transformer buffers, T = 250 -> 256).
+// One warp per OUTPUT row of C channels: fp32 in -> bf16 (GEMM operand) and/or fp32 out.  Rows may be
+// re-mapped from a compact [B * Lin] layout into a padded [B * Lout] layout (final CNN norm -> transformer
+// buffers, T = 250 -> 256); the pad rows are written as zeros on every call so that everything later
+// derived from them is finite and deterministic (0 * NaN in a masked P.V product would poison real rows).
 template <int C>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ X, int rows, int Lin, int Lout,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ X, int out_rows, int Lin, int Lout,
                                                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                       __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
   using RM = RowMap<C>;
   constexpr int PER = RM::PER;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int orow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (orow >= out_rows) return;
   const int lane = threadIdx.x & 31;
-  float x[PER], lw[PER], lb[PER];
-  RM::load(X + static_cast<size_t>(row) * C, lane, x);
-  RM::load(lnw, lane, lw);
-  RM::load(lnb, lane, lb);
-  RM::layer_norm(x, lw, lb);
-  const int orow = (row / Lin) * Lout + (row % Lin);
+  const int b = orow / Lout, t = orow - b * Lout;
+  float x[PER];
+  if (t < Lin) {
+    float lw[PER], lb[PER];
+    RM::load(X + (static_cast<size_t>(b) * Lin + t) * C, lane, x);
+    RM::load(lnw, lane, lw);
+    RM::load(lnb, lane, lb);
+    RM::layer_norm(x, lw, lb);
+  } else {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) x[j] = 0.f;
+  }
   if (out32 != nullptr) RM::store_f32(out32 + static_cast<size_t>(orow) * C, lane, x);
   if (out16 != nullptr) RM::store_bf16(out16 + static_cast<size_t>(orow) * C, lane, x);
 }

@@ -379,6 +379,18 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         _lib.check(eng.h, rc, "a2m_forward_host")
         return (logits[0], probs[0]) if single else (logits, probs)
 
+    def profile_steps(self, batch: int, repeats: int = 5, device: Optional[int] = None):
+        """Per-launch CUDA-event timings of the forward plan: list of (kernel, ms, algorithmic flops, bytes)."""
+        eng = self._engine(_default_device() if device is None else device)
+        n = eng.L.a2m_profile_steps(eng.h, batch, repeats, 0, None)
+        if n < 0:
+            _lib.check(eng.h, n, "a2m_profile_steps")
+        buf = (_lib.StepProfile * n)()
+        m = eng.L.a2m_profile_steps(eng.h, batch, repeats, n, buf)
+        if m < 0:
+            _lib.check(eng.h, m, "a2m_profile_steps")
+        return [(buf[i].kernel.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)) for i in range(m)]
+
     def last_launch_count(self, device: Optional[int] = None) -> int:
         eng = _Engine.get(_default_device() if device is None else device)
         return int(eng.L.a2m_last_launch_count(eng.h))

@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched model forward on synthetic windows (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One process per GPU (the driver launches N>1 through torch.distributed.run).  A "step" is one batched
+forward of B = 64 windows of 5 s per GPU (weak scaling: windows are independent, no collective).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WINDOW_S = 5.0
+FLOPS_PER_WINDOW = 2 * 3_618_361_856  # de-duplicated forward MACs x 2
+SEED = 1234
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor_sustained": p["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons of one GPU during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_forward_rate(n_windows: int, iters: int, threads: int):
+    """Times the oracle's PyTorch-CPU fp32 restatement (the reference cannot run: JAX absent).
+    Returns (audio-seconds per second, seconds per iteration)."""
+    import torch
+    from oracle import model_torch as T
+    from oracle import params as P
+    from oracle import synth
+    torch.set_num_threads(threads)
+    params = T.to_torch(P.init_params(SEED))
+    audio = torch.tensor(synth.make_windows_fast(n_windows, SEED))
+    with torch.no_grad():
+        T.forward(params, audio[:1])  # warm-up (thread pool, allocator)
+        times = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            T.forward(params, audio)
+            times.append(time.perf_counter() - t0)
+    best = statistics.median(times)
+    return n_windows * WINDOW_S / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The JAX reference cannot be imported
+    (no jax/equinox in the image, /root/reference absent on the GPU box), so this times the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    sample = 4
+    # warm-up + K steps, each a bounded sample of the B-window workload
+    import torch
+    from oracle import model_torch as T
+    from oracle import params as P
+    from oracle import synth
+    torch.set_num_threads(cores)
+    params = T.to_torch(P.init_params(SEED))
+    audio = torch.tensor(synth.make_windows_fast(sample, SEED))
+    with torch.no_grad():
+        for _ in range(min(args.warmup, 2)):
+            T.forward(params, audio)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            T.forward(params, audio)
+        dt = time.perf_counter() - t0
+    value = sample * WINDOW_S * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec transcribed (fwd)", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batched forward of the default model, {args.batch} synthetic 5 s windows per GPU "
+                               f"(configs[1]); CPU arm runs a bounded sample of {sample} windows per step"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} windows per step x {args.steps} steps, PyTorch-CPU fp32 restatement "
+                                   f"(oracle/model_torch.py); JAX reference not installable here"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import audio_to_midi_b200 as A
+    from oracle import synth  # synthetic inputs only (seeded generator); not on the measured path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    model = A.OutputSequenceGenerator(A.model_config, key=SEED)      # random-init weights of the reference architecture
+    rope = A.precompute_frequencies(A.model_config["attention_size"], 300)
+    # inputs: R distinct batches so that consecutive steps read different audio (R * B * 640 KB > 126 MB L2)
+    R = max(2, -(-140_000_000 // (B * 640_000)))
+    host_batches = [synth.make_windows_fast(B, SEED + 17 * (rank * R + r)) for r in range(R)]
+    dev_batches = [torch.tensor(h, device=dev) for h in host_batches]
+    predict = A.vmap(model.predict, in_axes=(None, 0, None))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds plan + CUDA graph)
+    for i in range(max(args.warmup, 3)):
+        predict(None, dev_batches[i % R], rope)
+    torch.cuda.synchronize()
+    launches_per_step = model.last_launch_count(local)
+
+    # ---- device-resident timing: exactly K steps between two events on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            predict(None, dev_batches[i % R], rope)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the sampler alive long enough for at least a few samples under load
+        t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
+        while time.perf_counter() < t_end:
+            predict(None, dev_batches[0], rope)
+        torch.cuda.synchronize()
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * WINDOW_S * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned staging, H2D and D2H inside)
+    for i in range(2):
+        predict(None, host_batches[i % R], rope)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _lg, pr = predict(None, host_batches[i % R], rope)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * WINDOW_S * args.steps / float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from per-launch CUDA-event timings of the same plan
+    peaks = _peaks()
+    prof = model.profile_steps(B, repeats=5, device=local)
+    fam = {}
+    for k, pms, fl, by in prof:
+        f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        f["ms"] += pms; f["flops"] += fl; f["bytes"] += by; f["n"] += 1
+    total_ms = sum(f["ms"] for f in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    name, f = top
+    tensor_bound = name in ("gemm_tc_kernel", "attn_global_kernel")
+    if tensor_bound:
+        achieved = f["flops"] / (f["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tensor_sustained"], "traffic": None}
+    else:
+        achieved = f["bytes"] / (f["ms"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm"], "traffic": None}
+    roof.update({"kernel": name, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
+                 "share_of_step": f["ms"] / total_ms, "peak_source": peaks["src"] + ", sustained bf16 figure",
+                 "flops_per_launch_avg": f["flops"] / f["n"], "bytes_per_launch_avg": f["bytes"] / f["n"],
+                 "whole_step_tflops": B * FLOPS_PER_WINDOW / (ms / args.steps / 1e3) / 1e12,
+                 "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}})
+
+    # ---- CPU baseline on this host (bounded sample)
+    cores = len(os.sched_getaffinity(0))
+    cpu_n, cpu_iters = 8, 3
+    cpu_rate, cpu_s = cpu_forward_rate(cpu_n, cpu_iters, cores)
+
+    line = {
+        "metric": "audio-seconds/sec transcribed (fwd)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"batched forward of the default model, {B} synthetic 5 s windows per GPU "
+                               f"(BASELINE.json configs[1]), random-init weights, windows batch-partitioned across GPUs",
+                   "batch_per_gpu": B, "l2": f"inputs rotated over {R} distinct batches ({R * B * 0.64:.0f} MB > 126 MB L2); "
+                                             "weights and activations stay L2-resident as in steady-state serving",
+                   "accumulate": "fp32", "residual_stream": "fp32", "cuda_graph": True},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * 2 * 80000 * 4 + 2 * 300 * 32 * 4,
+                "d2h_bytes_per_step": 2 * B * 250 * 90 * 4},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu_rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{cpu_n} windows x {cpu_iters} iterations ({cpu_s:.2f} s each), PyTorch-CPU fp32 "
+                                   f"restatement (oracle/model_torch.py); JAX reference not installable (SURVEY F1)"},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="windows per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,18 @@ int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const
 
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
+/* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between
+ * the stem and the decoder GEMM) is run `repeats` times back to back between two CUDA events on the
+ * handle's own stream.  Returns the number of steps written (or, with out == NULL, the number of steps).
+ * flops / bytes are the ALGORITHMIC counts of the launch (2 x MACs; operands in + results out). The
+ * residual stream in the workspace is left in an arbitrary (finite) state. */
+typedef struct {
+  char kernel[32];
+  float ms;
+  double flops;
+  double bytes;
+} A2mStepProfile;
+int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t max_steps, A2mStepProfile* out);
 /* Use a CUDA graph for the steady-state forward (default 1). */
 int a2m_set_use_graph(A2mHandle* h, int32_t enable);
 
