@@ -1,0 +1,158 @@
+"""CPU-side tests of the product's host logic: the C ABI loads and exports what include/a2m.h declares, the
+pytree mirrors the reference layout, modelutil (C++) matches the oracle bit for bit, window sharding, and the
+product refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import audio_to_midi_b200 as A
+from audio_to_midi_b200 import _lib
+from oracle import events as E
+from oracle import params as P
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "a2m.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(a2m_\w+|extract_midi_events|free_midi_events)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} not exported"
+
+
+def test_pytree_matches_reference_layout():
+    m = A.OutputSequenceGenerator(A.model_config, key=1)
+    leaves = m.tree_leaves_with_path()
+    ref = P.flatten(P.init_params(1))
+    assert [p for p, _ in leaves] == list(ref.keys())
+    assert all(np.shape(a) == np.shape(ref[p]) for p, a in leaves)
+    assert sum(np.asarray(a).size for _, a in leaves) == 11_606_269
+    top = [n for n in m._fields]
+    assert top == ["layers", "norm", "transformer_projection", "transformer", "decoder"]      # model.py:673-678
+    with pytest.raises(KeyError):
+        m.load_leaves({"norm.weight": np.ones(256, np.float32)})
+    bad = dict(ref)
+    bad["norm.weight"] = np.ones(255, np.float32)
+    with pytest.raises(ValueError):
+        m.load_leaves(bad)
+
+
+def test_rope_table_matches_oracle():
+    from oracle import model_np as M
+    r = A.precompute_frequencies(64, 300)
+    cos, sin = M.precompute_frequencies(64, 300, dtype=np.float32)
+    assert r.cos_freq.shape == (300, 32) and r.cos_freq.dtype == np.float32
+    assert np.array_equal(r.cos_freq, cos) and np.array_equal(r.sin_freq, sin)
+
+
+def test_modelutil_bit_exact_vs_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "events.npz"))
+    for name, ov in (("ov050", 0.5), ("ov025", 0.25), ("ov000", 0.0)):
+        st = A.modelutil.stitch_probs(g["probs"], ov, 0.02)
+        assert np.array_equal(st, g["stitched_" + name], equal_nan=True)
+        ev = A.modelutil.extract_events(st)
+        assert ev == [tuple(r) for r in g["events_" + name].tolist()]
+        fr = A.modelutil.to_frame_events([ev], st.shape[0])[0]
+        assert np.array_equal(fr, g["frames_" + name])
+
+
+def test_modelutil_edge_cases():
+    assert A.modelutil.extract_events(np.zeros((0, 90), np.float32)) == []
+    assert A.modelutil.extract_events(np.zeros((5, 90), np.float32)) == []
+    one = np.zeros((1, 90), np.float32)
+    one[0, 3] = 0.9
+    assert A.modelutil.extract_events(one) == E.extract_events(one) == [(0, 3, 1, 7)]
+    rng = np.random.Generator(np.random.PCG64(3))
+    for frames in (2, 7, 13, 64):
+        p = rng.uniform(size=(frames, 90)).astype(np.float32)
+        assert A.modelutil.extract_events(p) == E.extract_events(p)
+    w1 = rng.uniform(size=(1, 250, 90)).astype(np.float32)
+    assert np.array_equal(A.modelutil.stitch_probs(w1, 0.5, 0.02), w1[0])
+    assert A.modelutil.to_frame_events([[]], 10)[0].sum() == 0
+    with pytest.raises(ValueError):
+        A.modelutil.to_frame_events([[(0, 90, 5, 7)]], 10)
+
+
+def test_ios_c_abi_f16_strided():
+    """extract_midi_events (cbinds.rs:51-91): f16 data, strides in elements, stitch then extract."""
+    L = _lib.lib()
+    rng = np.random.Generator(np.random.PCG64(8))
+    probs = rng.uniform(size=(3, 250, 90)).astype(np.float16)
+    padded = np.zeros((3, 250, 96), np.float16)          # non-contiguous rows: stride 96 elements
+    padded[:, :, :90] = probs
+    w = _lib.MLMultiArrayWrapper3()
+    w.strides[:] = [250 * 96, 96, 1]
+    w.dims[:] = [3, 250, 90]
+    w.data = padded.ctypes.data
+    lst = L.extract_midi_events(w, 0.5, 0.02)
+    got = [(lst.contents.ptr[i].attack_time, lst.contents.ptr[i].note, lst.contents.ptr[i].duration,
+            lst.contents.ptr[i].velocity) for i in range(lst.contents.length)]
+    L.free_midi_events(lst)
+    L.free_midi_events(None)                              # null is tolerated (cbinds.rs:82)
+    want = E.extract_events(E.stitch_probs(probs.astype(np.float32), 0.5, 0.02))
+    assert got == want
+    assert C.sizeof(_lib.MidiEvent) == 32                 # #[repr(C)] {u64, u8, u64, u8}
+
+
+def test_slice_and_shard():
+    clip = np.zeros((2, 9_600_000), np.float32)
+    w, dur = A.slice_windows(clip, overlap=0.5)
+    assert w.shape == (134, 2, 80000) and dur == 5.0
+    ref = E.slice_windows(np.arange(2 * 200_000, dtype=np.float32).reshape(2, -1), overlap=0.25)
+    got, _ = A.slice_windows(np.arange(2 * 200_000, dtype=np.float32).reshape(2, -1), overlap=0.25)
+    assert np.array_equal(ref, got)
+    for n, ws in ((134, 8), (127, 8), (5, 8), (64, 4), (1, 2)):
+        blocks = [A.shard_windows(n, ws, r) for r in range(ws)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_no_cpu_fallback():
+    """Without an sm_100 device the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = A.OutputSequenceGenerator(A.model_config, key=1)
+    with pytest.raises(_lib.A2mError):
+        m.predict(None, np.zeros((1, 2, 80000), np.float32), A.precompute_frequencies(64, 300))
+    with pytest.raises(NotImplementedError):
+        m(np.zeros((2, 80000), np.float32), None, A.precompute_frequencies(64, 300), key=1, enable_dropout=True)
+    with pytest.raises(ValueError):
+        m.predict(None, np.zeros((2, 1000), np.float32), A.precompute_frequencies(64, 300))
+
+
+def _shard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 37
+    a, b = A.shard_windows(n, world, rank)
+    mine = torch.zeros(n)
+    mine[a:b] = torch.arange(a, b, dtype=torch.float32) + 1      # stand-in for per-window results
+    dist.all_reduce(mine)                                        # gather-by-sum: every window owned exactly once
+    q.put((rank, mine.tolist()))
+    dist.destroy_process_group()
+
+
+def test_window_sharding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for _, vals in res:
+        assert vals == [float(i + 1) for i in range(37)]
