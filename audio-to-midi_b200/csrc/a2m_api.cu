@@ -18,6 +18,7 @@
 
 #include "../../include/a2m.h"
 #include "attention.cuh"
+#include "block_fused.cuh"
 #include "cnn_kernels.cuh"
 #include "gemm_tc.cuh"
 
@@ -86,6 +87,8 @@ struct BigBlockW {   // Block with C >= 64 (tensor-core path)
   size_t w1, b1;     // bf16 [2C, C], fp32 [2C]
   size_t w2, b2;     // bf16 [C, 2C], fp32 [C]
   size_t gamma;      // fp32 [C]
+  size_t fused;      // fp32: dw[7][C] | dwb[C] | lnw[C] | lnb[C] | b1[2C] | gamma*b2[C]   (block_fused_kernel)
+  size_t w2g;        // bf16 [C, 2C] = gamma[c] * point_conv_2[c, :]
 };
 struct BigDownW {
   size_t lnw, lnb;   // fp32 [Cin]
@@ -269,6 +272,8 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc_kernel<128, GEMM_ROPE>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc_kernel<128, GEMM_DECODER>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<64>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<128>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
   if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -407,6 +412,16 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
         bw.w2 = ar->put_bf16(vec(w2));
         bw.b2 = ar->put_f32(vec(b2));
         bw.gamma = ar->put_f32(vec(gm));
+        // fused-kernel image: layer scale folded into point_conv_2 (out = x + (gamma*W2) h + gamma*b2)
+        std::vector<float> fimg = img, w2g(static_cast<size_t>(C) * H), b2g(C);
+        { auto v1 = vec(b1); fimg.insert(fimg.end(), v1.begin(), v1.end()); }
+        for (int c = 0; c < C; ++c) {
+          b2g[c] = gm.p[c] * b2.p[c];
+          for (int hh = 0; hh < H; ++hh) w2g[static_cast<size_t>(c) * H + hh] = gm.p[c] * w2.p[static_cast<size_t>(c) * H + hh];
+        }
+        fimg.insert(fimg.end(), b2g.begin(), b2g.end());
+        bw.fused = ar->put_f32(fimg);
+        bw.w2g = ar->put_bf16(w2g);
       }
     }
   }
@@ -580,6 +595,28 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
           case 2: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<16>(in, out, L, M, prm, st); }, label, out, te); break;
           default: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<32>(in, out, L, M, prm, st); }, label, out, te); break;
         }
+        cur ^= 1;
+      } else if (C <= 128) {
+        // fused Block: dwconv + LN + pw1 + GELU + pw2 + layer scale + residual in one launch (block_fused.cuh)
+        const BigBlockW& bw = w.big_block[s][j];
+        const float* in = ws.X[cur];
+        float* out = ws.X[cur ^ 1];
+        const float* prm = dev_ptr<float>(h, bw.fused);
+        CUtensorMap t1, t2;
+        if (!make_tmap(h, &t1, dev_ptr<__nv_bfloat16>(h, bw.w1), 2 * C, C, C, 64, 2 * C)) return false;
+        if (!make_tmap(h, &t2, dev_ptr<__nv_bfloat16>(h, bw.w2g), C, 2 * C, 2 * C, 64, C)) return false;
+        const Meta mf{"block_fused_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C + 8.0 * C * C};
+        const int tiles = (M + FB_TOK - 1) / FB_TOK;
+        if (C == 64)
+          add_step(p, mf, [=](cudaStream_t st) {
+            block_fused_kernel<64><<<tiles, FB_THREADS, FusedBlockCfg<64>::SMEM, st>>>(t1, t2, in, out, L, M, prm);
+            return cudaGetLastError();
+          }, label, out, static_cast<size_t>(M) * C);
+        else
+          add_step(p, mf, [=](cudaStream_t st) {
+            block_fused_kernel<128><<<tiles, FB_THREADS, FusedBlockCfg<128>::SMEM, st>>>(t1, t2, in, out, L, M, prm);
+            return cudaGetLastError();
+          }, label, out, static_cast<size_t>(M) * C);
         cur ^= 1;
       } else {
         const BigBlockW& bw = w.big_block[s][j];

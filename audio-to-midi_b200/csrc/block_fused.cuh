@@ -1,0 +1,278 @@
+// One whole ConvNeXt Block (model.py:160-167) per launch for C in {64, 128}:
+//     out = x + gamma * pw2( gelu( pw1( LN( dwconv7(x) ) ) ) )
+// on one tile of 128 tokens per CTA, everything between the first read of x and the final store on chip:
+//
+//   phase 1  CUDA cores   depthwise k7 + LayerNorm, one warp per token (register ring over rows, shuffles),
+//                         written as the bf16 A operand straight into the 128B-swizzled UMMA layout in smem
+//   phase 2  tcgen05      D1[128 x 2C] = A1 . W1^T           (W1 TMA-staged while phase 1 runs)
+//   phase 3  CUDA cores   bias + GELU(tanh) out of TMEM -> bf16 A2 in smem (overwrites A1)
+//                         (W2, pre-scaled by gamma, is TMA-staged into W1's slot meanwhile)
+//   phase 4  tcgen05      D2[128 x C] = A2 . (gamma*W2)^T
+//   phase 5  CUDA cores   + gamma*b2, staged through smem, then coalesced  out = stage + x
+//
+// HBM/L2 traffic per tile: x in (fp32, once + 6 halo rows), out (fp32, once), weights (bf16, 2*2C*C).
+// Replaces three launches (dwconv_ln_kernel + two gemm_tc_kernel) and the bf16 A16/H16 round trips.
+#pragma once
+#include "cnn_kernels.cuh"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace a2m {
+
+constexpr int FB_THREADS = 512;  // 16 warps
+constexpr int FB_TOK = 128;
+
+template <int C>
+struct FusedBlockCfg {
+  static constexpr int H = 2 * C;
+  static constexpr int KB1 = C / 64;
+  static constexpr int KB2 = H / 64;
+  static constexpr int A_BYTES = FB_TOK * H * 2;   // A1 (128 x C) then A2 (128 x H)
+  static constexpr int W_BYTES = H * C * 2;        // W1 [H, C] then W2' [C, H]
+  static constexpr int STAGE_STRIDE = C + 4;       // floats; conflict-free float4 rows
+  static constexpr int STAGE_BYTES = FB_TOK * STAGE_STRIDE * 4;
+  static constexpr int MAIN_BYTES = (A_BYTES + W_BYTES > STAGE_BYTES) ? A_BYTES + W_BYTES : STAGE_BYTES;
+  static constexpr int AUX_BYTES = (H + C) * 4 + 64;  // b1, b2', barriers, tmem slot
+  static constexpr size_t SMEM = 1024 + MAIN_BYTES + AUX_BYTES;
+  static constexpr uint32_t TMEM_COLS = (H + C <= 256) ? 256 : 512;
+};
+
+// Packed fp32 parameters: dw[7][C] | dwb[C] | lnw[C] | lnb[C] | b1[H] | b2g[C] (= gamma * b2)
+template <int C>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                   const float* __restrict__ X, float* __restrict__ Y, int L, int M, const float* __restrict__ params) {
+  using Cfg = FusedBlockCfg<C>;
+  using RM = RowMap<C>;
+  constexpr int H = Cfg::H;
+  constexpr int PER = RM::PER;
+  static_assert(RM::G == 1, "one vector of channels per lane");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + Cfg::A_BYTES;
+  float* sStage = reinterpret_cast<float*>(smem);  // aliases sA/sW after MMA2 has completed
+  float* sB1 = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES);
+  float* sB2 = sB1 + H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + C);
+  uint64_t* bar_w1 = bars;
+  uint64_t* bar_d1 = bars + 1;
+  uint64_t* bar_w2 = bars + 2;
+  uint64_t* bar_d2 = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile0 = blockIdx.x * FB_TOK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(bar_w1, 1);
+    mbar_init(bar_d1, 1);
+    mbar_init(bar_w2, 1);
+    mbar_init(bar_d2, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_w1, Cfg::W_BYTES);
+#pragma unroll
+    for (int kb = 0; kb < Cfg::KB1; ++kb) tma_load_2d(sW + kb * (H * 128), &tmW1, bar_w1, kb * 64, 0);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < H + C; i += FB_THREADS) sB1[i] = __ldg(params + 10 * C + i);
+
+  // ---------------------------------------------------------------- phase 1: dwconv7 + LN -> A1
+  {
+    float w[7][PER], bias[PER], lw[PER], lb[PER];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) RM::load(params + t * C, lane, w[t]);
+    RM::load(params + 7 * C, lane, bias);
+    RM::load(params + 8 * C, lane, lw);
+    RM::load(params + 9 * C, lane, lb);
+    constexpr int TPW = FB_TOK / (FB_THREADS / 32);  // 8 consecutive tokens per warp
+    const int r0 = warp * TPW;                       // first row (within the tile) of this warp
+    float rows[TPW + 6][PER];                        // rows r0-3 .. r0+TPW+2 of x (this lane's channels)
+#pragma unroll
+    for (int i = 0; i < TPW + 6; ++i) {
+      const int g = tile0 + r0 - 3 + i;
+      if (g >= 0 && g < M) {
+        RM::load(X + static_cast<size_t>(g) * C, lane, rows[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) rows[i][j] = 0.f;
+      }
+    }
+    const int col = RM::chan(lane, 0);
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      const int r = r0 + i;
+      const int tok = tile0 + r;
+      const int l = tok % L;
+      float y[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) y[j] = bias[j];
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int ll = l + t - 3;
+        if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < PER; ++j) y[j] = fmaf(w[t][j], rows[i + t][j], y[j]);
+        }
+      }
+      RM::layer_norm(y, lw, lb);
+      if (tok >= M) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) y[j] = 0.f;
+      }
+      uint8_t* dst = sA + (col >> 6) * (FB_TOK * 128) + sw128_offset(r, col & 63);
+      if constexpr (PER == 4) {
+        uint2 q;
+        q.x = pack_bf16x2(y[0], y[1]);
+        q.y = pack_bf16x2(y[2], y[3]);
+        *reinterpret_cast<uint2*>(dst) = q;
+      } else {
+        *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[0], y[1]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d1 = tmem_base;
+  const uint32_t tmem_d2 = tmem_base + H;
+
+  // ---------------------------------------------------------------- phase 2: D1 = A1 . W1^T
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_w1, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, H);
+#pragma unroll
+    for (int kb = 0; kb < Cfg::KB1; ++kb) {
+      const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * (FB_TOK * 128)));
+      const uint64_t db = umma_desc_sw128(smem_u32(sW + kb * (H * 128)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_d1, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc1, (kb | k) != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_d1);
+  }
+  __syncwarp();
+  mbar_wait(bar_d1, 0);
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    // MMA1 has finished reading A1 and W1: stage gamma-scaled W2 into W1's slot while the GELU phase runs
+    mbar_arrive_expect_tx(bar_w2, Cfg::W_BYTES);
+#pragma unroll
+    for (int kb = 0; kb < Cfg::KB2; ++kb) tma_load_2d(sW + kb * (C * 128), &tmW2, bar_w2, kb * 64, 0);
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- phase 3: A2 = bf16(gelu(D1 + b1))
+  const int quad = warp & 3;        // TMEM lanes 32*quad .. +31
+  const int cg = warp >> 2;         // column group 0..3
+  const int row = quad * 32 + lane;
+  const uint32_t t_row = static_cast<uint32_t>(quad * 32) << 16;
+  {
+    constexpr int COLS = H / 4;     // 64 (C = 128) or 32 (C = 64)
+#pragma unroll
+    for (int c = 0; c < COLS / 32; ++c) {
+      const int col0 = cg * COLS + c * 32;
+      uint32_t r[32];
+      tmem_ld_x32(tmem_d1 + t_row + col0, r);
+      tmem_ld_wait();
+      uint8_t* base = sA + (col0 >> 6) * (FB_TOK * 128);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(__uint_as_float(r[8 * q + j]) + sB1[col0 + 8 * q + j]);
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(base + sw128_offset(row, (col0 & 63) + 8 * q)) = o;
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 4: D2 = A2 . W2'^T
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_w2, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc2 = umma_idesc_bf16(128, C);
+#pragma unroll
+    for (int kb = 0; kb < Cfg::KB2; ++kb) {
+      const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * (FB_TOK * 128)));
+      const uint64_t db = umma_desc_sw128(smem_u32(sW + kb * (C * 128)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_d2, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc2, (kb | k) != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_d2);
+  }
+  __syncwarp();
+  mbar_wait(bar_d2, 0);
+  tc_fence_after();
+
+  // ---------------------------------------------------------------- phase 5: stage (D2 + b2'), then out = stage + x
+  {
+    constexpr int COLS = C / 4;  // 32 (C = 128) or 16 (C = 64)
+    const int col0 = cg * COLS;
+    float* srow = sStage + row * Cfg::STAGE_STRIDE + col0;
+    if constexpr (COLS == 32) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_d2 + t_row + col0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        reinterpret_cast<float4*>(srow)[q] =
+            make_float4(__uint_as_float(r[4 * q]) + sB2[col0 + 4 * q], __uint_as_float(r[4 * q + 1]) + sB2[col0 + 4 * q + 1],
+                        __uint_as_float(r[4 * q + 2]) + sB2[col0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + sB2[col0 + 4 * q + 3]);
+    } else {
+      uint32_t r[16];
+      tmem_ld_x16(tmem_d2 + t_row + col0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(srow)[q] =
+            make_float4(__uint_as_float(r[4 * q]) + sB2[col0 + 4 * q], __uint_as_float(r[4 * q + 1]) + sB2[col0 + 4 * q + 1],
+                        __uint_as_float(r[4 * q + 2]) + sB2[col0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + sB2[col0 + 4 * q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  {
+    // coalesced residual add: each warp owns rows warp, warp+16, ...; lanes span the channels
+    constexpr int RPW = FB_TOK / (FB_THREADS / 32);  // 8 rows per warp
+    float xv[RPW][PER];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int tok = tile0 + warp + i * (FB_THREADS / 32);
+      if (tok < M) RM::load(X + static_cast<size_t>(tok) * C, lane, xv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = warp + i * (FB_THREADS / 32);
+      const int tok = tile0 + r;
+      if (tok < M) {
+        float sv[PER];
+        RM::load(sStage + r * Cfg::STAGE_STRIDE, lane, sv);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) sv[j] += xv[i][j];
+        RM::store_f32(Y + static_cast<size_t>(tok) * C, lane, sv);
+      }
+    }
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace a2m
