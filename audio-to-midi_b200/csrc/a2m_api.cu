@@ -21,6 +21,7 @@
 #include "block_fused.cuh"
 #include "cnn_kernels.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 using namespace a2m;
 
@@ -185,6 +186,7 @@ struct A2mHandle {
   size_t own_ws_bytes = 0;
   std::vector<std::unique_ptr<Plan>> plans;
   bool use_graph = true;
+  bool use_gemm2 = true;   // TMA-staged epilogue GEMM (gemm_tc2.cuh); false = first-generation kernel (debug)
   int last_launches = 0;
   // host staging for a2m_forward_host
   float* pin_audio = nullptr;
@@ -205,15 +207,14 @@ T* dev_ptr(const A2mHandle* h, size_t off) {
 }
 
 // ------------------------------------------------------------------------------------------ tensor maps
-bool make_tmap(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-               uint32_t box_cols, uint32_t box_rows) {
+bool make_tmap_t(A2mHandle* h, CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t rows,
+                 uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * static_cast<uint64_t>(esize)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = h->encode(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     std::snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u base=%p",
@@ -223,6 +224,15 @@ bool make_tmap(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, ui
     return false;
   }
   return true;
+}
+// bf16 [rows, cols] row-major (row stride ld_elems), 128-byte swizzled boxes of box_cols x box_rows
+bool make_tmap(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+               uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_t(h, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_cols, box_rows);
+}
+bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                   uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_t(h, m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, ld_elems, box_cols, box_rows);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -251,6 +261,63 @@ cudaError_t launch_gemm(int BN, int mode, const CUtensorMap& a, const CUtensorMa
   }
 }
 
+template <int BN, int MODE, bool RESID>
+cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int num_sms,
+                           cudaStream_t s) {
+  const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
+  gemm_tc2_kernel<BN, MODE, RESID><<<std::min(tiles, num_sms), G2_THREADS, gemm2_smem_bytes<BN>(), s>>>(a, b, c, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm2(int BN, int mode, bool resid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                         const GemmArgs& g, int num_sms, cudaStream_t s) {
+  if (g.N % BN != 0 || g.K % GEMM_BK != 0 || g.M <= 0 || g.N > G2_MAXN) return cudaErrorInvalidValue;
+  switch (mode * 10000 + BN * 10 + (resid ? 1 : 0)) {
+    case G2_F32 * 10000 + 640: return launch_gemm2_t<64, G2_F32, false>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 641: return launch_gemm2_t<64, G2_F32, true>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 1280: return launch_gemm2_t<128, G2_F32, false>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 1281: return launch_gemm2_t<128, G2_F32, true>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 2560: return launch_gemm2_t<256, G2_F32, false>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 2561: return launch_gemm2_t<256, G2_F32, true>(a, b, c, g, num_sms, s);
+    case G2_BF16 * 10000 + 640: return launch_gemm2_t<64, G2_BF16, false>(a, b, c, g, num_sms, s);
+    case G2_BF16 * 10000 + 1280: return launch_gemm2_t<128, G2_BF16, false>(a, b, c, g, num_sms, s);
+    case G2_BF16 * 10000 + 2560: return launch_gemm2_t<256, G2_BF16, false>(a, b, c, g, num_sms, s);
+    case G2_GLU * 10000 + 2560: return launch_gemm2_t<256, G2_GLU, false>(a, b, c, g, num_sms, s);
+    case G2_ROPE * 10000 + 640: return launch_gemm2_t<64, G2_ROPE, false>(a, b, c, g, num_sms, s);
+    case G2_ROPE * 10000 + 1280: return launch_gemm2_t<128, G2_ROPE, false>(a, b, c, g, num_sms, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Chooses the v2 kernel (TMA-staged epilogue) for a GemmArgs; returns false if only gemm_tc_kernel can serve it.
+bool gemm2_route(A2mHandle* h, int mode, const GemmArgs& g, int* mode2, bool* resid, CUtensorMap* tc) {
+  *resid = false;
+  if (g.N > G2_MAXN) return false;
+  if (mode == GEMM_GENERIC) {
+    const bool o32 = g.flags & GF_OUT32, o16 = g.flags & GF_OUT16;
+    if (o32 == o16) return false;
+    if (o32) {
+      if ((g.flags & GF_RESID) && (g.resid != g.out32 || g.ldr != g.ld32)) return false;
+      *mode2 = G2_F32;
+      *resid = (g.flags & GF_RESID) != 0;
+      return make_tmap_f32(h, tc, g.out32, g.M, g.N, g.ld32, 32, 128);
+    }
+    if (g.flags & (GF_GAMMA | GF_RESID)) return false;
+    *mode2 = G2_BF16;
+    return make_tmap(h, tc, g.out16, g.M, g.N, g.ld16, 64, 128);
+  }
+  if (mode == GEMM_GLU) {
+    *mode2 = G2_GLU;
+    return make_tmap(h, tc, g.out16, g.M, g.N / 2, g.ld16, 64, 128);
+  }
+  if (mode == GEMM_ROPE) {
+    *mode2 = G2_ROPE;
+    const int cols = (g.vt_out != nullptr && g.vt_col0 < g.N) ? g.vt_col0 : g.N;
+    return make_tmap(h, tc, g.out16, g.M, cols, g.ld16, 64, 128);
+  }
+  return false;
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
@@ -271,6 +338,18 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc_kernel<64, GEMM_ROPE>, gemm_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc_kernel<128, GEMM_ROPE>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc_kernel<128, GEMM_DECODER>, gemm_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<64, G2_F32, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<64, G2_F32, true>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<128, G2_F32, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<128, G2_F32, true>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<256, G2_F32, false>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<256, G2_F32, true>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<64, G2_BF16, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<128, G2_BF16, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<256, G2_BF16, false>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<256, G2_GLU, false>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<64, G2_ROPE, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -521,7 +600,15 @@ bool add_gemm(A2mHandle* h, Plan* p, int BN, int mode, const __nv_bfloat16* A, i
     }
     st.bytes = 2.0 * g.M * g.K + 2.0 * g.N * g.K + out_b * g.M * out_cols;
   }
-  st.run = [=](cudaStream_t s) { return launch_gemm(BN, mode, ta, tb, g, sms, s); };
+  int mode2 = 0;
+  bool resid = false;
+  CUtensorMap tc;
+  if (h->use_gemm2 && gemm2_route(h, mode, g, &mode2, &resid, &tc)) {
+    st.kernel = "gemm_tc2_kernel";
+    st.run = [=](cudaStream_t s) { return launch_gemm2(BN, mode2, resid, ta, tb, tc, g, sms, s); };
+  } else {
+    st.run = [=](cudaStream_t s) { return launch_gemm(BN, mode, ta, tb, g, sms, s); };
+  }
   p->steps.push_back(std::move(st));
   return true;
 }
@@ -1069,7 +1156,21 @@ int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t 
   g.resid = resid; g.ldr = N;
   g.out32 = out32; g.ld32 = N;
   g.out16 = static_cast<__nv_bfloat16*>(out16); g.ld16 = N;
-  CUDA_TRY(launch_gemm(block_n, GEMM_GENERIC, ta, tb, g, h->num_sms, static_cast<cudaStream_t>(stream)));
+  int mode2 = 0;
+  bool resid_inplace = false;
+  CUtensorMap tc;
+  GemmArgs g2 = g;
+  if ((flags & GF_RESID) && (flags & GF_OUT32) && !(flags & GF_OUT16) && h->use_gemm2) {
+    // the production kernel adds the residual in place: seed the output with it
+    CUDA_TRY(cudaMemcpyAsync(out32, resid, sizeof(float) * static_cast<size_t>(M) * N, cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+    g2.resid = out32;
+  }
+  if (h->use_gemm2 && gemm2_route(h, GEMM_GENERIC, g2, &mode2, &resid_inplace, &tc)) {
+    CUDA_TRY(launch_gemm2(block_n, mode2, resid_inplace, ta, tb, tc, g2, h->num_sms, static_cast<cudaStream_t>(stream)));
+  } else {
+    CUDA_TRY(launch_gemm(block_n, GEMM_GENERIC, ta, tb, g, h->num_sms, static_cast<cudaStream_t>(stream)));
+  }
   return A2M_OK;
 }
 
