@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -186,6 +187,7 @@ struct A2mHandle {
   size_t own_ws_bytes = 0;
   std::vector<std::unique_ptr<Plan>> plans;
   bool use_graph = true;
+  bool use_pdl = true;     // programmatic dependent launch between the kernels of the plan
   bool use_gemm2 = true;   // TMA-staged epilogue GEMM (gemm_tc2.cuh); false = first-generation kernel (debug)
   int last_launches = 0;
   // host staging for a2m_forward_host
@@ -236,14 +238,36 @@ bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows
 }
 
 // ------------------------------------------------------------------------------------------ launchers
+// Launch helper: with tl_pdl set, the launch opts into programmatic dependent launch (the kernel's prologue may
+// overlap the tail of its predecessor; every kernel calls griddepcontrol.wait before touching activations).
+static thread_local bool tl_pdl = false;
+// bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
+static unsigned g_pdl_mask = 0xffffffffu;
+enum PdlFamily { PF_SMALL = 0, PF_LN = 1, PF_GEMM = 2, PF_FUSED = 3, PF_ATTN = 4 };
+
+template <class... KArgs, class... Args>
+cudaError_t launch_k(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (tl_pdl && ((g_pdl_mask >> family) & 1u)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int BN, int MODE>
 cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int num_sms, cudaStream_t s) {
   constexpr size_t smem = gemm_smem_bytes<BN>();
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
   const int per_sm = (smem * 2 + 2048 <= 227 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;
   const int grid = std::min(tiles, num_sms * per_sm);
-  gemm_tc_kernel<BN, MODE><<<grid, GEMM_THREADS, smem, s>>>(a, b, g);
-  return cudaGetLastError();
+  return launch_k(PF_GEMM, gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(GEMM_THREADS), smem, s, a, b, g);
 }
 
 cudaError_t launch_gemm(int BN, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int num_sms,
@@ -265,8 +289,8 @@ template <int BN, int MODE, bool RESID>
 cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int num_sms,
                            cudaStream_t s) {
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
-  gemm_tc2_kernel<BN, MODE, RESID><<<std::min(tiles, num_sms), G2_THREADS, gemm2_smem_bytes<BN>(), s>>>(a, b, c, g);
-  return cudaGetLastError();
+  return launch_k(PF_GEMM, gemm_tc2_kernel<BN, MODE, RESID>, dim3(std::min(tiles, num_sms)), dim3(G2_THREADS),
+                  gemm2_smem_bytes<BN>(), s, a, b, c, g);
 }
 
 cudaError_t launch_gemm2(int BN, int mode, bool resid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
@@ -360,25 +384,23 @@ cudaError_t configure_kernels() {
 
 template <int C>
 cudaError_t launch_small_block(const float* in, float* out, int L, int M, const float* params, cudaStream_t s) {
-  block_small_kernel<C><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, small_block_smem<C>(), s>>>(in, out, L, M, params);
-  return cudaGetLastError();
+  return launch_k(PF_SMALL, block_small_kernel<C>, dim3((M + SB_TOK - 1) / SB_TOK), dim3(SB_TOK), small_block_smem<C>(), s, in, out, L,
+                  M, params);
 }
 template <int CIN>
 cudaError_t launch_small_down(const float* in, float* out, int M_out, const float* params, cudaStream_t s) {
-  downsample_small_kernel<CIN>
-      <<<(M_out + 127) / 128, 128, SmallDownLayout<CIN>::TOTAL * sizeof(float), s>>>(in, out, M_out, params);
-  return cudaGetLastError();
+  return launch_k(PF_SMALL, downsample_small_kernel<CIN>, dim3((M_out + 127) / 128), dim3(128),
+                  SmallDownLayout<CIN>::TOTAL * sizeof(float), s, in, out, M_out, params);
 }
 template <int C>
 cudaError_t launch_dwln(const float* X, __nv_bfloat16* A, int L, int M, const float* params, cudaStream_t s) {
-  dwconv_ln_kernel<C><<<(M + DW_TOK - 1) / DW_TOK, DW_THREADS, (DW_TOK + 6) * C * sizeof(float), s>>>(X, A, L, M, params);
-  return cudaGetLastError();
+  return launch_k(PF_LN, dwconv_ln_kernel<C>, dim3((M + DW_TOK - 1) / DW_TOK), dim3(DW_THREADS), (DW_TOK + 6) * C * sizeof(float), s,
+                  X, A, L, M, params);
 }
 template <int C>
 cudaError_t launch_ln(const float* X, int rows, int Lin, int Lout, const float* w, const float* b,
                       __nv_bfloat16* o16, float* o32, cudaStream_t s) {
-  ln_rows_kernel<C><<<(rows + 7) / 8, 256, 0, s>>>(X, rows, Lin, Lout, w, b, o16, o32);
-  return cudaGetLastError();
+  return launch_k(PF_LN, ln_rows_kernel<C>, dim3((rows + 7) / 8), dim3(256), 0, s, X, rows, Lin, Lout, w, b, o16, o32);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -696,13 +718,11 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         const int tiles = (M + FB_TOK - 1) / FB_TOK;
         if (C == 64)
           add_step(p, mf, [=](cudaStream_t st) {
-            block_fused_kernel<64><<<tiles, FB_THREADS, FusedBlockCfg<64>::SMEM, st>>>(t1, t2, in, out, L, M, prm);
-            return cudaGetLastError();
+            return launch_k(PF_FUSED, block_fused_kernel<64>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<64>::SMEM, st, t1, t2, in, out, L, M, prm);
           }, label, out, static_cast<size_t>(M) * C);
         else
           add_step(p, mf, [=](cudaStream_t st) {
-            block_fused_kernel<128><<<tiles, FB_THREADS, FusedBlockCfg<128>::SMEM, st>>>(t1, t2, in, out, L, M, prm);
-            return cudaGetLastError();
+            return launch_k(PF_FUSED, block_fused_kernel<128>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<128>::SMEM, st, t1, t2, in, out, L, M, prm);
           }, label, out, static_cast<size_t>(M) * C);
         cur ^= 1;
       } else {
@@ -763,9 +783,8 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       const int total_warps = B * ATT_HEADS * 32;
       // as written in the reference: 31 windows x 4 heads x (QK^T + PV) of 16 x 16 x 64
       add_step(p, Meta{"attn_local_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * (256 + 512 + 256)}, [=](cudaStream_t st) {
-        attn_local_kernel<<<(total_warps + AL_WARPS - 1) / AL_WARPS, AL_WARPS * 32, 0, st>>>(
-            qc, kQC, kv, kv + 256, kKV, o16, kD, rope_cos, rope_sin, total_warps);
-        return cudaGetLastError();
+        return launch_k(PF_ATTN, attn_local_kernel, dim3((total_warps + AL_WARPS - 1) / AL_WARPS), dim3(AL_WARPS * 32), 0, st, qc, kQC, kv,
+                        kv + 256, kKV, o16, kD, rope_cos, rope_sin, total_warps);
       });
     } else {
       GemmArgs g = gemm_args(Mt, kQC, kD);
@@ -776,15 +795,14 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       GemmArgs g2 = gemm_args(Mt, kKV, 64);
       g2.out16 = kv; g2.ld16 = kKV;
       g2.rope_cos = rope_cos; g2.rope_sin = rope_sin; g2.rope_cols = 256; g2.rows_per_window = kTP;
-      g2.vt_out = vt; g2.vt_col0 = 256;
+      g2.vt_out = nullptr; g2.vt_col0 = 1 << 30;
       if (!add_gemm(h, p, 128, GEMM_ROPE, qc + 256, kQC, t.wkv, g2)) return false;
       CUtensorMap tq, tk, tv;
       if (!make_tmap(h, &tq, qc, Mt, 256, kQC, 64, 128)) return false;
       if (!make_tmap(h, &tk, kv, Mt, 256, kKV, 64, 256)) return false;
-      if (!make_tmap(h, &tv, vt, static_cast<uint64_t>(B) * ATT_HEADS * ATT_HD, kTP, kTP, 64, 64)) return false;
+      if (!make_tmap(h, &tv, kv, Mt, kKV, kKV, 64, 256)) return false;   // V = columns 256..511, row-major [key][d]
       add_step(p, Meta{"attn_global_kernel", 2.0 * B * ATT_HEADS * (2.0 * kT * kT * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
-        attn_global_kernel<<<dim3(2, ATT_HEADS, B), AG_THREADS, AG_SMEM, st>>>(tq, tk, tv, o16, kD);
-        return cudaGetLastError();
+        return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256);
       });
     }
     {
@@ -889,6 +907,10 @@ int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, co
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
+  struct PdlScope {
+    explicit PdlScope(bool on) { tl_pdl = on; }
+    ~PdlScope() { tl_pdl = false; }
+  } pdl_scope(h->use_pdl);
   if (tap_label) {
     bool found = false;
     for (auto& st : p->steps) {
@@ -931,6 +953,7 @@ int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, co
     for (auto& st : p->steps) CUDA_TRY(st.run(stream));
   }
   launches += static_cast<int>(p->steps.size());
+  tl_pdl = false;  // the decoder GEMM writes caller buffers: plain stream order
   {
     GemmArgs g = gemm_args(B * kTP, 128, kD);
     g.bias = dev_ptr<float>(h, h->w.db);
@@ -972,6 +995,9 @@ int a2m_create(int device, A2mHandle** out) {
   CUDA_TRY(cudaMalloc(&h->rope_dev, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
   CUDA_TRY(cudaMemset(h->rope_dev, 0, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  if (const char* e = std::getenv("A2M_PDL")) h->use_pdl = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_PDL_MASK")) g_pdl_mask = static_cast<unsigned>(std::strtoul(e, nullptr, 0));
+  if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   return A2M_OK;
 }
 
@@ -1114,6 +1140,10 @@ int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t 
   const int n = static_cast<int>(p->steps.size());
   if (!out) return n;
   cudaStream_t s = h->own_stream;
+  struct PdlScope {
+    explicit PdlScope(bool on) { tl_pdl = on; }
+    ~PdlScope() { tl_pdl = false; }
+  } pdl_scope(h->use_pdl);
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));

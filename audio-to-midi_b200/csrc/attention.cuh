@@ -22,22 +22,23 @@ constexpr int ATT_HEADS = 4;
 constexpr int AG_THREADS = 128;
 constexpr int AG_SQ = 128 * 64 * 2;       // 16 KB
 constexpr int AG_SK = 256 * 64 * 2;       // 32 KB
-constexpr int AG_SV = 4 * 64 * 64 * 2;    // 32 KB: 4 k-blocks of V^T [64 d x 64 pos]
-constexpr int AG_SP = 4 * 128 * 64 * 2;   // 64 KB: 4 k-blocks of P [128 q x 64 keys]
-constexpr size_t AG_SMEM = 1024 + AG_SQ + AG_SK + AG_SV + AG_SP + 128;
+constexpr int AG_SV = 256 * 64 * 2;       // 32 KB: V[key][d], MN-major B operand of P.V
+constexpr int AG_SP = 4 * 128 * 64 * 2;   // 64 KB: 4 k-blocks of P [128 q x 64 keys]; ALIASES Q and K (dead after S)
+constexpr size_t AG_SMEM = 1024 + AG_SP + AG_SV + 128;   // ~98 KB -> two CTAs per SM
+constexpr uint32_t AG_TMEM_COLS = 256;    // S: 256 columns; O re-uses columns 0..63 once S has been consumed
 
-// grid = (2 m-tiles, heads, B).  tmQ: [B*256, ldq] box {64,128}; tmK: [B*256, 256] box {64,256};
-// tmV: V^T as [B*heads*64, 256] box {64,64}.
-__global__ void __launch_bounds__(AG_THREADS, 1)
+// grid = (2 m-tiles, heads, B).  tmQ: Q  [B*256, ldq] box {64,128}; tmK: K [B*256, ldkv] box {64,256};
+// tmV: V [B*256, ldkv] (columns 256 + h*64 ..) box {64,256}.  Q and K arrive RoPE-rotated (GEMM epilogue).
+__global__ void __launch_bounds__(AG_THREADS, 2)
 attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo) {
+                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int v_col0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AG_SQ;
-  uint8_t* sV = sK + AG_SK;
-  uint8_t* sP = sV + AG_SV;
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + AG_SP);
+  uint8_t* sP = smem;            // overwrites Q/K after the S MMAs have completed
+  uint8_t* sV = smem + AG_SP;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sV + AG_SV);
   uint64_t* bar_s = bar_load + 1;
   uint64_t* bar_o = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
@@ -45,6 +46,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -54,21 +56,20 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc<AG_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 256 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 64 columns
+  const uint32_t tmem_S = tmem_base;  // 256 columns
+  const uint32_t tmem_O = tmem_base;  // 64 columns, written only after every thread has read S
+  pdl_wait();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_load, AG_SQ + AG_SK + AG_SV);
     tma_load_2d(sQ, &tmQ, bar_load, h * ATT_HD, b * ATT_TP + mt * 128);
     tma_load_2d(sK, &tmK, bar_load, h * ATT_HD, b * ATT_TP);
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb)
-      tma_load_2d(sV + kb * (64 * 64 * 2), &tmV, bar_load, kb * 64, (b * ATT_HEADS + h) * ATT_HD);
+    tma_load_2d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, b * ATT_TP);
     mbar_wait(bar_load, 0);
     tc_fence_after();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
@@ -136,14 +137,14 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0) {
     tc_fence_after();
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);  // B = V[key][d]: MN-major
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       const uint64_t dp = umma_desc_sw128(smem_u32(sP + kb * (128 * 64 * 2)));
-      const uint64_t dv = umma_desc_sw128(smem_u32(sV + kb * (64 * 64 * 2)));
+      const uint64_t dv = umma_desc_sw128(smem_u32(sV + kb * (64 * 128)));
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_O, umma_desc_advance_k(dp, k * 32), umma_desc_advance_k(dv, k * 32), idesc_o,
+        umma_bf16(tmem_O, umma_desc_advance_k(dp, k * 32), umma_desc_advance_k(dv, k * 2048), idesc_o,
                   (kb | k) != 0 ? 1u : 0u);
     }
     umma_commit(bar_o);
@@ -178,7 +179,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<AG_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -200,10 +201,12 @@ struct AlSmem {
 };
 
 __global__ void __launch_bounds__(AL_WARPS * 32)
-attn_local_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K,
-                  const __nv_bfloat16* __restrict__ V, int ldkv, __nv_bfloat16* __restrict__ O, int ldo,
+attn_local_kernel(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, const __nv_bfloat16* V, int ldkv,
+                  __nv_bfloat16* O, int ldo,
                   const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int total_warps) {
   __shared__ AlSmem sm_all[AL_WARPS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int id = blockIdx.x * AL_WARPS + warp;
   if (id >= total_warps) return;

@@ -41,7 +41,7 @@ struct FusedBlockCfg {
 template <int C>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                   const float* __restrict__ X, float* __restrict__ Y, int L, int M, const float* __restrict__ params) {
+                   const float* X, float* Y, int L, int M, const float* __restrict__ params) {
   using Cfg = FusedBlockCfg<C>;
   using RM = RowMap<C>;
   constexpr int H = Cfg::H;
@@ -65,6 +65,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile0 = blockIdx.x * FB_TOK;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -88,6 +89,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     RM::load(params + 7 * C, lane, bias);
     RM::load(params + 8 * C, lane, lw);
     RM::load(params + 9 * C, lane, lb);
+    pdl_wait();  // weights / parameters above are constants; x is produced by the previous kernel
     constexpr int TPW = FB_TOK / (FB_THREADS / 32);  // 8 consecutive tokens per warp
     const int r0 = warp * TPW;                       // first row (within the tile) of this warp
     float rows[TPW + 6][PER];                        // rows r0-3 .. r0+TPW+2 of x (this lane's channels)

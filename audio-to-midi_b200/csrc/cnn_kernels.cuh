@@ -11,10 +11,16 @@
 //   ln_rows_kernel<C>        LN over a row -> bf16 and/or fp32 (Downsample norm for Cin >= 64,
 //                            final norm model.py:759, transformer/decoder norms model.py:190,539,546)
 // All are HBM/L2-bound glue: coalesced 128-bit accesses, warp-shuffle reductions, no atomics.
+//
+// Activation pointers are deliberately NOT `__restrict__` and never read through __ldg: with programmatic
+// dependent launch the previous kernel may still be writing them when this kernel starts, and ptxas hoists
+// read-only (ld.global.nc) loads above griddepcontrol.wait (seen in SASS: LDG.E.CONSTANT before ACQBULK).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "ptx.cuh"
 
 namespace a2m {
 
@@ -96,7 +102,7 @@ struct SmallBlockLayout {
 constexpr int SB_TOK = 128;  // tokens (= threads) per CTA
 
 template <int C>
-__global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* __restrict__ Xin, float* __restrict__ Xout,
+__global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, float* Xout,
                                                              int L, int M, const float* __restrict__ params) {
   using Lay = SmallBlockLayout<C>;
   constexpr int H = Lay::H;
@@ -105,7 +111,9 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* __rest
   float* sp = smem_f;                          // parameters
   float* sx = smem_f + ((Lay::TOTAL + 3) & ~3);  // (SB_TOK + 6) rows of input
 
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < Lay::TOTAL; i += SB_TOK) sp[i] = __ldg(params + i);
+  pdl_wait();  // parameters are constants; activations of the previous kernel are read below
   const int tile0 = blockIdx.x * SB_TOK;
   // rows tile0-3 .. tile0+SB_TOK+2, zero outside [0, M)
   constexpr int V = C / 4;
@@ -211,13 +219,15 @@ struct SmallDownLayout {
 // X [M_in, CIN] fp32 -> Y [M_in / 2, 2*CIN] fp32.  One thread per OUTPUT token (two adjacent input tokens;
 // L_in is even at every stage so a pair never straddles a window).
 template <int CIN>
-__global__ void __launch_bounds__(128) downsample_small_kernel(const float* __restrict__ X, float* __restrict__ Y,
+__global__ void __launch_bounds__(128) downsample_small_kernel(const float* X, float* Y,
                                                                int M_out, const float* __restrict__ params) {
   using Lay = SmallDownLayout<CIN>;
   constexpr int COUT = Lay::COUT;
   constexpr int K = 2 * CIN;
   extern __shared__ __align__(16) float smem_f[];
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < Lay::TOTAL; i += blockDim.x) smem_f[i] = __ldg(params + i);
+  pdl_wait();
   __syncthreads();
   const int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= M_out) return;
@@ -334,19 +344,21 @@ constexpr int DW_TOK = 32;       // tokens per CTA
 constexpr int DW_THREADS = 256;  // 8 warps, 4 tokens each
 
 template <int C>
-__global__ void __launch_bounds__(DW_THREADS) dwconv_ln_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ A,
+__global__ void __launch_bounds__(DW_THREADS) dwconv_ln_kernel(const float* X, __nv_bfloat16* A,
                                                                int L, int M, const float* __restrict__ params) {
   using RM = RowMap<C>;
   constexpr int PER = RM::PER;
   extern __shared__ __align__(16) float smem_f[];
   float* sx = smem_f;  // (DW_TOK + 6) x C
+  pdl_launch_dependents();
+  pdl_wait();
   const int tile0 = blockIdx.x * DW_TOK;
   constexpr int V = C / 4;
   for (int i = threadIdx.x; i < (DW_TOK + 6) * V; i += DW_THREADS) {
     const int r = i / V, q = i - r * V;
     const int g = tile0 - 3 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g >= 0 && g < M) v = __ldg(reinterpret_cast<const float4*>(X + static_cast<size_t>(g) * C) + q);
+    if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(X + static_cast<size_t>(g) * C)[q];
     reinterpret_cast<float4*>(sx + r * C)[q] = v;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,11 +400,13 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_ln_kernel(const float* __re
 // buffers, T = 250 -> 256); the pad rows are written as zeros on every call so that everything later
 // derived from them is finite and deterministic (0 * NaN in a masked P.V product would poison real rows).
 template <int C>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ X, int out_rows, int Lin, int Lout,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* X, int out_rows, int Lin, int Lout,
                                                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                       __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
   using RM = RowMap<C>;
   constexpr int PER = RM::PER;
+  pdl_launch_dependents();
+  pdl_wait();
   const int orow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (orow >= out_rows) return;
   const int lane = threadIdx.x & 31;

@@ -66,6 +66,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_tiles = num_m * num_n;
   const int num_kb = g.K / GEMM_BK;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -93,6 +94,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above touched only constants (weights, bias); activations are read below
 
   if (warp == 0) {
     // ------------------------------------------------------------ operand producer
@@ -157,9 +159,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t rsw = static_cast<uint32_t>(r & 7);
     uint32_t a = 0, aph = 0, ck = 0;
+    float rc[MODE == G2_ROPE ? 32 : 1], rs[MODE == G2_ROPE ? 32 : 1];  // this row's cos / sin (all 32 pairs)
+    int rope_mblk = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row0 = m_blk * GEMM_BM;
+      if constexpr (MODE == G2_ROPE) {
+        if (m_blk != rope_mblk) {  // fetched before waiting for the accumulator: latency hides behind the MMAs
+          rope_mblk = m_blk;
+          const int pos = row0 % g.rows_per_window + r;
+          const float4* cp = reinterpret_cast<const float4*>(g.rope_cos + pos * 32);
+          const float4* sp = reinterpret_cast<const float4*>(g.rope_sin + pos * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cs = __ldg(cp + j), sn = __ldg(sp + j);
+            rc[4 * j] = cs.x; rc[4 * j + 1] = cs.y; rc[4 * j + 2] = cs.z; rc[4 * j + 3] = cs.w;
+            rs[4 * j] = sn.x; rs[4 * j + 1] = sn.y; rs[4 * j + 2] = sn.z; rs[4 * j + 3] = sn.w;
+          }
+        }
+      }
       mbar_wait(&bar_tfull[a], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * BN;
@@ -250,20 +268,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
                 }
               } else if (col0 < g.rope_cols) {  // rope.py:43-52, pairs (2i, 2i+1), i = (col % 64) / 2
-                const int i0 = (col0 & 63) >> 1;
-                const float4* cp = reinterpret_cast<const float4*>(g.rope_cos + pos * 32 + i0);
-                const float4* sp = reinterpret_cast<const float4*>(g.rope_sin + pos * 32 + i0);
+                constexpr int kPairsPerHalf = 16;  // output chunks start at multiples of 64 columns
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 cs = __ldg(cp + j), sn = __ldg(sp + j);
-                  const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
-                  const float ss[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float x1 = v[8 * j + 2 * t], x2 = v[8 * j + 2 * t + 1];
-                    v[8 * j + 2 * t] = x1 * cc[t] - x2 * ss[t];
-                    v[8 * j + 2 * t + 1] = x1 * ss[t] + x2 * cc[t];
-                  }
+                for (int t = 0; t < 16; ++t) {
+                  const float x1 = v[2 * t], x2 = v[2 * t + 1];
+                  const float cc = rc[half * kPairsPerHalf + t], ss = rs[half * kPairsPerHalf + t];
+                  v[2 * t] = x1 * cc - x2 * ss;
+                  v[2 * t + 1] = x1 * ss + x2 * cc;
                 }
               }
               if (transposed) {

@@ -13,6 +13,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start its prologue early / wait until the
+// previous kernel's writes are visible.  Both are no-ops when the launch did not opt in.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -184,6 +189,13 @@ __device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t d, uint32_t byt
 //   bit 15/16 A/B major (0 = K); [17,23) N >> 3; [24,29) M >> 4.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Same, with the B operand MN-major: B is stored as [K rows][N contiguous] (e.g. V[key][d] for P.V), i.e. the
+// transpose bit of B (bit 16) is set.  With 64 bf16 (128 B) of N per row and the 128-byte swizzle, the smem tile
+// uses the same descriptor as a K-major tile; a K step of 16 advances the start address by 16 rows = 2048 B.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t n) {
+  return umma_idesc_bf16(m, n) | (1u << 16);
 }
 
 // Byte offset of element (row, col_bf16) inside a [rows x 64] bf16 tile in the canonical
