@@ -232,6 +232,23 @@ bool make_tmap(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, ui
                uint32_t box_cols, uint32_t box_rows) {
   return make_tmap_t(h, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_cols, box_rows);
 }
+// bf16 3-D view {cols, rows_per_batch, batches} with batch stride `batch_ld_rows` rows; box {box_cols, box_rows, 1}.
+// Rows outside [0, rows_per_batch) (including negative start coordinates) are zero-filled by the TMA unit.
+bool make_tmap_3d(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows_per_batch, uint64_t batches,
+                  uint64_t ld_elems, uint64_t batch_ld_rows, uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t gdim[3] = {cols, rows_per_batch, batches};
+  cuuint64_t gstride[2] = {ld_elems * 2, batch_ld_rows * ld_elems * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->err = "cuTensorMapEncodeTiled (3-D) failed: " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
 bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                    uint32_t box_cols, uint32_t box_rows) {
   return make_tmap_t(h, m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, ld_elems, box_cols, box_rows);
@@ -289,8 +306,12 @@ template <int BN, int MODE, bool RESID>
 cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int num_sms,
                            cudaStream_t s) {
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
-  return launch_k(PF_GEMM, gemm_tc2_kernel<BN, MODE, RESID>, dim3(std::min(tiles, num_sms)), dim3(G2_THREADS),
-                  gemm2_smem_bytes<BN>(), s, a, b, c, g);
+  int grid = std::min(tiles, num_sms);
+  if (MODE == G2_ROPE) {  // even/odd CTAs own even/odd m-blocks (gemm_tc2.cuh: tile_coords)
+    if (((g.M + GEMM_BM - 1) / GEMM_BM) % 2 != 0 || g.rows_per_window != 2 * GEMM_BM) return cudaErrorInvalidValue;
+    grid = std::max(2, grid & ~1);
+  }
+  return launch_k(PF_GEMM, gemm_tc2_kernel<BN, MODE, RESID>, dim3(grid), dim3(G2_THREADS), gemm2_smem_bytes<BN>(), s, a, b, c, g);
 }
 
 cudaError_t launch_gemm2(int BN, int mode, bool resid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
@@ -375,6 +396,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<64, G2_ROPE, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
@@ -774,17 +796,25 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
     }
     if (local) {
+      // q / k are rotated with their ABSOLUTE row index, exactly like the global layers: RoPE logits depend
+      // only on position differences, so this equals the reference's per-window positions (attention.cuh)
       GemmArgs g = gemm_args(Mt, kQC, kD);
-      g.flags = GF_OUT16; g.out16 = qc; g.ld16 = kQC;
-      if (!add_gemm(h, p, 64, GEMM_GENERIC, a16, kD, t.wqc, g)) return false;
+      g.out16 = qc; g.ld16 = kQC;
+      g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.rope_cols = 256; g.rows_per_window = kTP;
+      g.vt_out = nullptr; g.vt_col0 = 1 << 30;
+      if (!add_gemm(h, p, 64, GEMM_ROPE, a16, kD, t.wqc, g)) return false;
       GemmArgs g2 = gemm_args(Mt, kKV, 64);
-      g2.flags = GF_OUT16; g2.out16 = kv; g2.ld16 = kKV;
-      if (!add_gemm(h, p, 128, GEMM_GENERIC, qc + 256, kQC, t.wkv, g2)) return false;
-      const int total_warps = B * ATT_HEADS * 32;
+      g2.out16 = kv; g2.ld16 = kKV;
+      g2.rope_cos = rope_cos; g2.rope_sin = rope_sin; g2.rope_cols = 256; g2.rows_per_window = kTP;
+      g2.vt_out = nullptr; g2.vt_col0 = 1 << 30;
+      if (!add_gemm(h, p, 128, GEMM_ROPE, qc + 256, kQC, t.wkv, g2)) return false;
+      CUtensorMap tq, tk, tv;
+      if (!make_tmap_3d(h, &tq, qc, 256, kT, B, kQC, kTP, 64, 128)) return false;
+      if (!make_tmap_3d(h, &tk, kv, 256, kT, B, kKV, kTP, 64, AL_NK)) return false;
+      if (!make_tmap_3d(h, &tv, kv, kKV, kT, B, kKV, kTP, 64, AL_NK)) return false;
       // as written in the reference: 31 windows x 4 heads x (QK^T + PV) of 16 x 16 x 64
-      add_step(p, Meta{"attn_local_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * (256 + 512 + 256)}, [=](cudaStream_t st) {
-        return launch_k(PF_ATTN, attn_local_kernel, dim3((total_warps + AL_WARPS - 1) / AL_WARPS), dim3(AL_WARPS * 32), 0, st, qc, kQC, kv,
-                        kv + 256, kKV, o16, kD, rope_cos, rope_sin, total_warps);
+      add_step(p, Meta{"attn_local_tc_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
+        return launch_k(PF_ATTN, attn_local_tc_kernel, dim3(2, ATT_HEADS, B), dim3(AL_THREADS), AL_SMEM, st, tq, tk, tv, o16, kD, 256);
       });
     } else {
       GemmArgs g = gemm_args(Mt, kQC, kD);

@@ -3,8 +3,7 @@
 //   attn_global_kernel  SelfAttention over the whole 250-frame window (model.py:241-257, 364-366):
 //                       S = Q K^T and O = P V on tcgen05 (UMMA 128x256x16 and 128x64x16), S and O in
 //                       TMEM, operands TMA-staged (Q, K, V^T) or written by the softmax threads (P).
-//   attn_local_kernel   LocalSelfAttention (model.py:409-471) on CUDA cores: 16-frame windows at
-//                       stride 8; tiny contractions (16x16x64), latency bound.
+//   attn_local_tc_kernel LocalSelfAttention (model.py:409-471) as one banded attention on tcgen05 (see below).
 //
 // Both read RoPE-ready bf16 projections produced by the GEMM epilogues and write the bf16 operand of the
 // output projection.  Sequence rows are padded 250 -> 256 per window (row = b * 256 + t).
@@ -17,6 +16,11 @@ constexpr int ATT_T = 250;    // real frames per window
 constexpr int ATT_TP = 256;   // padded rows per window
 constexpr int ATT_HD = 64;    // head dim
 constexpr int ATT_HEADS = 4;
+
+__device__ __forceinline__ uint32_t pack_bf16x2_att(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 
 // ------------------------------------------------------------------------------------------ global
 constexpr int AG_THREADS = 128;
@@ -183,131 +187,203 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------------------------------ local
-// One warp per (window b, head h, block w of 8 output rows j = 8w .. 8w+7).  The reference pads the
-// normalised sequence with 3 zero rows on the left (and 3 on the right), runs attention in 31 windows
-// of 16 padded rows at stride 8, and scatter-adds window row r into output row (start + r) of the
-// UNPADDED buffer (model.py:422-469).  Hence output row j = mean over the windows {w-1, w} that exist
-// of the attention result for padded row j = token j-3; zero-padding tokens have q = k = v = 0 (the
-// projections are bias free) but still occupy a slot in each softmax.  RoPE positions are the row
-// index inside the window (rope.py:40-41), so K is rotated per window.
-// The output projection is linear and bias free, so it is applied AFTER the mean (one GEMM on 256 rows).
-constexpr int AL_WARPS = 4;
-constexpr int AL_SK_STRIDE = 66;  // floats; conflict-free 64-bit reads for 16 keys
-struct AlSmem {
-  float k[16][AL_SK_STRIDE];
-  float q[8][64];
-  float p[8][16];
-};
+// ------------------------------------------------------------------------------------------ local (tensor cores)
+// LocalSelfAttention (model.py:409-471) restated for the tensor cores.
+//
+// Reference: pad the normalised sequence with 3 zero rows left / 3 right (256 padded rows), attend inside 31
+// windows of 16 padded rows at stride 8 with RoPE positions 0..15 INSIDE each window, scatter-add window row r
+// to output row (start + r) of the unpadded buffer (so output row j holds the result for padded row j = token
+// j-3; rows >= 250 are dropped) and divide by the number of windows that covered the row.
+//
+// Two identities make this one banded attention:
+//  (1) RoPE scores depend only on the position DIFFERENCE: <R(a) q, R(b) k> = <R(a+c) q, R(b+c) k>.  Rotating
+//      q and k once with their absolute row index (done in the projection GEMM epilogue, as for the global
+//      layers) gives the same logits as the per-window positions 0..15, up to fp32 rounding of the table.
+//  (2) the output projection is linear and bias free, so the mean over the <= 2 covering windows commutes with
+//      it: P = mean over windows of that window's softmax row, then one P.V product.
+// Zero-padding tokens (token < 0 or >= 250) have q = k = v = 0 (bias-free projections) but still own a softmax
+// slot with logit 0.  They are produced by TMA out-of-bounds zero fill: the tensor maps view each window as
+// [250 rows] so negative rows and rows 250.. come back as zeros.
+//
+// Per CTA: 128 padded query rows j = 128 mt .. +127 of one (window b, head h); keys = padded rows 128 mt - 8 ..
+// 128 mt + 135 (144 rows).  S = Q K^T (UMMA 128x144x16) in TMEM, banded two-window softmax on CUDA cores straight
+// from TMEM, P (bf16) into the swizzled A-operand layout, O = P V (UMMA 128x64x16, V MN-major), bf16 store.
+constexpr int AL_THREADS = 128;
+constexpr int AL_NK = 144;                 // keys per tile
+constexpr int AL_SQ = 128 * 64 * 2;        // 16 KB
+constexpr int AL_SK = AL_NK * 64 * 2;      // 18 KB
+constexpr int AL_SV = AL_NK * 64 * 2;      // 18 KB, V[key][d]
+constexpr int AL_SP = 3 * 128 * 64 * 2;    // 48 KB: key blocks 0-63, 64-127, 128-143
+constexpr size_t AL_SMEM = 1024 + AL_SQ + AL_SK + AL_SV + AL_SP + 128;  // ~101 KB -> two CTAs per SM
+constexpr uint32_t AL_TMEM_COLS = 256;     // S: columns 0..143, O: columns 192..255
 
-__global__ void __launch_bounds__(AL_WARPS * 32)
-attn_local_kernel(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, const __nv_bfloat16* V, int ldkv,
-                  __nv_bfloat16* O, int ldo,
-                  const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int total_warps) {
-  __shared__ AlSmem sm_all[AL_WARPS];
-  pdl_launch_dependents();
-  pdl_wait();
+// tmQ / tmK / tmV are 3-D maps {cols, 250 rows, B} over the q||c and k||v projection buffers.
+__global__ void __launch_bounds__(AL_THREADS, 2)
+attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* O, int ldo, int v_col0) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AL_SQ;
+  uint8_t* sV = sK + AL_SK;
+  uint8_t* sP = sV + AL_SV;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + AL_SP);
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_o = bar_load + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+
+  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int id = blockIdx.x * AL_WARPS + warp;
-  if (id >= total_warps) return;
-  AlSmem& sm = sm_all[warp];
-  const int w = id & 31;
-  const int h = (id >> 5) & 3;
-  const int b = id >> 7;
-  const size_t rowbase = static_cast<size_t>(b) * ATT_TP;
 
-  float o[8][2];
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) o[jj][0] = o[jj][1] = 0.f;
-  int count = 0;
-
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const int win = w - 1 + which;  // window w-1 first, then window w
-    if (win < 0 || win > 30) continue;
-    ++count;
-    const int s = 8 * win;          // first padded row of the window
-    float v[16][2];
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const int tok = s + kk - 3;
-      float k0 = 0.f, k1 = 0.f;
-      v[kk][0] = v[kk][1] = 0.f;
-      if (tok >= 0 && tok < ATT_T) {
-        const size_t r = rowbase + tok;
-        const __nv_bfloat162 kv = *reinterpret_cast<const __nv_bfloat162*>(K + r * ldkv + h * ATT_HD + 2 * lane);
-        const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(V + r * ldkv + h * ATT_HD + 2 * lane);
-        k0 = __low2float(kv); k1 = __high2float(kv);
-        v[kk][0] = __low2float(vv); v[kk][1] = __high2float(vv);
-      }
-      const float c = __ldg(rope_cos + kk * 32 + lane), sn = __ldg(rope_sin + kk * 32 + lane);
-      *reinterpret_cast<float2*>(&sm.k[kk][2 * lane]) = make_float2(k0 * c - k1 * sn, k0 * sn + k1 * c);
-    }
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = 8 * w + jj;      // output row == padded row
-      const int tok = j - 3;
-      const int pos = j - s;         // position inside the window (0..15)
-      float q0 = 0.f, q1 = 0.f;
-      if (tok >= 0 && tok < ATT_T) {
-        const __nv_bfloat162 qv =
-            *reinterpret_cast<const __nv_bfloat162*>(Q + (rowbase + tok) * ldq + h * ATT_HD + 2 * lane);
-        q0 = __low2float(qv); q1 = __high2float(qv);
-      }
-      const float c = __ldg(rope_cos + pos * 32 + lane), sn = __ldg(rope_sin + pos * 32 + lane);
-      *reinterpret_cast<float2*>(&sm.q[jj][2 * lane]) = make_float2(q0 * c - q1 * sn, q0 * sn + q1 * c);
-    }
-    __syncwarp();
-
-    // scores: lane -> key kk = lane & 15, queries jj = 4 * (lane >> 4) + u
-    const int kk = lane & 15, g = lane >> 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int d = 0; d < 64; d += 2) {
-      const float2 kv = *reinterpret_cast<const float2*>(&sm.k[kk][d]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 qv = *reinterpret_cast<const float2*>(&sm.q[4 * g + u][d]);
-        acc[u] = fmaf(qv.x, kv.x, acc[u]);
-        acc[u] = fmaf(qv.y, kv.y, acc[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float sc = acc[u] * 0.125f;  // query / sqrt(64)
-      float m = sc;
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-      const float e = __expf(sc - m);
-      float t = e;
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-      sm.p[4 * g + u][kk] = __fdividef(e, t);
-    }
-    __syncwarp();
-
-    // O += P V : lane owns head dims (2 lane, 2 lane + 1)
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-#pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const float pw = sm.p[jj][k2];
-        o[jj][0] = fmaf(pw, v[k2][0], o[jj][0]);
-        o[jj][1] = fmaf(pw, v[k2][1], o[jj][1]);
-      }
-    }
-    __syncwarp();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
   }
+  if (warp == 0) tmem_alloc<AL_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 192;
+  pdl_wait();
 
-  const float inv = 1.0f / static_cast<float>(count);
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, AL_SQ + AL_SK + AL_SV);
+    // padded row j <-> token j - 3; rows outside [0, 250) are zero-filled by the TMA unit
+    tma_load_3d(sQ, &tmQ, bar_load, h * ATT_HD, mt * 128 - 3, b);
+    tma_load_3d(sK, &tmK, bar_load, h * ATT_HD, mt * 128 - 8 - 3, b);
+    tma_load_3d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, mt * 128 - 8 - 3, b);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, AL_NK);
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t dk = umma_desc_sw128(smem_u32(sK));
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const int j = 8 * w + jj;
-    // pad rows 250..255 are written as zeros: they feed the output projection of the padded rows and must
-    // stay finite (stale memory there could be NaN/Inf)
-    const bool real = j < ATT_T;
-    *reinterpret_cast<__nv_bfloat162*>(O + (rowbase + j) * ldo + h * ATT_HD + 2 * lane) =
-        __floats2bfloat162_rn(real ? o[jj][0] * inv : 0.f, real ? o[jj][1] * inv : 0.f);
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_S, umma_desc_advance_k(dq, k * 32), umma_desc_advance_k(dk, k * 32), idesc_s, k != 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;        // query row in the tile
+  const int j = mt * 128 + row;            // padded row == output row
+  const uint32_t t_row = static_cast<uint32_t>(warp * 32) << 16;
+  // key columns (tile relative) of this row's two windows:  A = window floor(j/8)-1 : [off, off+16),
+  //                                                           B = window floor(j/8)   : [off+8, off+24)
+  // relative to the warp's 48-column slab that starts at column 32 * warp.
+  const int off = (lane >> 3) << 3;
+  const bool has_a = j >= 8;               // window index >= 0
+  const bool has_b = j < 248;              // window index <= 30
+  float s[48];
+  {
+    uint32_t r0[32], r1[16];
+    tmem_ld_x32(tmem_S + t_row + warp * 32, r0);
+    tmem_ld_x16(tmem_S + t_row + warp * 32 + 32, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) s[c] = __uint_as_float(r0[c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s[32 + c] = __uint_as_float(r1[c]);
+  }
+  const float kscale = 0.125f * 1.4426950408889634f;   // (q / sqrt(64)) . k, exp2 domain
+  float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 48; ++c) {
+    const bool in_a = static_cast<unsigned>(c - off) < 16u;
+    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
+    if (in_a) ma = fmaxf(ma, s[c]);
+    if (in_b) mb = fmaxf(mb, s[c]);
+  }
+  float suma = 0.f, sumb = 0.f;
+#pragma unroll
+  for (int c = 0; c < 48; ++c) {
+    const bool in_a = static_cast<unsigned>(c - off) < 16u;
+    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
+    if (in_a) suma += exp2f((s[c] - ma) * kscale);
+    if (in_b) sumb += exp2f((s[c] - mb) * kscale);
+  }
+  const float wn = (has_a && has_b) ? 0.5f : 1.0f;      // divide by the number of covering windows
+  const float ia = has_a ? __fdividef(wn, suma) : 0.f;
+  const float ib = has_b ? __fdividef(wn, sumb) : 0.f;
+#pragma unroll
+  for (int c = 0; c < 48; ++c) {
+    const bool in_a = static_cast<unsigned>(c - off) < 16u;
+    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
+    float p = 0.f;
+    if (in_a) p += exp2f((s[c] - ma) * kscale) * ia;
+    if (in_b) p += exp2f((s[c] - mb) * kscale) * ib;
+    s[c] = p;
+  }
+  // P row (144 keys = 18 chunks of 8) into the swizzled K-major layout; this warp's slab is chunks 4w .. 4w+5
+  {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int cc = 0; cc < 18; ++cc) {
+      if (cc < 4 * warp || cc >= 4 * warp + 6)
+        *reinterpret_cast<uint4*>(sP + (cc >> 3) * (128 * 128) + sw128_offset(row, (cc & 7) * 8)) = zero;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int cc = 4 * warp + i;
+      uint4 v;
+      v.x = pack_bf16x2_att(s[8 * i], s[8 * i + 1]);
+      v.y = pack_bf16x2_att(s[8 * i + 2], s[8 * i + 3]);
+      v.z = pack_bf16x2_att(s[8 * i + 4], s[8 * i + 5]);
+      v.w = pack_bf16x2_att(s[8 * i + 6], s[8 * i + 7]);
+      *reinterpret_cast<uint4*>(sP + (cc >> 3) * (128 * 128) + sw128_offset(row, (cc & 7) * 8)) = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+    const uint64_t dv = umma_desc_sw128(smem_u32(sV));
+#pragma unroll
+    for (int ks = 0; ks < AL_NK / 16; ++ks) {   // 9 key steps of 16
+      const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (128 * 128)));
+      umma_bf16(tmem_O, umma_desc_advance_k(dp, (ks & 3) * 32), umma_desc_advance_k(dv, ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  __nv_bfloat16* dst = O + static_cast<size_t>(b * ATT_TP + j) * ldo + h * ATT_HD;
+  const bool real = j < ATT_T;   // rows 250..255 are written as zeros (kept finite for the padded projections)
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld_x32(tmem_O + t_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 v;
+      v.x = real ? pack_bf16x2_att(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])) : 0u;
+      v.y = real ? pack_bf16x2_att(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])) : 0u;
+      v.z = real ? pack_bf16x2_att(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])) : 0u;
+      v.w = real ? pack_bf16x2_att(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])) : 0u;
+      reinterpret_cast<uint4*>(dst + c * 32)[q] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<AL_TMEM_COLS>(tmem_base);
   }
 }
 

@@ -65,6 +65,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_m = (g.M + GEMM_BM - 1) / GEMM_BM;
   const int num_tiles = num_m * num_n;
   const int num_kb = g.K / GEMM_BK;
+  // Tile schedule (identical in every role).  RoPE mode: CTAs with even / odd blockIdx own the even / odd
+  // m-blocks, so the position of a thread's row (row % 256) -- and with it the cos/sin row it keeps in
+  // registers -- never changes.  The host launches an even grid and num_m is even (two m-blocks per window).
+  auto tile_coords = [&](int it, int& m_blk, int& n_blk) -> bool {
+    if constexpr (MODE == G2_ROPE) {
+      const int li = static_cast<int>(blockIdx.x >> 1) + it * static_cast<int>(gridDim.x >> 1);
+      if (li >= (num_m >> 1) * num_n) return false;
+      m_blk = 2 * (li / num_n) + static_cast<int>(blockIdx.x & 1);
+      n_blk = li % num_n;
+      return true;
+    } else {
+      const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      if (tile >= num_tiles) return false;
+      m_blk = tile / num_n;
+      n_blk = tile % num_n;
+      return true;
+    }
+  };
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -100,8 +118,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------ operand producer
     if (elect_one()) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      int m_blk, n_blk;
+      for (int it = 0; tile_coords(it, m_blk, n_blk); ++it) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bar_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&bar_full[s], A_BYTES + B_BYTES);
@@ -116,7 +134,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       uint32_t s = 0, ph = 0, a = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      for (int it = 0; tile_coords(it, m_blk, n_blk); ++it) {
         mbar_wait(&bar_tempty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
@@ -141,8 +160,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (RESID) {
       if (elect_one()) {
         uint32_t ck = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m_blk = tile / num_n, n_blk = tile % num_n;
+        int m_blk, n_blk;
+        for (int it = 0; tile_coords(it, m_blk, n_blk); ++it) {
           for (int c = 0; c < BN / 32; ++c, ++ck) {
             const uint32_t cb = ck % G2_NCH, cph = (ck / G2_NCH) & 1;
             mbar_wait(&bar_cempty[cb], cph ^ 1);
@@ -161,12 +180,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t a = 0, aph = 0, ck = 0;
     float rc[MODE == G2_ROPE ? 32 : 1], rs[MODE == G2_ROPE ? 32 : 1];  // this row's cos / sin (all 32 pairs)
     int rope_mblk = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    int m_blk, n_blk;
+    for (int it = 0; tile_coords(it, m_blk, n_blk); ++it) {
       const int row0 = m_blk * GEMM_BM;
       if constexpr (MODE == G2_ROPE) {
-        if (m_blk != rope_mblk) {  // fetched before waiting for the accumulator: latency hides behind the MMAs
-          rope_mblk = m_blk;
+        if ((m_blk & 1) != rope_mblk) {  // once per CTA (see tile_coords); before the accumulator wait
+          rope_mblk = m_blk & 1;
           const int pos = row0 % g.rows_per_window + r;
           const float4* cp = reinterpret_cast<const float4*>(g.rope_cos + pos * 32);
           const float4* sp = reinterpret_cast<const float4*>(g.rope_sin + pos * 32);
