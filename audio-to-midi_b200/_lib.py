@@ -35,7 +35,8 @@ class MLMultiArrayWrapper3(C.Structure):
 
 EXPORTS = [
     "a2m_create", "a2m_destroy", "a2m_last_error", "a2m_load_weights", "a2m_workspace_bytes", "a2m_forward",
-    "a2m_forward_host", "a2m_last_launch_count", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
+    "a2m_forward_host", "a2m_submit_host", "a2m_collect_host", "a2m_host_alloc", "a2m_host_free",
+    "a2m_last_launch_count", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
 ]
 
@@ -69,6 +70,14 @@ def lib() -> C.CDLL:
     L.a2m_forward.restype = C.c_int
     L.a2m_forward_host.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
     L.a2m_forward_host.restype = C.c_int
+    L.a2m_submit_host.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp]
+    L.a2m_submit_host.restype = C.c_int
+    L.a2m_collect_host.argtypes = [vp, i32]
+    L.a2m_collect_host.restype = C.c_int
+    L.a2m_host_alloc.argtypes = [sz]
+    L.a2m_host_alloc.restype = vp
+    L.a2m_host_free.argtypes = [vp]
+    L.a2m_host_free.restype = None
     L.a2m_last_launch_count.argtypes = [vp]
     L.a2m_last_launch_count.restype = i32
     L.a2m_profile_steps.argtypes = [vp, i32, i32, i32, C.POINTER(StepProfile)]

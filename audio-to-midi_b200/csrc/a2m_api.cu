@@ -190,14 +190,24 @@ struct A2mHandle {
   bool use_pdl = true;     // programmatic dependent launch between the kernels of the plan
   bool use_gemm2 = true;   // TMA-staged epilogue GEMM (gemm_tc2.cuh); false = first-generation kernel (debug)
   int last_launches = 0;
-  // host staging for a2m_forward_host
-  float* pin_audio = nullptr;
-  float* pin_out = nullptr;
+  // host path: two slots so that the copies of one batch overlap the compute of the other
+  struct Slot {
+    float* dev_audio = nullptr;
+    float* dev_out = nullptr;     // logits then probs
+    float* pin_audio = nullptr;   // staging, used only when the caller's buffers are pageable
+    float* pin_out = nullptr;
+    int cap = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    bool pending = false;
+    int B = 0;
+    float* user_logits = nullptr;
+    float* user_probs = nullptr;
+    bool out_direct = false;
+  } slots[2];
   float* pin_rope = nullptr;
-  float* dev_audio = nullptr;
-  float* dev_out = nullptr;
   float* dev_rope_in = nullptr;
-  int staged_B = 0;
+  std::vector<float> rope_host_cache;
   cudaStream_t own_stream = nullptr;
 };
 
@@ -1040,11 +1050,17 @@ void a2m_destroy(A2mHandle* h) {
   if (h->arena_dev) cudaFree(h->arena_dev);
   if (h->rope_dev) cudaFree(h->rope_dev);
   if (h->own_ws) cudaFree(h->own_ws);
-  if (h->pin_audio) cudaFreeHost(h->pin_audio);
-  if (h->pin_out) cudaFreeHost(h->pin_out);
+  for (auto& sl : h->slots) {
+    if (sl.dev_audio) cudaFree(sl.dev_audio);
+    if (sl.dev_out) cudaFree(sl.dev_out);
+    if (sl.pin_audio) cudaFreeHost(sl.pin_audio);
+    if (sl.pin_out) cudaFreeHost(sl.pin_out);
+    if (sl.copy) cudaStreamDestroy(sl.copy);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+  }
   if (h->pin_rope) cudaFreeHost(h->pin_rope);
-  if (h->dev_audio) cudaFree(h->dev_audio);
-  if (h->dev_out) cudaFree(h->dev_out);
   if (h->dev_rope_in) cudaFree(h->dev_rope_in);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -1112,49 +1128,131 @@ int a2m_debug_forward_tap(A2mHandle* h, const float* audio_dev, int32_t batch, c
                      static_cast<cudaStream_t>(stream), label, out_dev, out_elems);
 }
 
-int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
-                     const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                    const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
   if (!h) return A2M_EINVAL;
-  if (batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !logits_host || !probs_host || rope_max_pos < kT) {
-    h->err = "bad forward_host arguments";
+  if (slot < 0 || slot > 1 || batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !logits_host || !probs_host ||
+      rope_max_pos < kT) {
+    h->err = "bad submit_host arguments";
     return A2M_EINVAL;
   }
+  A2mHandle::Slot& sl = h->slots[slot];
+  if (sl.pending) { h->err = "slot still in flight: call a2m_collect_host first"; return A2M_ESTATE; }
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t a_elems = static_cast<size_t>(batch) * 2 * A2M_WINDOW_SAMPLES;
   const size_t o_elems = static_cast<size_t>(batch) * A2M_FRAMES * A2M_VOCAB;
+  if (!sl.copy) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+  }
+  if (sl.cap < batch) {
+    if (sl.dev_audio) cudaFree(sl.dev_audio);
+    if (sl.dev_out) cudaFree(sl.dev_out);
+    if (sl.pin_audio) cudaFreeHost(sl.pin_audio);
+    if (sl.pin_out) cudaFreeHost(sl.pin_out);
+    sl.dev_audio = sl.dev_out = sl.pin_audio = sl.pin_out = nullptr;
+    sl.cap = 0;
+    CUDA_TRY(cudaMalloc(&sl.dev_audio, a_elems * 4));
+    CUDA_TRY(cudaMalloc(&sl.dev_out, 2 * o_elems * 4));
+    sl.cap = batch;
+  }
+  // RoPE table: re-uploaded only when its contents change (it is an input of every call, rope.py:5-22)
   const int rows = std::min(rope_max_pos, kRopeRows);
   const size_t r_elems = static_cast<size_t>(rows) * A2M_ROPE_DIM;
-  if (h->staged_B < batch) {
-    if (h->pin_audio) cudaFreeHost(h->pin_audio);
-    if (h->pin_out) cudaFreeHost(h->pin_out);
-    if (h->dev_audio) cudaFree(h->dev_audio);
-    if (h->dev_out) cudaFree(h->dev_out);
-    h->pin_audio = h->pin_out = h->dev_audio = h->dev_out = nullptr;
-    h->staged_B = 0;
-    CUDA_TRY(cudaMallocHost(&h->pin_audio, a_elems * 4));
-    CUDA_TRY(cudaMallocHost(&h->pin_out, 2 * o_elems * 4));
-    CUDA_TRY(cudaMalloc(&h->dev_audio, a_elems * 4));
-    CUDA_TRY(cudaMalloc(&h->dev_out, 2 * o_elems * 4));
-    h->staged_B = batch;
-  }
   if (!h->pin_rope) {
     CUDA_TRY(cudaMallocHost(&h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4));
     CUDA_TRY(cudaMalloc(&h->dev_rope_in, 2 * kRopeRows * A2M_ROPE_DIM * 4));
+    CUDA_TRY(cudaMemset(h->dev_rope_in, 0, 2 * kRopeRows * A2M_ROPE_DIM * 4));
   }
-  cudaStream_t s = h->own_stream;
-  std::memcpy(h->pin_audio, audio_host, a_elems * 4);
-  std::memcpy(h->pin_rope, rope_cos_host, r_elems * 4);
-  std::memcpy(h->pin_rope + kRopeRows * A2M_ROPE_DIM, rope_sin_host, r_elems * 4);
-  CUDA_TRY(cudaMemcpyAsync(h->dev_audio, h->pin_audio, a_elems * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice, s));
-  int rc = run_forward(h, h->dev_audio, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, h->dev_out,
-                       h->dev_out + o_elems, nullptr, 0, s, nullptr, nullptr, 0);
+  cudaStream_t cs = h->own_stream;  // compute stream shared by both slots: forwards are serialised, one workspace
+  if (h->rope_host_cache.size() != 2 * r_elems || std::memcmp(h->rope_host_cache.data(), rope_cos_host, r_elems * 4) != 0 ||
+      std::memcmp(h->rope_host_cache.data() + r_elems, rope_sin_host, r_elems * 4) != 0) {
+    CUDA_TRY(cudaStreamSynchronize(cs));  // the staging buffer may still feed an earlier upload
+    h->rope_host_cache.assign(rope_cos_host, rope_cos_host + r_elems);
+    h->rope_host_cache.insert(h->rope_host_cache.end(), rope_sin_host, rope_sin_host + r_elems);
+    std::memset(h->pin_rope, 0, 2 * kRopeRows * A2M_ROPE_DIM * 4);
+    std::memcpy(h->pin_rope, rope_cos_host, r_elems * 4);
+    std::memcpy(h->pin_rope + kRopeRows * A2M_ROPE_DIM, rope_sin_host, r_elems * 4);
+    CUDA_TRY(cudaMemcpyAsync(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice, cs));
+  }
+  // input: straight from the caller's buffer when it is page-locked, else through the slot's staging buffer
+  const float* src = audio_host;
+  if (!is_pinned(audio_host)) {
+    if (!sl.pin_audio) CUDA_TRY(cudaMallocHost(&sl.pin_audio, static_cast<size_t>(sl.cap) * 2 * A2M_WINDOW_SAMPLES * 4));
+    std::memcpy(sl.pin_audio, audio_host, a_elems * 4);
+    src = sl.pin_audio;
+  }
+  CUDA_TRY(cudaMemcpyAsync(sl.dev_audio, src, a_elems * 4, cudaMemcpyHostToDevice, sl.copy));
+  CUDA_TRY(cudaEventRecord(sl.ev_in, sl.copy));
+  CUDA_TRY(cudaStreamWaitEvent(cs, sl.ev_in, 0));
+  int rc = run_forward(h, sl.dev_audio, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, sl.dev_out,
+                       sl.dev_out + o_elems, nullptr, 0, cs, nullptr, nullptr, 0);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h->pin_out, h->dev_out, 2 * o_elems * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  std::memcpy(logits_host, h->pin_out, o_elems * 4);
-  std::memcpy(probs_host, h->pin_out + o_elems, o_elems * 4);
+  CUDA_TRY(cudaEventRecord(sl.ev_done, cs));
+  CUDA_TRY(cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
+  sl.out_direct = is_pinned(logits_host) && is_pinned(probs_host);
+  if (sl.out_direct) {
+    CUDA_TRY(cudaMemcpyAsync(logits_host, sl.dev_out, o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
+    CUDA_TRY(cudaMemcpyAsync(probs_host, sl.dev_out + o_elems, o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
+  } else {
+    if (!sl.pin_out) CUDA_TRY(cudaMallocHost(&sl.pin_out, static_cast<size_t>(sl.cap) * 2 * A2M_FRAMES * A2M_VOCAB * 4));
+    CUDA_TRY(cudaMemcpyAsync(sl.pin_out, sl.dev_out, 2 * o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
+  }
+  CUDA_TRY(cudaEventRecord(sl.ev_out, sl.copy));
+  sl.pending = true;
+  sl.B = batch;
+  sl.user_logits = logits_host;
+  sl.user_probs = probs_host;
   return A2M_OK;
+}
+
+int a2m_collect_host(A2mHandle* h, int32_t slot) {
+  if (!h) return A2M_EINVAL;
+  if (slot < 0 || slot > 1) { h->err = "bad slot"; return A2M_EINVAL; }
+  A2mHandle::Slot& sl = h->slots[slot];
+  if (!sl.pending) { h->err = "nothing submitted on this slot"; return A2M_ESTATE; }
+  sl.pending = false;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(sl.ev_out));
+  if (!sl.out_direct) {
+    const size_t o_elems = static_cast<size_t>(sl.B) * A2M_FRAMES * A2M_VOCAB;
+    std::memcpy(sl.user_logits, sl.pin_out, o_elems * 4);
+    std::memcpy(sl.user_probs, sl.pin_out + o_elems, o_elems * 4);
+  }
+  return A2M_OK;
+}
+
+int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                     const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
+  if (!h) return A2M_EINVAL;
+  if (h->slots[0].pending) { h->err = "slot 0 in flight (mixing a2m_forward_host with a2m_submit_host)"; return A2M_ESTATE; }
+  int rc = a2m_submit_host(h, 0, audio_host, batch, rope_cos_host, rope_sin_host, rope_max_pos, logits_host, probs_host);
+  if (rc) return rc;
+  return a2m_collect_host(h, 0);
+}
+
+void* a2m_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void a2m_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }

@@ -306,6 +306,7 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         self.decoder = Decoder(rng, d)
         self._version = 0
         self._rope_cache = {}
+        self._out_ring = {}
 
     # -- pytree helpers (what eqx.tree_at / tree_deserialise_leaves would be used for)
     def load_leaves(self, leaves: Dict[str, np.ndarray]):
@@ -379,6 +380,47 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         _lib.check(eng.h, rc, "a2m_forward_host")
         return (logits[0], probs[0]) if single else (logits, probs)
 
+    def predict_pipelined(self, batches, rope_freqs: RopeFreqs, state=None, copy: bool = False):
+        """Generator over an iterable of host batches (B, 2, 80000): yields (logits, probs) per batch, in order,
+        keeping two batches in flight so the H2D / D2H copies of one overlap the kernels of the other
+        (a2m_submit_host / a2m_collect_host).  Use ``pinned_empty`` arrays for the inputs to make the copies
+        truly asynchronous.  Outputs live in a ring of three page-locked buffers (page-locking is expensive, so
+        they are allocated once per batch size): a yielded pair stays valid until two more pairs have been
+        yielded; pass copy=True to get private copies instead."""
+        eng = self._engine(_default_device())
+        cos = np.ascontiguousarray(rope_freqs.cos_freq, np.float32)
+        sin = np.ascontiguousarray(rope_freqs.sin_freq, np.float32)
+        inflight = []
+        slot = 0
+
+        def finish(item):
+            s0, _keep, lg, pr = item
+            _lib.check(eng.h, eng.L.a2m_collect_host(eng.h, s0), "a2m_collect_host")
+            return (lg.copy(), pr.copy()) if copy else (lg, pr)
+
+        for x in batches:
+            if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous):
+                x = np.ascontiguousarray(x, dtype=np.float32)
+            if x.ndim != 3 or x.shape[1:] != (2, 80000):
+                raise ValueError(f"batches must be (B, 2, 80000), got {x.shape}")
+            if len(inflight) == 2:
+                yield finish(inflight.pop(0))
+            B = x.shape[0]
+            ring = self._out_ring.setdefault(B, {"bufs": [], "n": 0})
+            if len(ring["bufs"]) < 3:
+                ring["bufs"].append((pinned_empty((B, 250, 90)), pinned_empty((B, 250, 90))))
+                lg, pr = ring["bufs"][-1]
+            else:
+                lg, pr = ring["bufs"][ring["n"] % 3]
+            ring["n"] += 1
+            rc = eng.L.a2m_submit_host(eng.h, slot, x.ctypes.data, B, cos.ctypes.data, sin.ctypes.data, cos.shape[0],
+                                       lg.ctypes.data, pr.ctypes.data)
+            _lib.check(eng.h, rc, "a2m_submit_host")
+            inflight.append((slot, x, lg, pr))
+            slot ^= 1
+        for item in inflight:
+            yield finish(item)
+
     def profile_steps(self, batch: int, repeats: int = 5, device: Optional[int] = None):
         """Per-launch CUDA-event timings of the forward plan: list of (kernel, ms, algorithmic flops, bytes)."""
         eng = self._engine(_default_device() if device is None else device)
@@ -399,6 +441,37 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
 def _default_device() -> int:
     import os
     return int(os.environ.get("LOCAL_RANK", os.environ.get("A2M_DEVICE", "0")))
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.lib().a2m_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array backed by page-locked host memory (a2m_host_alloc): the host path copies to / from it directly,
+    asynchronously, without the pageable -> pinned staging copy."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = _lib.lib().a2m_host_alloc(max(n, 1))
+    if not ptr:
+        raise MemoryError("a2m_host_alloc failed (is a CUDA device present?)")
+    owner = _PinnedOwner(ptr)
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = owner  # keep the allocation alive as long as the ctypes buffer object
+    import weakref
+    weakref.finalize(buf, _PINNED.pop, id(buf), None)
+    return arr
+
+
+_PINNED: dict = {}
 
 
 def vmap(fn, in_axes=(None, 0, None)):

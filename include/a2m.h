@@ -81,6 +81,18 @@ int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float
 int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
                      const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host);
 
+/* Pipelined host path: two slots (0, 1).  a2m_submit_host enqueues H2D copy -> forward -> D2H copy for one batch
+ * and returns; a2m_collect_host waits for that slot's results.  Copies of one slot overlap the compute of the
+ * other (separate copy streams, one compute stream).  Buffers allocated with a2m_host_alloc (page-locked) are
+ * copied from / to directly; pageable buffers go through an internal staging copy.  The caller's buffers must
+ * stay valid and untouched until the slot has been collected. */
+int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                    const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host);
+int a2m_collect_host(A2mHandle* h, int32_t slot);
+/* Page-locked host memory for the calls above (cudaMallocHost / cudaFreeHost). */
+void* a2m_host_alloc(size_t bytes);
+void a2m_host_free(void* p);
+
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
 /* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between

@@ -82,3 +82,23 @@ def test_default_init_forward(golden_dir):
     audio = synth.make_windows(2, 1234)
     _, pr = model.predict(None, audio, A.precompute_frequencies(64, 300))
     assert np.abs(pr[1] - g["probs"]).max() < 2e-2
+
+
+def test_pipelined_host_path_matches_sync(setup):
+    """predict_pipelined (submit/collect on two slots, pinned buffers) returns the same numbers as predict."""
+    import audio_to_midi_b200 as A
+    model, _, audio, _, _, _ = setup
+    rope = A.precompute_frequencies(64, 300)
+    rng = np.random.Generator(np.random.PCG64(5))
+    batches = []
+    for i in range(5):
+        b = A.pinned_empty((2 + (i % 2), 2, 80000))          # ragged batch sizes
+        b[...] = audio[:1] * rng.uniform(0.5, 1.5, size=(b.shape[0], 1, 1)).astype(np.float32)
+        batches.append(b)
+    outs = list(model.predict_pipelined(iter(batches), rope))
+    assert len(outs) == 5
+    for b, (lg, pr) in zip(batches, outs):
+        lg_s, pr_s = model.predict(None, np.array(b), rope)
+        assert lg.shape == (b.shape[0], 250, 90)
+        assert np.array_equal(lg, lg_s) and np.array_equal(pr, pr_s)
+    assert list(model.predict_pipelined(iter([]), rope)) == []
