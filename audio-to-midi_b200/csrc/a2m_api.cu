@@ -23,6 +23,9 @@
 #include "cnn_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_wgrad.cuh"
+#include "attention_bwd.cuh"
+#include "train_kernels.cuh"
 
 using namespace a2m;
 
@@ -63,26 +66,54 @@ uint16_t f32_to_bf16(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 
-// Host image of the device weights arena.
+// Host image of the device weights arena.  In map mode (training) the "values" being packed are 1-based indices into
+// the fp32 master parameter blob (0 = constant zero) and the arena records, per packed element, where it comes from,
+// so that the same packing code drives the device-side re-pack after every optimizer step (pack_weights_kernel) and
+// the scatter of packed gradients back to the leaf layout (grad_unpack_kernel).
 struct Arena {
   std::vector<uint8_t> bytes;
+  bool map_mode = false;
+  std::vector<int> src, mul;          // per packed element: master index (or -1), multiplier index (or -1)
+  std::vector<uint32_t> dst;          // arena byte offset | 0x80000000 for bf16
+  std::map<size_t, size_t> ord;       // arena byte offset of a tensor -> ordinal of its first element
   size_t reserve(size_t n) {
     const size_t off = (bytes.size() + 255) & ~size_t(255);
     bytes.resize(off + n, 0);
     return off;
   }
-  size_t put_f32(const std::vector<float>& v) {
-    const size_t off = reserve(v.size() * 4);
-    std::memcpy(bytes.data() + off, v.data(), v.size() * 4);
+  static int to_index(float v) { return static_cast<int>(std::lround(v)) - 1; }
+  // mulv: empty, or one multiplier per element with NaN meaning "none"
+  size_t put(const std::vector<float>& v, bool bf16, const std::vector<float>& mulv = {}) {
+    const size_t es = bf16 ? 2 : 4;
+    const size_t off = reserve(v.size() * es);
+    ord[off] = dst.size();
+    if (map_mode) {
+      for (size_t i = 0; i < v.size(); ++i) {
+        src.push_back(to_index(v[i]));
+        mul.push_back((mulv.empty() || std::isnan(mulv[i])) ? -1 : to_index(mulv[i]));
+        dst.push_back(static_cast<uint32_t>(off + i * es) | (bf16 ? 0x80000000u : 0u));
+      }
+      return off;
+    }
+    n_elems += v.size();
+    for (size_t i = 0; i < v.size(); ++i) {
+      const float x = (mulv.empty() || std::isnan(mulv[i])) ? v[i] : v[i] * mulv[i];
+      if (bf16) reinterpret_cast<uint16_t*>(bytes.data() + off)[i] = f32_to_bf16(x);
+      else reinterpret_cast<float*>(bytes.data() + off)[i] = x;
+    }
     return off;
   }
-  size_t put_bf16(const std::vector<float>& v) {
-    const size_t off = reserve(v.size() * 2);
-    uint16_t* d = reinterpret_cast<uint16_t*>(bytes.data() + off);
-    for (size_t i = 0; i < v.size(); ++i) d[i] = f32_to_bf16(v[i]);
-    return off;
-  }
+  size_t n_elems = 0;
+  size_t put_f32(const std::vector<float>& v) { return put(v, false); }
+  size_t put_bf16(const std::vector<float>& v) { return put(v, true); }
 };
+
+std::vector<float> transposed(const std::vector<float>& v, int rows, int cols) {   // [rows, cols] -> [cols, rows]
+  std::vector<float> t(v.size());
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[static_cast<size_t>(c) * rows + r] = v[static_cast<size_t>(r) * cols + c];
+  return t;
+}
 
 struct BigBlockW {   // Block with C >= 64 (tensor-core path)
   size_t dwln;       // fp32: dw[7][C] | dwb[C] | lnw[C] | lnb[C]
@@ -91,13 +122,16 @@ struct BigBlockW {   // Block with C >= 64 (tensor-core path)
   size_t gamma;      // fp32 [C]
   size_t fused;      // fp32: dw[7][C] | dwb[C] | lnw[C] | lnb[C] | b1[2C] | gamma*b2[C]   (block_fused_kernel)
   size_t w2g;        // bf16 [C, 2C] = gamma[c] * point_conv_2[c, :]
+  size_t w1t, w2gt;  // training (dgrad B operands): bf16 [C, 2C] = w1^T, bf16 [2C, C] = w2g^T
 };
 struct BigDownW {
   size_t lnw, lnb;   // fp32 [Cin]
   size_t w, b;       // bf16 [Cout, 2*Cin] (k = tap * Cin + c), fp32 [Cout]
+  size_t wt;         // training: bf16 [2*Cin, Cout]
 };
 struct TLayerW {
   size_t ln1w, ln1b, wqc, wkv, wo, ln2w, ln2b, w1, b1, w2, b2;
+  size_t wqct, wkvt, wot, w1t, w2t;   // training: transposed bf16 copies (dgrad B operands)
 };
 
 struct Weights {
@@ -109,6 +143,8 @@ struct Weights {
   size_t fnw, fnb;
   TLayerW tl[2 * kNumTL];         // 2*i local, 2*i+1 global
   size_t dlnw, dlnb, dw, db;      // decoder: bf16 [128, 256] zero padded, fp32 [128]
+  size_t dwt;                     // training: bf16 [256, 128]
+  size_t stem_img;                // training: fp32 w[4][2][5] | b[4] | lnw[4] | lnb[4]  (stem_train_kernel)
 };
 
 struct Workspace {
@@ -171,6 +207,7 @@ struct Plan {
   cudaGraphExec_t graph = nullptr;
 };
 
+struct TrainState;
 }  // namespace
 
 struct A2mHandle {
@@ -209,6 +246,7 @@ struct A2mHandle {
   float* dev_rope_in = nullptr;
   std::vector<float> rope_host_cache;
   cudaStream_t own_stream = nullptr;
+  TrainState* train = nullptr;   // training path (a2m_train.inc)
 };
 
 namespace {
@@ -468,7 +506,7 @@ std::vector<float> vec(const LeafView& l, size_t offset = 0, size_t n = 0) {
   return std::vector<float>(l.p + offset, l.p + offset + n);
 }
 
-void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
+void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
   // ---- stem (model.py:84-100)
   {
     const std::string p = "layers.0.layers.0.";
@@ -480,6 +518,12 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
     std::memcpy(w->stem.b, cb.p, sizeof(float) * 4);
     std::memcpy(w->stem.ln_w, lw.p, sizeof(float) * 4);
     std::memcpy(w->stem.ln_b, lb.p, sizeof(float) * 4);
+    if (train) {
+      std::vector<float> img = vec(cw);
+      auto app = [&](const std::vector<float>& v) { img.insert(img.end(), v.begin(), v.end()); };
+      app(vec(cb)); app(vec(lw)); app(vec(lb));
+      w->stem_img = ar->put_f32(img);
+    }
   }
   for (int s = 0; s < kStages; ++s) {
     const int C = kDims[s], H = 2 * C;
@@ -508,6 +552,7 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
         w->big_down[s].lnb = ar->put_f32(vec(lb));
         w->big_down[s].w = ar->put_bf16(wk);
         w->big_down[s].b = ar->put_f32(vec(cb));
+        if (train) w->big_down[s].wt = ar->put_bf16(transposed(wk, C, 2 * Cin));
       }
     }
     // ---- blocks (model.py:120-167)
@@ -546,15 +591,20 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
         bw.b2 = ar->put_f32(vec(b2));
         bw.gamma = ar->put_f32(vec(gm));
         // fused-kernel image: layer scale folded into point_conv_2 (out = x + (gamma*W2) h + gamma*b2)
-        std::vector<float> fimg = img, w2g(static_cast<size_t>(C) * H), b2g(C);
-        { auto v1 = vec(b1); fimg.insert(fimg.end(), v1.begin(), v1.end()); }
+        const float kNone = std::nanf("");
+        std::vector<float> fimg = img, fmul(img.size(), kNone), w2s = vec(w2), w2m(static_cast<size_t>(C) * H);
+        { auto v1 = vec(b1); fimg.insert(fimg.end(), v1.begin(), v1.end()); fmul.insert(fmul.end(), v1.size(), kNone); }
         for (int c = 0; c < C; ++c) {
-          b2g[c] = gm.p[c] * b2.p[c];
-          for (int hh = 0; hh < H; ++hh) w2g[static_cast<size_t>(c) * H + hh] = gm.p[c] * w2.p[static_cast<size_t>(c) * H + hh];
+          fimg.push_back(b2.p[c]);
+          fmul.push_back(gm.p[c]);
+          for (int hh = 0; hh < H; ++hh) w2m[static_cast<size_t>(c) * H + hh] = gm.p[c];
         }
-        fimg.insert(fimg.end(), b2g.begin(), b2g.end());
-        bw.fused = ar->put_f32(fimg);
-        bw.w2g = ar->put_bf16(w2g);
+        bw.fused = ar->put(fimg, false, fmul);
+        bw.w2g = ar->put(w2s, true, w2m);
+        if (train) {
+          bw.w1t = ar->put_bf16(transposed(vec(w1), H, C));
+          bw.w2gt = ar->put(transposed(w2s, C, H), true, transposed(w2m, C, H));
+        }
       }
     }
   }
@@ -607,6 +657,13 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
       t.b1 = ar->put_f32(b1p);
       t.w2 = ar->put_bf16(vec(f2w, li * kD * kFF, kD * kFF));
       t.b2 = ar->put_f32(vec(f2b, li * kD, kD));
+      if (train) {
+        t.wqct = ar->put_bf16(transposed(qc, kQC, kD));
+        t.wkvt = ar->put_bf16(transposed(kv, kKV, 64));
+        t.wot = ar->put_bf16(transposed(vec(wo, li * kD * 256, kD * 256), kD, 256));
+        t.w1t = ar->put_bf16(transposed(w1p, 2 * kFF, kD));
+        t.w2t = ar->put_bf16(transposed(vec(f2w, li * kD * kFF, kD * kFF), kD, kFF));
+      }
     }
   }
   // ---- decoder (model.py:169-198): N = 90 padded to 128 with zero rows
@@ -618,6 +675,7 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar) {
     std::memcpy(bp.data(), dbs.p, sizeof(float) * A2M_VOCAB);
     w->dw = ar->put_bf16(wp);
     w->db = ar->put_f32(bp);
+    if (train) w->dwt = ar->put_bf16(transposed(wp, 128, kD));
     w->dlnw = ar->put_f32(vec(leaf(m, "decoder.norm.weight", {kD})));
     w->dlnb = ar->put_f32(vec(leaf(m, "decoder.norm.bias", {kD})));
   }
@@ -842,7 +900,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (!make_tmap(h, &tk, kv, Mt, 256, kKV, 64, 256)) return false;
       if (!make_tmap(h, &tv, kv, Mt, kKV, kKV, 64, 256)) return false;   // V = columns 256..511, row-major [key][d]
       add_step(p, Meta{"attn_global_kernel", 2.0 * B * ATT_HEADS * (2.0 * kT * kT * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
-        return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256);
+        return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256, static_cast<float*>(nullptr));
       });
     }
     {
@@ -1008,6 +1066,8 @@ int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, co
 
 }  // namespace
 
+#include "a2m_train.inc"
+
 // ============================================================================================= C ABI
 extern "C" {
 
@@ -1063,6 +1123,7 @@ void a2m_destroy(A2mHandle* h) {
   if (h->pin_rope) cudaFreeHost(h->pin_rope);
   if (h->dev_rope_in) cudaFree(h->dev_rope_in);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  train_free(h);
   delete h;
 }
 
@@ -1083,9 +1144,10 @@ int a2m_load_weights(A2mHandle* h, const void* blob, size_t blob_bytes, const A2
     v.p = reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob) + table[i].offset_bytes);
     m[table[i].path] = v;
   }
+  train_free(h);   // a plain weight load ends a training session on this handle (its arena layout differs)
   Arena ar;
   try {
-    pack_weights(m, &h->w, &ar);
+    pack_weights(m, &h->w, &ar, false);
   } catch (const PackError& e) {
     h->err = e.msg;
     return A2M_EINVAL;

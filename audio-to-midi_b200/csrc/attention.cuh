@@ -35,7 +35,8 @@ constexpr uint32_t AG_TMEM_COLS = 256;    // S: 256 columns; O re-uses columns 0
 // tmV: V [B*256, ldkv] (columns 256 + h*64 ..) box {64,256}.  Q and K arrive RoPE-rotated (GEMM epilogue).
 __global__ void __launch_bounds__(AG_THREADS, 2)
 attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int v_col0) {
+                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int v_col0,
+                   float* __restrict__ lse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -158,6 +159,8 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   mbar_wait(bar_o, 0);
   tc_fence_after();
   const float inv = __fdividef(1.0f, sum);
+  // training: natural-log softmax denominator per (row, head), P = exp(s / 8 - lse)  (attention_bwd.cuh)
+  if (lse != nullptr) lse[static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ATT_HEADS + h] = mx * 0.125f + __logf(sum);
   __nv_bfloat16* dst = O + static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ldo + h * ATT_HD;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {

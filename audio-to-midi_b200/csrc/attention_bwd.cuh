@@ -1,0 +1,384 @@
+// Backward of the attention cores (the `eqx.filter_value_and_grad` of model.py:241-257 / 409-471 inside train.py:50).
+//
+//   attn_global_bwd_kernel  one CTA per (window b, head h); all five products of the flash-style backward on
+//                           tcgen05 with fp32 accumulators in TMEM:
+//                               S = Q K^T,  dP = dO V^T                      (recomputed, K-major operands)
+//                               P = exp(S/8 - lse),  dS = P o (dP - D) / 8   (CUDA cores, from TMEM)
+//                               dV += P^T dO,  dK += dS^T Q                  (A operand MN-major: P / dS as stored)
+//                               dQ += dS K                                   (B operand MN-major: K as stored)
+//                           then the inverse RoPE rotation of dQ / dK in the epilogue, bf16 stores.
+//   attn_local_bwd_kernel   LocalSelfAttention: 31 windows of 16 x 16 per (b, h) on CUDA cores (tiny tiles).
+//
+// Inputs are the RoPE-rotated bf16 projections the forward wrote (q||c and k||v buffers), the forward output O,
+// the softmax log-sum-exp per (row, head), and dO (bf16).  Outputs: dQ (raw, pre-RoPE) into the q columns of the
+// dQC buffer, dK (raw) || dV into the dKV buffer.  Rows 250..255 of every window are written as zeros.
+#pragma once
+#include "attention.cuh"
+#include "gemm_wgrad.cuh"
+
+namespace a2m {
+
+constexpr int AGB_THREADS = 256;
+constexpr int AGB_TILE = 128 * 64 * 2;               // 16 KB: one 128-row tile of a [rows][64] bf16 operand
+constexpr int AGB_OPER = 2 * AGB_TILE;               // 32 KB: 256 rows
+constexpr int AGB_PS = 2 * 128 * 64 * 2;             // 32 KB: P or dS tile [128 q][128 keys] as two k-blocks of 64 keys
+constexpr size_t AGB_SMEM = 1024 + 4 * AGB_OPER + 2 * AGB_PS + 128;   // ~193 KB
+constexpr uint32_t AGB_TMEM_COLS = 512;
+
+// TMEM columns
+constexpr uint32_t AGB_C_S = 0, AGB_C_DP = 128, AGB_C_DK = 256, AGB_C_DV = 320, AGB_C_DQ0 = 384, AGB_C_DQ1 = 448;
+
+// tmQ: q||c buffer [B*256, ldq], tmK / tmV: k||v buffer, tmDO: dO [B*256, 256]; all box {64, 256}.
+// lse [B*256, 4] fp32 (natural log of the row's softmax denominator, including the running max);
+// O, dO row-major bf16 with leading dimension ldo.
+__global__ void __launch_bounds__(AGB_THREADS, 1)
+attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                       const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, int ldo,
+                       const float* __restrict__ lse, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+                       __nv_bfloat16* __restrict__ dQ, int lddq, __nv_bfloat16* __restrict__ dKV, int lddkv, int v_col0) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AGB_OPER;
+  uint8_t* sV = sK + AGB_OPER;
+  uint8_t* sDO = sV + AGB_OPER;
+  uint8_t* sP = sDO + AGB_OPER;
+  uint8_t* sDS = sP + AGB_PS;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sDS + AGB_PS);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant; which 64 of a tile's 128 columns
+  const int row = quad * 32 + lane;              // row inside a 128-row tile
+  const uint32_t t_row = static_cast<uint32_t>(quad * 32) << 16;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<AGB_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128);        // S, dP: both K-major
+  constexpr uint32_t idesc_ab = umma_idesc_bf16_abmn(128, 64);    // dV, dK: A (P / dS) and B (dO / Q) MN-major
+  constexpr uint32_t idesc_b = umma_idesc_bf16_bmn(128, 64);      // dQ: A (dS) K-major, B (K) MN-major
+
+  auto issue_scores = [&](int i, int j) {   // S = Q_i K_j^T, dP = dO_i V_j^T
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ + i * AGB_TILE)), dk = umma_desc_sw128(smem_u32(sK + j * AGB_TILE));
+    const uint64_t dd = umma_desc_sw128(smem_u32(sDO + i * AGB_TILE)), dv = umma_desc_sw128(smem_u32(sV + j * AGB_TILE));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + AGB_C_S, umma_desc_advance_k(dq, k * 32), umma_desc_advance_k(dk, k * 32), idesc_kk, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + AGB_C_DP, umma_desc_advance_k(dd, k * 32), umma_desc_advance_k(dv, k * 32), idesc_kk, k != 0);
+  };
+  auto issue_grads = [&](int i, int j) {
+    // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (reduction over the 128 queries of tile i: 8 steps of 16 rows)
+    const uint64_t ap = umma_desc_sw128_mn(smem_u32(sP), 128 * 128), as = umma_desc_sw128_mn(smem_u32(sDS), 128 * 128);
+    const uint64_t bd = umma_desc_sw128(smem_u32(sDO + i * AGB_TILE)), bq = umma_desc_sw128(smem_u32(sQ + i * AGB_TILE));
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16(tmem + AGB_C_DV, umma_desc_advance_k(ap, k * 2048), umma_desc_advance_k(bd, k * 2048), idesc_ab, (i | k) != 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16(tmem + AGB_C_DK, umma_desc_advance_k(as, k * 2048), umma_desc_advance_k(bq, k * 2048), idesc_ab, (i | k) != 0);
+    // dQ_i += dS K_j   (reduction over the 128 keys of tile j: 2 k-blocks of 64 keys x 4 steps)
+    const uint64_t bk = umma_desc_sw128(smem_u32(sK + j * AGB_TILE));
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      const uint64_t a = umma_desc_sw128(smem_u32(sDS + kb * (128 * 128)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem + (i == 0 ? AGB_C_DQ0 : AGB_C_DQ1), umma_desc_advance_k(a, k * 32),
+                  umma_desc_advance_k(bk, (kb * 4 + k) * 2048), idesc_b, (j | kb | k) != 0);
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, 4 * AGB_OPER);
+    tma_load_2d(sQ, &tmQ, bar_load, h * ATT_HD, b * ATT_TP);
+    tma_load_2d(sK, &tmK, bar_load, h * ATT_HD, b * ATT_TP);
+    tma_load_2d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, b * ATT_TP);
+    tma_load_2d(sDO, &tmDO, bar_load, h * ATT_HD, b * ATT_TP);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    issue_scores(0, 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  // per-row constants for both query tiles: D = rowsum(dO o O), lse
+  float Dv[2], Lv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const size_t grow = static_cast<size_t>(b) * ATT_TP + i * 128 + row;
+    const uint4* po = reinterpret_cast<const uint4*>(O + grow * ldo + h * ATT_HD);
+    const uint4* pd = reinterpret_cast<const uint4*>(dO + grow * ldo + h * ATT_HD);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 a = __ldg(po + q), c = __ldg(pd + q);
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 fa = __bfloat1622float2(ha[t]), fc = __bfloat1622float2(hc[t]);
+        acc = fmaf(fa.x, fc.x, acc);
+        acc = fmaf(fa.y, fc.y, acc);
+      }
+    }
+    Dv[i] = acc;
+    Lv[i] = __ldg(lse + grow * ATT_HEADS + h) * 1.4426950408889634f;   // log2 domain
+  }
+
+  // inverse RoPE + bf16 store of a 64-column accumulator (this thread: row `r_in_win`, columns half*32 .. +31)
+  auto store_rot = [&](uint32_t tcol, int r_in_win, __nv_bfloat16* dst_base, int ld, int col0, bool rotate) {
+    uint32_t r[32];
+    tmem_ld_x32(tmem + t_row + tcol + half * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    const bool real = r_in_win < ATT_T;
+    if (rotate && real) {
+      const float4* cp = reinterpret_cast<const float4*>(rope_cos + r_in_win * 32 + half * 16);
+      const float4* sp = reinterpret_cast<const float4*>(rope_sin + r_in_win * 32 + half * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 cs = __ldg(cp + j), sn = __ldg(sp + j);
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float y1 = v[8 * j + 2 * t], y2 = v[8 * j + 2 * t + 1];
+          v[8 * j + 2 * t] = y1 * cc[t] + y2 * ss[t];
+          v[8 * j + 2 * t + 1] = -y1 * ss[t] + y2 * cc[t];
+        }
+      }
+    }
+    __nv_bfloat16* dst = dst_base + (static_cast<size_t>(b) * ATT_TP + r_in_win) * ld + col0 + h * ATT_HD + half * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = real ? pack_bf16x2_att(v[8 * q], v[8 * q + 1]) : 0u;
+      o.y = real ? pack_bf16x2_att(v[8 * q + 2], v[8 * q + 3]) : 0u;
+      o.z = real ? pack_bf16x2_att(v[8 * q + 4], v[8 * q + 5]) : 0u;
+      o.w = real ? pack_bf16x2_att(v[8 * q + 6], v[8 * q + 7]) : 0u;
+      reinterpret_cast<uint4*>(dst)[q] = o;
+    }
+  };
+
+  const float kscale = 0.125f * 1.4426950408889634f;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; ++blk) {
+    const int j = blk >> 1, i = blk & 1;
+    mbar_wait(bar_mma, blk & 1);
+    tc_fence_after();
+    if (blk == 2) {   // key tile 0 is complete
+      store_rot(AGB_C_DK, row, dKV, lddkv, 0, true);
+      store_rot(AGB_C_DV, row, dKV, lddkv, v_col0, false);
+    }
+    const bool qreal = i * 128 + row < ATT_T;
+    const float Dr = Dv[i], Lr = Lv[i];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = half * 64 + c * 32;     // key column inside the tile
+      uint32_t rs[32], rp[32];
+      tmem_ld_x32(tmem + t_row + AGB_C_S + col0, rs);
+      tmem_ld_x32(tmem + t_row + AGB_C_DP + col0, rp);
+      tmem_ld_wait();
+      uint32_t pp[16], ps[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        float p2[2], d2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int key = j * 128 + col0 + 2 * t + u;
+          float p = exp2f(__uint_as_float(rs[2 * t + u]) * kscale - Lr);
+          p = (key < ATT_T && qreal) ? p : 0.f;
+          p2[u] = p;
+          d2[u] = p * (__uint_as_float(rp[2 * t + u]) - Dr) * 0.125f;
+        }
+        pp[t] = pack_bf16x2_att(p2[0], p2[1]);
+        ps[t] = pack_bf16x2_att(d2[0], d2[1]);
+      }
+      // [128 q][64 keys] k-block `half`, 128B-swizzled rows; this thread's 32 columns = chunks 4c .. 4c+3
+      uint8_t* bp = sP + half * (128 * 128);
+      uint8_t* bs = sDS + half * (128 * 128);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4*>(bp + sw128_offset(row, c * 32 + 8 * q)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+        *reinterpret_cast<uint4*>(bs + sw128_offset(row, c * 32 + 8 * q)) = make_uint4(ps[4 * q], ps[4 * q + 1], ps[4 * q + 2], ps[4 * q + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_grads(i, j);
+      if (blk < 3) issue_scores((blk + 1) & 1, (blk + 1) >> 1);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  store_rot(AGB_C_DK, 128 + row, dKV, lddkv, 0, true);
+  store_rot(AGB_C_DV, 128 + row, dKV, lddkv, v_col0, false);
+  store_rot(AGB_C_DQ0, row, dQ, lddq, 0, true);
+  store_rot(AGB_C_DQ1, 128 + row, dQ, lddq, 0, true);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<AGB_TMEM_COLS>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ local (CUDA cores)
+// One CTA per (window b, head h).  Padded row j (0..255) <-> token j - 3; pad tokens are zero rows.  Window w
+// (0..30) covers padded rows 8w .. 8w+15; the output row of padded row j is token-buffer row j (model.py:452-464,
+// the reference's index shift), rows >= 250 are dropped, the mean is over the covering windows.
+constexpr int ALB_THREADS = 256;
+constexpr int ALB_ROWS = 256;
+constexpr int ALB_LD = 66;   // bf16 elements per smem row (odd word stride: conflict-free row-strided reads)
+constexpr size_t ALB_SMEM = 4 * ALB_ROWS * ALB_LD * 2 + 2 * 31 * 256 * 4;   // q, k, v, dO tiles + P / dS: ~199 KB
+
+// Q [B*256, ldq] (q columns, RoPE-rotated), KV [B*256, ldkv] (k rotated || v at v_col0), dOut [B*256, ldo] bf16:
+// gradient wrt the local-attention output rows (buffer row j = padded row j).  Outputs like the global kernel.
+__global__ void __launch_bounds__(ALB_THREADS, 1)
+attn_local_bwd_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ KV, int ldkv, int v_col0,
+                      const __nv_bfloat16* __restrict__ dOut, int ldo, const float* __restrict__ rope_cos,
+                      const float* __restrict__ rope_sin, __nv_bfloat16* __restrict__ dQ, int lddq,
+                      __nv_bfloat16* __restrict__ dKV, int lddkv) {
+  extern __shared__ uint8_t smem_raw[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sk = sq + ALB_ROWS * ALB_LD;
+  __nv_bfloat16* sv = sk + ALB_ROWS * ALB_LD;
+  __nv_bfloat16* sd = sv + ALB_ROWS * ALB_LD;
+  float* sP = reinterpret_cast<float*>(sd + ALB_ROWS * ALB_LD);   // [31][16][16]  wn * softmax
+  float* sS = sP + 31 * 256;                                       // [31][16][16]  dS (already / 8)
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- stage q, k, v (padded-row indexed, zero pad tokens) and dOut (output-row indexed, zero rows >= 250)
+  for (int idx = threadIdx.x; idx < ALB_ROWS * 32; idx += ALB_THREADS) {
+    const int j = idx >> 5, cpair = idx & 31;
+    const int tok = j - 3;
+    uint32_t q = 0u, k = 0u, v = 0u, d = 0u;
+    if (tok >= 0 && tok < ATT_T) {
+      const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
+      q = __ldg(reinterpret_cast<const uint32_t*>(Q + g * ldq + h * ATT_HD) + cpair);
+      k = __ldg(reinterpret_cast<const uint32_t*>(KV + g * ldkv + h * ATT_HD) + cpair);
+      v = __ldg(reinterpret_cast<const uint32_t*>(KV + g * ldkv + v_col0 + h * ATT_HD) + cpair);
+    }
+    if (j < ATT_T) d = __ldg(reinterpret_cast<const uint32_t*>(dOut + (static_cast<size_t>(b) * ATT_TP + j) * ldo + h * ATT_HD) + cpair);
+    reinterpret_cast<uint32_t*>(sq + j * ALB_LD)[cpair] = q;
+    reinterpret_cast<uint32_t*>(sk + j * ALB_LD)[cpair] = k;
+    reinterpret_cast<uint32_t*>(sv + j * ALB_LD)[cpair] = v;
+    reinterpret_cast<uint32_t*>(sd + j * ALB_LD)[cpair] = d;
+  }
+  __syncthreads();
+
+  // ---- phase 1: per (window, row): softmax row and dS row
+  for (int wr = threadIdx.x; wr < 31 * 16; wr += ALB_THREADS) {
+    const int w = wr >> 4, r = wr & 15;
+    const int j = 8 * w + r;
+    const bool has_a = j >= 8, has_b = j < 248;
+    const float wn = (j < ATT_T) ? ((has_a && has_b) ? 0.5f : 1.0f) : 0.f;   // rows >= 250 are dropped by the scatter
+    float s[16], dp[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { s[k] = 0.f; dp[k] = 0.f; }
+    const __nv_bfloat162* qr = reinterpret_cast<const __nv_bfloat162*>(sq + j * ALB_LD);
+    const __nv_bfloat162* dr = reinterpret_cast<const __nv_bfloat162*>(sd + j * ALB_LD);
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      const float2 qv = __bfloat1622float2(qr[c]), dv = __bfloat1622float2(dr[c]);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 kv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sk + (8 * w + k) * ALB_LD)[c]);
+        const float2 vv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sv + (8 * w + k) * ALB_LD)[c]);
+        s[k] = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, s[k]));
+        dp[k] = fmaf(dv.x, vv.x, fmaf(dv.y, vv.y, dp[k]));
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) mx = fmaxf(mx, s[k]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { s[k] = __expf((s[k] - mx) * 0.125f); sum += s[k]; }
+    const float inv = wn / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { s[k] *= inv; dot = fmaf(s[k], dp[k], dot); }   // s = wn * p
+    // d logit_k = wn p_k (dp_k - sum_k' p_k' dp_k') / 8, and dot = wn * sum p dp  ->  s_k (dp_k - dot / wn) / 8
+    const float mean = (wn > 0.f) ? dot / wn : 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      sP[wr * 16 + k] = s[k];
+      sS[wr * 16 + k] = s[k] * (dp[k] - mean) * 0.125f;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: gather per padded row; a warp owns a row, a lane owns a pair of head dims
+  for (int j = warp; j < ALB_ROWS; j += ALB_THREADS / 32) {
+    const int tok = j - 3;
+    if (tok < 0 || tok >= ATT_T) continue;   // pad tokens carry no gradient
+    float2 aq = make_float2(0.f, 0.f), ak = aq, av = aq;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int w = (j >> 3) - 1 + t;      // the two windows that contain padded row j
+      if (w < 0 || w > 30) continue;
+      const int r = j - 8 * w;             // row (as a query) / column (as a key) inside the window
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        const int o = 8 * w + k;
+        const float ds_qk = sS[(w * 16 + r) * 16 + k];     // query j, key o
+        const float ds_kq = sS[(w * 16 + k) * 16 + r];     // query o, key j
+        const float p_kq = sP[(w * 16 + k) * 16 + r];
+        const float2 kk = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sk + o * ALB_LD)[lane]);
+        const float2 qq = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sq + o * ALB_LD)[lane]);
+        const float2 dd = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sd + o * ALB_LD)[lane]);
+        aq.x = fmaf(ds_qk, kk.x, aq.x); aq.y = fmaf(ds_qk, kk.y, aq.y);
+        ak.x = fmaf(ds_kq, qq.x, ak.x); ak.y = fmaf(ds_kq, qq.y, ak.y);
+        av.x = fmaf(p_kq, dd.x, av.x); av.y = fmaf(p_kq, dd.y, av.y);
+      }
+    }
+    // inverse RoPE at the token's absolute position (the forward rotated q / k with it, see attention.cuh)
+    const float c = __ldg(rope_cos + tok * 32 + lane), s = __ldg(rope_sin + tok * 32 + lane);
+    const float2 rq = make_float2(aq.x * c + aq.y * s, -aq.x * s + aq.y * c);
+    const float2 rk = make_float2(ak.x * c + ak.y * s, -ak.x * s + ak.y * c);
+    const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
+    reinterpret_cast<uint32_t*>(dQ + g * lddq + h * ATT_HD)[lane] = pack_bf16x2_att(rq.x, rq.y);
+    reinterpret_cast<uint32_t*>(dKV + g * lddkv + h * ATT_HD)[lane] = pack_bf16x2_att(rk.x, rk.y);
+    reinterpret_cast<uint32_t*>(dKV + g * lddkv + v_col0 + h * ATT_HD)[lane] = pack_bf16x2_att(av.x, av.y);
+  }
+  // rows 250..255 of the gradient buffers stay zero: written once here by the CTA of head h
+  for (int idx = threadIdx.x; idx < (ATT_TP - ATT_T) * 32; idx += ALB_THREADS) {
+    const int tok = ATT_T + (idx >> 5), cpair = idx & 31;
+    const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
+    reinterpret_cast<uint32_t*>(dQ + g * lddq + h * ATT_HD)[cpair] = 0u;
+    reinterpret_cast<uint32_t*>(dKV + g * lddkv + h * ATT_HD)[cpair] = 0u;
+    reinterpret_cast<uint32_t*>(dKV + g * lddkv + v_col0 + h * ATT_HD)[cpair] = 0u;
+  }
+}
+
+}  // namespace a2m

@@ -1,0 +1,970 @@
+// CUDA-core kernels of the training path (train.py:39-62, 259-332): loss gradient, the memory-bound backward glue
+// (LayerNorm, GELU / GLU, depthwise conv), the small-channel CNN stages, gradient (un)packing and AdamW.
+// Parameter gradients are accumulated in fp32 into a "packed gradient" buffer that mirrors the packed weight
+// images the forward kernels read (same layouts), and are scattered back to the reference's leaf layout by
+// grad_unpack_kernel.  Per-channel reductions keep per-thread register partials over a grid-stride loop and
+// finish with one shared-memory reduction and one atomicAdd per channel per CTA.
+#pragma once
+#include "cnn_kernels.cuh"
+#include "gemm_tc.cuh"
+
+namespace a2m {
+
+// d/dx of gelu_tanh(x) = x * sigmoid(2u), u = k (x + a x^3)
+__device__ __forceinline__ void gelu_tanh_grad(float x, float* g, float* dg) {
+  const float k = 0.7978845608028654f, a = 0.044715f;
+  const float u = k * (x + a * x * x * x);
+  const float s = __fdividef(1.0f, 1.0f + __expf(-2.0f * u));
+  *g = x * s;
+  *dg = s + x * s * (1.0f - s) * 2.0f * k * (1.0f + 3.0f * a * x * x);
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// ------------------------------------------------------------------------------------------ loss
+// logits, labels [B, 250, 90] fp32 -> dz [B*256, 128] bf16 (zero in the padding) = (sigmoid(z) - y) * gscale,
+// loss[0] += sum BCEWithLogits(z, y) * lscale   (optax.sigmoid_binary_cross_entropy, train.py:43-47, 61-62)
+__global__ void __launch_bounds__(256) bce_grad_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                       __nv_bfloat16* __restrict__ dz, float* __restrict__ loss, int B,
+                                                       float gscale, float lscale) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;   // over B*256*128
+  float l = 0.f;
+  if (idx < B * 256 * 128) {
+    const int col = idx & 127, row = (idx >> 7) & 255, b = idx >> 15;
+    float d = 0.f;
+    if (col < 90 && row < 250) {
+      const size_t o = (static_cast<size_t>(b) * 250 + row) * 90 + col;
+      const float z = logits[o], y = labels[o];
+      const float p = __fdividef(1.0f, 1.0f + __expf(-z));
+      d = (p - y) * gscale;
+      l = (fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)))) * lscale;
+    }
+    dz[idx] = __float2bfloat16_rn(d);
+  }
+  l = warp_sum(l);
+  __shared__ float sl[8];
+  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sl[i];
+    atomicAdd(loss, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ column sums (bias grads)
+// out[n] += sum_rows dY[row, n]   (bf16 [M, N], N % 8 == 0, N <= 1024)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, int ld, int M, int N,
+                                                          float* __restrict__ out) {
+  const int groups = N / 8;                 // uint4 column groups
+  const int rows_per_it = 256 / groups > 0 ? 256 / groups : 1;
+  // thread -> (column group cg, row lane rl); N <= 1024 -> groups <= 128
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < rows_per_it) {
+    for (int r = blockIdx.x * rows_per_it + rl; r < M; r += gridDim.x * rows_per_it) {
+      const uint4 v = *reinterpret_cast<const uint4*>(dY + static_cast<size_t>(r) * ld + cg * 8);
+      acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+      acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+    }
+  }
+  __shared__ float s[256 * 8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float t = 0.f;
+    const int g = c / 8, j = c % 8;
+    for (int r = 0; r < rows_per_it; ++r) t += s[(r * groups + g) * 8 + j];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm backward (rows)
+// y = xhat * w + b over a row of C channels (model.py:100,117,162,190,539,546,759).  One warp per row, grid-stride.
+//   X    fp32 rows (compact [B*Lx] layout), dY fp32 rows ([B*Ly] layout; row t of window b is valid for t < Lx)
+//   dX   fp32 [B*Lx]: ACCUMULATE ? dX += dx : dX = dx;  dX16 optional bf16 copy of the final dX
+//   gw / gb: fp32 [C] accumulated with atomics
+template <int C, bool ACCUMULATE>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* X, const float* dY, int nB, int Lx, int Ly,
+                                                     const float* __restrict__ lnw, float* dX, __nv_bfloat16* dX16,
+                                                     float* __restrict__ gw, float* __restrict__ gb) {
+  using RM = RowMap<C>;
+  constexpr int PER = RM::PER;
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float lw[PER], aw[PER], ab[PER];
+  RM::load(lnw, lane, lw);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { aw[j] = 0.f; ab[j] = 0.f; }
+  pdl_wait();
+  const int rows = nB * Lx;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const int b = r / Lx, t = r - b * Lx;
+    float x[PER], dy[PER];
+    RM::load(X + static_cast<size_t>(r) * C, lane, x);
+    RM::load(dY + (static_cast<size_t>(b) * Ly + t) * C, lane, dy);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) s += x[j];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { x[j] -= mean; v += x[j] * x[j]; }
+    const float inv = rsqrtf(warp_sum(v) * (1.0f / C) + kLnEps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      x[j] *= inv;                       // xhat
+      aw[j] += dy[j] * x[j];
+      ab[j] += dy[j];
+      dy[j] *= lw[j];                    // d xhat
+      s1 += dy[j];
+      s2 += dy[j] * x[j];
+    }
+    s1 = warp_sum(s1) * (1.0f / C);
+    s2 = warp_sum(s2) * (1.0f / C);
+    float dx[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) dx[j] = inv * (dy[j] - s1 - x[j] * s2);
+    float* dst = dX + static_cast<size_t>(r) * C;
+    if constexpr (ACCUMULATE) {
+      float old[PER];
+      RM::load(dst, lane, old);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) dx[j] += old[j];
+    }
+    RM::store_f32(dst, lane, dx);
+    if (dX16 != nullptr) RM::store_bf16(dX16 + static_cast<size_t>(r) * C, lane, dx);
+  }
+  __shared__ float sw[8][C], sb[8][C];
+#pragma unroll
+  for (int g = 0; g < RM::G; ++g)
+#pragma unroll
+    for (int j = 0; j < RM::VW; ++j) {
+      sw[warp][RM::chan(lane, g) + j] = aw[g * RM::VW + j];
+      sb[warp][RM::chan(lane, g) + j] = ab[g * RM::VW + j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tw += sw[w][c]; tb += sb[w][c]; }
+    atomicAdd(gw + c, tw);
+    atomicAdd(gb + c, tb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ GELU / GLU
+// h = gelu(u)  (bf16, n8 = elements / 8)
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* U, __nv_bfloat16* Hh, size_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n8; i += gridDim.x * 256ull) {
+    const uint4 u = reinterpret_cast<const uint4*>(U)[i];
+    uint4 o;
+    o.x = pack_bf16x2(gelu_tanh_f(bf16lo(u.x)), gelu_tanh_f(bf16hi(u.x)));
+    o.y = pack_bf16x2(gelu_tanh_f(bf16lo(u.y)), gelu_tanh_f(bf16hi(u.y)));
+    o.z = pack_bf16x2(gelu_tanh_f(bf16lo(u.z)), gelu_tanh_f(bf16hi(u.z)));
+    o.w = pack_bf16x2(gelu_tanh_f(bf16lo(u.w)), gelu_tanh_f(bf16hi(u.w)));
+    reinterpret_cast<uint4*>(Hh)[i] = o;
+  }
+}
+// du = dh * gelu'(u)   (in place over dh allowed)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* U, const __nv_bfloat16* dH, __nv_bfloat16* dU, size_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n8; i += gridDim.x * 256ull) {
+    const uint4 u = reinterpret_cast<const uint4*>(U)[i];
+    const uint4 d = reinterpret_cast<const uint4*>(dH)[i];
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float g0, g1, d0, d1;
+      gelu_tanh_grad(bf16lo(uu[q]), &g0, &d0);
+      gelu_tanh_grad(bf16hi(uu[q]), &g1, &d1);
+      oo[q] = pack_bf16x2(bf16lo(dd[q]) * d0, bf16hi(dd[q]) * d1);
+    }
+    reinterpret_cast<uint4*>(dU)[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  }
+}
+// FeedForwardBlock gate (model.py:233-234) in the tile-permuted layout of the packed FFN-1 weight: U [rows, 2F] holds,
+// per 256-column tile tb, 128 "gelu" columns then their 128 "gate" columns; H [rows, F] column tb*128 + r.
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const __nv_bfloat16* U, __nv_bfloat16* Hh, int rows, int F) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int per_row = F / 8;
+  const size_t n = static_cast<size_t>(rows) * per_row;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const int r = static_cast<int>(i / per_row), c8 = static_cast<int>(i % per_row) * 8;
+    const int tb = c8 >> 7, rr = c8 & 127;
+    const __nv_bfloat16* up = U + static_cast<size_t>(r) * 2 * F + tb * 256 + rr;
+    const uint4 a = *reinterpret_cast<const uint4*>(up), g = *reinterpret_cast<const uint4*>(up + 128);
+    uint4 o;
+    o.x = pack_bf16x2(gelu_tanh_f(bf16lo(a.x)) * bf16lo(g.x), gelu_tanh_f(bf16hi(a.x)) * bf16hi(g.x));
+    o.y = pack_bf16x2(gelu_tanh_f(bf16lo(a.y)) * bf16lo(g.y), gelu_tanh_f(bf16hi(a.y)) * bf16hi(g.y));
+    o.z = pack_bf16x2(gelu_tanh_f(bf16lo(a.z)) * bf16lo(g.z), gelu_tanh_f(bf16hi(a.z)) * bf16hi(g.z));
+    o.w = pack_bf16x2(gelu_tanh_f(bf16lo(a.w)) * bf16lo(g.w), gelu_tanh_f(bf16hi(a.w)) * bf16hi(g.w));
+    *reinterpret_cast<uint4*>(Hh + static_cast<size_t>(r) * F + c8) = o;
+  }
+}
+// dU (same permuted layout as U) from dH [rows, F]
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* U, const __nv_bfloat16* dH, __nv_bfloat16* dU, int rows, int F) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int per_row = F / 8;
+  const size_t n = static_cast<size_t>(rows) * per_row;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const int r = static_cast<int>(i / per_row), c8 = static_cast<int>(i % per_row) * 8;
+    const int tb = c8 >> 7, rr = c8 & 127;
+    const size_t uo = static_cast<size_t>(r) * 2 * F + tb * 256 + rr;
+    const uint4 a = *reinterpret_cast<const uint4*>(U + uo), g = *reinterpret_cast<const uint4*>(U + uo + 128);
+    const uint4 d = *reinterpret_cast<const uint4*>(dH + static_cast<size_t>(r) * F + c8);
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, gg[4] = {g.x, g.y, g.z, g.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float g0, g1, d0, d1;
+      gelu_tanh_grad(bf16lo(aa[q]), &g0, &d0);
+      gelu_tanh_grad(bf16hi(aa[q]), &g1, &d1);
+      const float dl = bf16lo(dd[q]), dh = bf16hi(dd[q]);
+      o1[q] = pack_bf16x2(dl * bf16lo(gg[q]) * d0, dh * bf16hi(gg[q]) * d1);
+      o2[q] = pack_bf16x2(dl * g0, dh * g1);
+    }
+    *reinterpret_cast<uint4*>(dU + uo) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(dU + uo + 128) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+// fp32 -> bf16 copy (n4 = elements / 4)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* X, __nv_bfloat16* Y, size_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n4; i += gridDim.x * 256ull) {
+    const float4 v = reinterpret_cast<const float4*>(X)[i];
+    reinterpret_cast<uint2*>(Y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Block (C >= 64): dwconv + LN backward
+// Forward (model.py:160-162): y = dwconv7(x) + b ; a = LN(y).  Given dA (grad wrt a, fp32) and dOut (grad wrt the Block
+// output == grad wrt the residual branch input), produces
+//     dX = dOut + dwconv7^T( LN'(dA) )      (fp32 + bf16 copy)
+// and accumulates the parameter gradients in the packed image layout  dw[7][C] | dwb[C] | lnw[C] | lnb[C].
+// Tile of DWB_TOK tokens per iteration; g = LN'(dA) is recomputed for 3 halo rows on each side.
+constexpr int DWB_TOK = 32;
+constexpr int DWB_THREADS = 256;
+template <int C>
+constexpr size_t dwconv_ln_bwd_smem() { return static_cast<size_t>((DWB_TOK + 12) + (DWB_TOK + 6)) * C * 4 + 8 * 10 * C * 4; }
+
+template <int C>
+__global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float* X, const float* dA, const float* dOut, float* dX,
+                                                                    __nv_bfloat16* dX16, int L, int M,
+                                                                    const float* __restrict__ params, float* __restrict__ gparams) {
+  using RM = RowMap<C>;
+  constexpr int PER = RM::PER;
+  extern __shared__ __align__(16) float smem_f[];
+  float* sx = smem_f;                          // rows tile0-6 .. tile0+TOK+5
+  float* sg = sx + (DWB_TOK + 12) * C;         // rows tile0-3 .. tile0+TOK+2
+  float* sred = sg + (DWB_TOK + 6) * C;        // [8 warps][10][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  float w[7][PER], bias[PER], lw[PER];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) RM::load(params + t * C, lane, w[t]);
+  RM::load(params + 7 * C, lane, bias);
+  RM::load(params + 8 * C, lane, lw);
+  float gdw[7][PER], gdb[PER], glw[PER], glb[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    gdb[j] = glw[j] = glb[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) gdw[t][j] = 0.f;
+  }
+  pdl_wait();
+  const int ntiles = (M + DWB_TOK - 1) / DWB_TOK;
+  constexpr int V = C / 4;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tile0 = tile * DWB_TOK;
+    __syncthreads();   // previous iteration finished reading sx / sg
+    for (int i = threadIdx.x; i < (DWB_TOK + 12) * V; i += DWB_THREADS) {
+      const int r = i / V, q = i - r * V;
+      const int g = tile0 - 6 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(X + static_cast<size_t>(g) * C)[q];
+      reinterpret_cast<float4*>(sx + r * C)[q] = v;
+    }
+    __syncthreads();
+    // phase A: g rows tile0-3 .. tile0+TOK+2
+    for (int lr = warp; lr < DWB_TOK + 6; lr += DWB_THREADS / 32) {
+      const int tok = tile0 - 3 + lr;
+      float g[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) g[j] = 0.f;
+      if (tok >= 0 && tok < M) {
+        const int l = tok % L;
+        float y[PER], xr[7][PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) y[j] = bias[j];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+          const int ll = l + t - 3;
+          if (ll >= 0 && ll < L) {
+            RM::load(sx + (lr + t) * C, lane, xr[t]);   // sx row of token tok + t - 3 is (lr + 3) + (t - 3)
+#pragma unroll
+            for (int j = 0; j < PER; ++j) y[j] = fmaf(w[t][j], xr[t][j], y[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) xr[t][j] = 0.f;
+          }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) s += y[j];
+        const float mean = warp_sum(s) * (1.0f / C);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { y[j] -= mean; v += y[j] * y[j]; }
+        const float inv = rsqrtf(warp_sum(v) * (1.0f / C) + kLnEps);
+        float da[PER];
+        RM::load(dA + static_cast<size_t>(tok) * C, lane, da);
+        const bool inner = lr >= 3 && lr < DWB_TOK + 3;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          y[j] *= inv;
+          if (inner) { glw[j] += da[j] * y[j]; glb[j] += da[j]; }
+          da[j] *= lw[j];
+          s1 += da[j];
+          s2 += da[j] * y[j];
+        }
+        s1 = warp_sum(s1) * (1.0f / C);
+        s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) g[j] = inv * (da[j] - s1 - y[j] * s2);
+        if (inner) {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            gdb[j] += g[j];
+#pragma unroll
+            for (int t = 0; t < 7; ++t) gdw[t][j] = fmaf(g[j], xr[t][j], gdw[t][j]);
+          }
+        }
+      }
+      RM::store_f32(sg + lr * C, lane, g);
+    }
+    __syncthreads();
+    // phase B: dX[m] = dOut[m] + sum_t w[t] g[m - t + 3]  (conv positions inside the same window only)
+    for (int lr = warp; lr < DWB_TOK; lr += DWB_THREADS / 32) {
+      const int tok = tile0 + lr;
+      if (tok >= M) break;
+      const int l = tok % L;
+      float acc[PER];
+      RM::load(dOut + static_cast<size_t>(tok) * C, lane, acc);
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int ll = l - t + 3;
+        if (ll >= 0 && ll < L) {
+          float gr[PER];
+          RM::load(sg + (lr + 3 - t + 3) * C, lane, gr);
+#pragma unroll
+          for (int j = 0; j < PER; ++j) acc[j] = fmaf(w[t][j], gr[j], acc[j]);
+        }
+      }
+      RM::store_f32(dX + static_cast<size_t>(tok) * C, lane, acc);
+      if (dX16 != nullptr) RM::store_bf16(dX16 + static_cast<size_t>(tok) * C, lane, acc);
+    }
+  }
+  // parameter gradients: registers -> smem [warp][10][C] -> atomics
+  float* mine = sred + warp * 10 * C;
+#pragma unroll
+  for (int g = 0; g < RM::G; ++g)
+#pragma unroll
+    for (int j = 0; j < RM::VW; ++j) {
+      const int c = RM::chan(lane, g) + j, jj = g * RM::VW + j;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) mine[t * C + c] = gdw[t][jj];
+      mine[7 * C + c] = gdb[jj];
+      mine[8 * C + c] = glw[jj];
+      mine[9 * C + c] = glb[jj];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * C; i += DWB_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sred[wv * 10 * C + i];
+    atomicAdd(gparams + i, t);
+  }
+}
+
+// Finishes the layer-scale chain rule of a Block (model.py:166-167: out = x + gamma * (W2 h + b2)) after the tensor-core
+// wgrad produced, with the UNSCALED block-output gradient as dY,  G[c,k] = sum_t dOut[t,c] h[t,k]  (in the dW2 slot)
+// and g[c] = sum_t dOut[t,c] (in the db2 slot):   dgamma[c] = sum_k W2[c,k] G[c,k] + b2[c] g[c];  dW2 = gamma G;  db2 = gamma g.
+__global__ void __launch_bounds__(256) block_gamma_finish_kernel(const __nv_bfloat16* __restrict__ W2, const float* __restrict__ b2,
+                                                                 const float* __restrict__ gamma, float* G, float* gb2, float* ggamma,
+                                                                 int C, int H) {
+  const int c = blockIdx.x;
+  const float gm = gamma[c];
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < H; k += 256) {
+    const float gv = G[static_cast<size_t>(c) * H + k];
+    acc = fmaf(__bfloat162float(W2[static_cast<size_t>(c) * H + k]), gv, acc);
+    G[static_cast<size_t>(c) * H + k] = gm * gv;
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    const float g = gb2[c];
+    ggamma[c] += t + b2[c] * g;
+    gb2[c] = gm * g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ token-reduced outer products
+// acc[i] (+)= sum_tok A[r_i][tok] * B[c_i][tok] for the (r, c) pairs a thread owns: the per-CTA "mini wgrad" of the
+// small-channel stages.  sA [R][ST], sB [Cc][ST] fp32 in shared memory, ST = tokens + 1 (odd stride).
+template <int R, int Cc, int NT, int ST, int THREADS>
+struct OuterAcc {
+  static constexpr int ITEMS = R * Cc;
+  static constexpr int PER = (ITEMS + THREADS - 1) / THREADS;
+  __device__ static __forceinline__ void run(const float* sA, const float* sB, float* acc) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int it = threadIdx.x + i * THREADS;
+      if (it < ITEMS) {
+        const float* a = sA + (it / Cc) * ST;
+        const float* b = sB + (it % Cc) * ST;
+        float s = 0.f;
+#pragma unroll 8
+        for (int t = 0; t < NT; ++t) s = fmaf(a[t], b[t], s);
+        acc[i] += s;
+      }
+    }
+  }
+  __device__ static __forceinline__ void flush(float* gdst, const float* acc) {   // gdst [R][Cc]
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int it = threadIdx.x + i * THREADS;
+      if (it < ITEMS) atomicAdd(gdst + it, acc[i]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ small Block backward (C <= 32)
+// One thread per token recomputes the Block (block_small_kernel) and its backward; tile = SBB_IN inner tokens + 3 halo
+// tokens on each side whose g = d(dwconv output) is needed by the transposed depthwise conv.  Parameter gradients are
+// written in the SmallBlockLayout image.
+constexpr int SBB_THREADS = 128;
+constexpr int SBB_IN = SBB_THREADS - 6;
+constexpr int SBB_ST = SBB_THREADS + 1;
+
+template <int C>
+struct SmallBwdSmem {
+  using Lay = SmallBlockLayout<C>;
+  static constexpr int H = 2 * C;
+  static constexpr int RS = (C == 4) ? 4 : C + 4;
+  static constexpr int P = (Lay::TOTAL + 3) & ~3;
+  static constexpr int SX = (SBB_THREADS + 6) * RS;        // rows tile0-6 .. tile0+IN+5  (IN + 12 = THREADS + 6)
+  static constexpr int SG = SBB_THREADS * RS;              // g rows tile0-3 .. tile0+IN+2
+  static constexpr int SV = (2 * H + 2 * C) * SBB_ST;      // du[H] | gl[H] | a[C] | dg2[C], token-transposed
+  static constexpr size_t BYTES = static_cast<size_t>(P + SX + SG + SV) * 4;
+};
+
+template <int C>
+__global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int M,
+                                                                      const float* __restrict__ params, float* __restrict__ gparams) {
+  using Lay = SmallBlockLayout<C>;
+  using SM = SmallBwdSmem<C>;
+  constexpr int H = Lay::H, RS = SM::RS, V = C / 4, ST = SBB_ST;
+  extern __shared__ __align__(16) float smem_f[];
+  float* sp = smem_f;
+  float* sx = sp + SM::P;
+  float* sg = sx + SM::SX;
+  float* sdu = sg + SM::SG;          // [H][ST]
+  float* sgl = sdu + H * ST;         // [H][ST]
+  float* sa = sgl + H * ST;          // [C][ST]
+  float* sdg = sa + C * ST;          // [C][ST]
+  using OA = OuterAcc<H, C, SBB_THREADS, ST, SBB_THREADS>;
+  float accW1[OA::PER], accW2[OA::PER];
+#pragma unroll
+  for (int i = 0; i < OA::PER; ++i) { accW1[i] = 0.f; accW2[i] = 0.f; }
+  // per-channel parameter gradients: warp-shuffle sums per tile into a CTA accumulator  [dw 7C | dwb | lnw | lnb | b2 | gamma]
+  __shared__ float sacc[12 * C];
+  for (int i = threadIdx.x; i < 12 * C; i += SBB_THREADS) sacc[i] = 0.f;
+  const int lane = threadIdx.x & 31;
+  float gb1_acc[(H + SBB_THREADS - 1) / SBB_THREADS];
+#pragma unroll
+  for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) gb1_acc[i] = 0.f;
+
+  for (int i = threadIdx.x; i < Lay::TOTAL; i += SBB_THREADS) sp[i] = __ldg(params + i);
+  const int ntiles = (M + SBB_IN - 1) / SBB_IN;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tile0 = tile * SBB_IN;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (SBB_THREADS + 6) * V; i += SBB_THREADS) {
+      const int r = i / V, q = i - r * V;
+      const int g = tile0 - 6 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];
+      reinterpret_cast<float4*>(sx + r * RS)[q] = v;
+    }
+    __syncthreads();
+    const int tok = tile0 - 3 + threadIdx.x;                 // this thread's token (halo included)
+    const bool inner = threadIdx.x >= 3 && threadIdx.x < SBB_IN + 3 && tok < M;
+    const bool live = tok >= 0 && tok < M;
+    const int tokc = min(max(tok, 0), M - 1);   // dead threads compute on a clamped token with every contribution masked
+    float g[C];
+    {
+      const int l = tokc % L;
+      float y[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) y[c] = sp[Lay::DWB + c];
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int ll = l + t - 3;
+        if (ll >= 0 && ll < L) {
+          const float* row = sx + (threadIdx.x + t) * RS;    // sx row of token tok + t - 3
+#pragma unroll
+          for (int c = 0; c < C; ++c) y[c] = fmaf(sp[Lay::DW + t * C + c], row[c], y[c]);
+        }
+      }
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) mean += y[c];
+      mean *= (1.0f / C);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { y[c] -= mean; var += y[c] * y[c]; }
+      const float inv = rsqrtf(var * (1.0f / C) + kLnEps);
+      float a[C], dout[C], dg2[C], da[C], o[C];
+      const float4* dsrc = reinterpret_cast<const float4*>(dOut + static_cast<size_t>(tokc) * C);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 v = dsrc[q];
+        dout[4 * q] = v.x; dout[4 * q + 1] = v.y; dout[4 * q + 2] = v.z; dout[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        y[c] *= inv;                                          // xhat
+        a[c] = y[c] * sp[Lay::LNW + c] + sp[Lay::LNB + c];
+        dg2[c] = dout[c] * sp[Lay::GAMMA + c];
+        da[c] = 0.f;
+        o[c] = sp[Lay::B2 + c];
+        sa[c * ST + threadIdx.x] = inner ? a[c] : 0.f;
+        sdg[c * ST + threadIdx.x] = inner ? dg2[c] : 0.f;
+      }
+#pragma unroll 2
+      for (int h = 0; h < H; ++h) {
+        float u = sp[Lay::B1 + h], dh = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          u = fmaf(sp[Lay::W1 + h * C + c], a[c], u);
+          dh = fmaf(sp[Lay::W2T + h * C + c], dg2[c], dh);
+        }
+        float gl, dgl;
+        gelu_tanh_grad(u, &gl, &dgl);
+        const float du = dh * dgl;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          da[c] = fmaf(sp[Lay::W1 + h * C + c], du, da[c]);
+          o[c] = fmaf(sp[Lay::W2T + h * C + c], gl, o[c]);
+        }
+        sdu[h * ST + threadIdx.x] = inner ? du : 0.f;
+        sgl[h * ST + threadIdx.x] = inner ? gl : 0.f;
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float m = inner ? 1.f : 0.f;
+        const float v1 = warp_sum(m * da[c] * y[c]), v2 = warp_sum(m * da[c]), v3 = warp_sum(m * dg2[c]), v4 = warp_sum(m * dout[c] * o[c]);
+        if (lane == 0) {
+          atomicAdd(&sacc[8 * C + c], v1);
+          atomicAdd(&sacc[9 * C + c], v2);
+          atomicAdd(&sacc[10 * C + c], v3);
+          atomicAdd(&sacc[11 * C + c], v4);
+        }
+        da[c] *= sp[Lay::LNW + c];
+        s1 += da[c];
+        s2 += da[c] * y[c];
+      }
+      s1 *= (1.0f / C);
+      s2 *= (1.0f / C);
+#pragma unroll
+      for (int c = 0; c < C; ++c) g[c] = live ? inv * (da[c] - s1 - y[c] * s2) : 0.f;
+      {
+        const float m = inner ? 1.f : 0.f;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+          const int ll = l + t - 3;
+          const float mt = (ll >= 0 && ll < L) ? m : 0.f;
+          const float* row = sx + (threadIdx.x + t) * RS;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float v = warp_sum(mt * g[c] * row[c]);
+            if (lane == 0) atomicAdd(&sacc[t * C + c], v);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float v = warp_sum(m * g[c]);
+          if (lane == 0) atomicAdd(&sacc[7 * C + c], v);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) sg[threadIdx.x * RS + c] = g[c];
+    __syncthreads();
+    // dX for the inner tokens
+    if (inner) {
+      const int l = tok % L;
+      float acc[C];
+      const float4* dsrc = reinterpret_cast<const float4*>(dOut + static_cast<size_t>(tok) * C);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 v = dsrc[q];
+        acc[4 * q] = v.x; acc[4 * q + 1] = v.y; acc[4 * q + 2] = v.z; acc[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int ll = l - t + 3;
+        if (ll >= 0 && ll < L) {
+          const float* gr = sg + (threadIdx.x - t + 3) * RS;
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(sp[Lay::DW + t * C + c], gr[c], acc[c]);
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(dX + static_cast<size_t>(tok) * C);
+#pragma unroll
+      for (int q = 0; q < V; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+    // weight gradients of the two pointwise convs: token-reduced outer products
+    OA::run(sdu, sa, accW1);     // dW1[h][c]  += du[h] a[c]
+    OA::run(sgl, sdg, accW2);    // dW2t[h][c] += gelu(u)[h] dg2[c]
+#pragma unroll
+    for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) {
+      const int h = threadIdx.x + i * SBB_THREADS;
+      if (h < H) {
+        float s = 0.f;
+        for (int t = 0; t < SBB_THREADS; ++t) s += sdu[h * ST + t];
+        gb1_acc[i] += s;
+      }
+    }
+  }
+  OA::flush(gparams + Lay::W1, accW1);
+  OA::flush(gparams + Lay::W2T, accW2);
+#pragma unroll
+  for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) {
+    const int h = threadIdx.x + i * SBB_THREADS;
+    if (h < H) atomicAdd(gparams + Lay::B1 + h, gb1_acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 12 * C; i += SBB_THREADS) {
+    // sacc order: dw[7][C] | dwb | lnw | lnb | b2 | gamma  ->  SmallBlockLayout offsets
+    const int seg = i / C, c = i % C;
+    const int off = seg < 7 ? Lay::DW + i : seg == 7 ? Lay::DWB + c : seg == 8 ? Lay::LNW + c : seg == 9 ? Lay::LNB + c
+                  : seg == 10 ? Lay::B2 + c : Lay::GAMMA + c;
+    atomicAdd(gparams + off, sacc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ small Downsample backward
+// Forward (downsample_small_kernel): n = LN(x) of two adjacent tokens (2*CIN values), y = W n + b.
+// dY [M_out, COUT] -> dX [2*M_out, CIN]; parameter gradients in the SmallDownLayout image.
+constexpr int SDB_THREADS = 128;
+template <int CIN>
+constexpr size_t small_down_bwd_smem() {
+  return static_cast<size_t>(SmallDownLayout<CIN>::TOTAL + (2 * CIN + 2 * CIN) * (SDB_THREADS + 1)) * 4;
+}
+template <int CIN>
+__global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const float* X, const float* dY, float* dX, int M_out,
+                                                                           const float* __restrict__ params, float* __restrict__ gparams) {
+  using Lay = SmallDownLayout<CIN>;
+  constexpr int COUT = Lay::COUT, K = 2 * CIN, ST = SDB_THREADS + 1;
+  extern __shared__ __align__(16) float smem_f[];
+  float* sp = smem_f;
+  float* sdy = sp + Lay::TOTAL;     // [COUT][ST]
+  float* sn = sdy + COUT * ST;      // [K][ST]
+  using OA = OuterAcc<COUT, K, SDB_THREADS, ST, SDB_THREADS>;
+  float accW[OA::PER];
+#pragma unroll
+  for (int i = 0; i < OA::PER; ++i) accW[i] = 0.f;
+  float glw[CIN], glb[CIN], gbo = 0.f;
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) { glw[c] = 0.f; glb[c] = 0.f; }
+  for (int i = threadIdx.x; i < Lay::TOTAL; i += SDB_THREADS) sp[i] = __ldg(params + i);
+  const int ntiles = (M_out + SDB_THREADS - 1) / SDB_THREADS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    const int tok = tile * SDB_THREADS + threadIdx.x;
+    if (tok < M_out) {
+      float n[K], dy[COUT], dn[K], inv[2];
+      const float4* src = reinterpret_cast<const float4*>(X + static_cast<size_t>(tok) * K);
+#pragma unroll
+      for (int q = 0; q < K / 4; ++q) {
+        const float4 v = src[q];
+        n[4 * q] = v.x; n[4 * q + 1] = v.y; n[4 * q + 2] = v.z; n[4 * q + 3] = v.w;
+      }
+      const float4* dsrc = reinterpret_cast<const float4*>(dY + static_cast<size_t>(tok) * COUT);
+#pragma unroll
+      for (int q = 0; q < COUT / 4; ++q) {
+        const float4 v = dsrc[q];
+        dy[4 * q] = v.x; dy[4 * q + 1] = v.y; dy[4 * q + 2] = v.z; dy[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) mean += n[t * CIN + c];
+        mean *= (1.0f / CIN);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) { n[t * CIN + c] -= mean; var += n[t * CIN + c] * n[t * CIN + c]; }
+        inv[t] = rsqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) n[t * CIN + c] *= inv[t];   // xhat
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        dn[k] = 0.f;
+        sn[k * ST + threadIdx.x] = n[k] * sp[Lay::LNW + (k % CIN)] + sp[Lay::LNB + (k % CIN)];
+      }
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        sdy[o * ST + threadIdx.x] = dy[o];
+#pragma unroll
+        for (int k = 0; k < K; ++k) dn[k] = fmaf(sp[Lay::W + o * K + k], dy[o], dn[k]);
+      }
+      float* dst = dX + static_cast<size_t>(tok) * K;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float d = dn[t * CIN + c];
+          glw[c] += d * n[t * CIN + c];
+          glb[c] += d;
+          dn[t * CIN + c] = d * sp[Lay::LNW + c];
+          s1 += dn[t * CIN + c];
+          s2 += dn[t * CIN + c] * n[t * CIN + c];
+        }
+        s1 *= (1.0f / CIN);
+        s2 *= (1.0f / CIN);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) dn[t * CIN + c] = inv[t] * (dn[t * CIN + c] - s1 - n[t * CIN + c] * s2);
+      }
+#pragma unroll
+      for (int q = 0; q < K / 4; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(dn[4 * q], dn[4 * q + 1], dn[4 * q + 2], dn[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sn[k * ST + threadIdx.x] = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) sdy[o * ST + threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    OA::run(sdy, sn, accW);
+    if (threadIdx.x < COUT) {
+      float s = 0.f;
+      for (int t = 0; t < SDB_THREADS; ++t) s += sdy[threadIdx.x * ST + t];
+      gbo += s;
+    }
+  }
+  OA::flush(gparams + Lay::W, accW);
+  if (threadIdx.x < COUT) atomicAdd(gparams + Lay::B + threadIdx.x, gbo);
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) {
+    const float v1 = warp_sum(glw[c]), v2 = warp_sum(glb[c]);
+    if (lane == 0) {
+      atomicAdd(gparams + Lay::LNW + c, v1);
+      atomicAdd(gparams + Lay::LNB + c, v2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Stem (training variant + backward)
+// Packed fp32 image: w[4][2][5] (40) | b[4] | lnw[4] | lnb[4]
+constexpr int STEM_P = 52;
+__global__ void __launch_bounds__(256) stem_train_kernel(const float* __restrict__ audio, float* __restrict__ out, int n_samples,
+                                                         int L0, int total_tokens, const float* __restrict__ params) {
+  __shared__ float sp[STEM_P];
+  if (threadIdx.x < STEM_P) sp[threadIdx.x] = params[threadIdx.x];
+  __syncthreads();
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= total_tokens) return;
+  const int b = tok / L0, l = tok - b * L0;
+  const float* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
+  const float* a1 = a0 + n_samples;
+  float x[10];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { x[k] = __ldg(a0 + k); x[5 + k] = __ldg(a1 + k); }
+  float y[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float acc = sp[40 + o];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc = fmaf(sp[o * 10 + k], x[k], acc);
+    y[o] = acc;
+  }
+  const float mean = 0.25f * (y[0] + y[1] + y[2] + y[3]);
+  float var = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) var += (y[o] - mean) * (y[o] - mean);
+  const float inv = rsqrtf(0.25f * var + kLnEps);
+  float4 r;
+  r.x = (y[0] - mean) * inv * sp[44] + sp[48];
+  r.y = (y[1] - mean) * inv * sp[45] + sp[49];
+  r.z = (y[2] - mean) * inv * sp[46] + sp[50];
+  r.w = (y[3] - mean) * inv * sp[47] + sp[51];
+  reinterpret_cast<float4*>(out)[tok] = r;
+}
+
+__global__ void __launch_bounds__(256) stem_bwd_kernel(const float* __restrict__ audio, const float* __restrict__ dOut, int n_samples,
+                                                       int L0, int total_tokens, const float* __restrict__ params,
+                                                       float* __restrict__ gparams) {
+  __shared__ float sp[STEM_P];
+  __shared__ float sred[8][STEM_P];
+  if (threadIdx.x < STEM_P) sp[threadIdx.x] = params[threadIdx.x];
+  __syncthreads();
+  float acc[STEM_P];
+#pragma unroll
+  for (int i = 0; i < STEM_P; ++i) acc[i] = 0.f;
+  for (int tok = blockIdx.x * 256 + threadIdx.x; tok < total_tokens; tok += gridDim.x * 256) {
+    const int b = tok / L0, l = tok - b * L0;
+    const float* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
+    const float* a1 = a0 + n_samples;
+    float x[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { x[k] = __ldg(a0 + k); x[5 + k] = __ldg(a1 + k); }
+    float y[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float a = sp[40 + o];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) a = fmaf(sp[o * 10 + k], x[k], a);
+      y[o] = a;
+    }
+    const float mean = 0.25f * (y[0] + y[1] + y[2] + y[3]);
+    float var = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { y[o] -= mean; var += y[o] * y[o]; }
+    const float inv = rsqrtf(0.25f * var + kLnEps);
+    const float4 d4 = reinterpret_cast<const float4*>(dOut)[tok];
+    float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      y[o] *= inv;
+      acc[44 + o] += d[o] * y[o];
+      acc[48 + o] += d[o];
+      d[o] *= sp[44 + o];
+      s1 += d[o];
+      s2 += d[o] * y[o];
+    }
+    s1 *= 0.25f;
+    s2 *= 0.25f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float g = inv * (d[o] - s1 - y[o] * s2);
+      acc[40 + o] += g;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc[o * 10 + k] = fmaf(g, x[k], acc[o * 10 + k]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < STEM_P; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) sred[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < STEM_P) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[w][threadIdx.x];
+    atomicAdd(gparams + threadIdx.x, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ packing / unpacking / optimiser
+// Packed weight images from the fp32 master parameters (reference leaf layout): element i of the flat packed list
+// is master[src[i]] (* master[mul[i]] when mul[i] >= 0), or 0 when src[i] < 0, stored as fp32 or bf16 at byte offset
+// dst_off[i] & 0x7fffffff of the arena (top bit = bf16).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ master, const int* __restrict__ src,
+                                                           const int* __restrict__ mul, const uint32_t* __restrict__ dst_off,
+                                                           uint8_t* __restrict__ arena, size_t n) {
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const int s = src[i];
+    float v = 0.f;
+    if (s >= 0) {
+      v = master[s];
+      const int m = mul[i];
+      if (m >= 0) v *= master[m];
+    }
+    const uint32_t d = dst_off[i];
+    if (d & 0x80000000u) *reinterpret_cast<__nv_bfloat16*>(arena + (d & 0x7fffffffu)) = __float2bfloat16_rn(v);
+    else *reinterpret_cast<float*>(arena + d) = v;
+  }
+}
+// grads[src[i]] += gpack[i]: every master element receives contributions only from the packed copies the backward
+// kernels wrote (the others stay zero), so plain atomics over a handful of aliases are enough.
+__global__ void __launch_bounds__(256) grad_unpack_kernel(const float* __restrict__ gpack, const int* __restrict__ src,
+                                                          float* __restrict__ grads, size_t n) {
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const float g = gpack[i];
+    const int s = src[i];
+    if (s >= 0 && g != 0.f) atomicAdd(grads + s, g);
+  }
+}
+
+// AdamW (optax.adamw as configured in train.py:646-726) followed by optax.clip_by_global_norm on the UPDATES
+// (train.py:726 chains the clip after the optimiser).  Pass 1: moments, raw update u, sum u^2 and a finite flag.
+// Pass 2: p += u * min(1, clip / ||u||).
+struct AdamArgs {
+  float lr, b1, b2, eps, wd, bc1, bc2, inv_div;   // bc = 1 - beta^t ; grads are multiplied by inv_div first
+};
+__global__ void __launch_bounds__(256) adamw_pass1_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, float* __restrict__ u, const float* __restrict__ lr_mult,
+                                                          size_t n, AdamArgs a, float* __restrict__ stats /* [0] sum u^2, [1] non-finite count */) {
+  float ss = 0.f, bad = 0.f;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const float gi = g[i] * a.inv_div;
+    if (!isfinite(gi)) bad += 1.f;
+    const float mi = a.b1 * m[i] + (1.f - a.b1) * gi;
+    const float vi = a.b2 * v[i] + (1.f - a.b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float mh = mi / a.bc1, vh = vi / a.bc2;
+    const float lr = a.lr * (lr_mult ? lr_mult[i] : 1.f);
+    const float ui = -lr * (mh / (sqrtf(vh) + a.eps) + a.wd * p[i]);
+    u[i] = ui;
+    ss += ui * ui;
+  }
+  ss = warp_sum(ss);
+  bad = warp_sum(bad);
+  __shared__ float s0[8], s1[8];
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = ss; s1[threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 8; ++i) { t0 += s0[i]; t1 += s1[i]; }
+    atomicAdd(stats, t0);
+    if (t1 != 0.f) atomicAdd(stats + 1, t1);
+  }
+}
+__global__ void __launch_bounds__(256) adamw_pass2_kernel(float* __restrict__ p, const float* __restrict__ u, size_t n, float clip,
+                                                          const float* __restrict__ stats) {
+  const float norm = sqrtf(stats[0]);
+  const float f = (norm > clip) ? clip / norm : 1.f;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) p[i] += u[i] * f;
+}
+
+}  // namespace a2m

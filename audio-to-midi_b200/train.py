@@ -1,0 +1,207 @@
+"""Host side of the training step: mirror of the reference's train.py hot path over the C ABI.
+
+Reference                                         here
+------------------------------------------------  --------------------------------------------------------------
+compute_loss (train.py:48-62)                      compute_loss(...) -> ((loss, state), grads)   [value_and_grad]
+compute_training_step (train.py:259-332)           TrainEngine.training_step(...)
+setup_optimizers (train.py:646-728)                OptimizerConfig + layer_lr_multipliers(...)
+create_learning_rate_schedule (train.py:454-466)   create_learning_rate_schedule(...)
+batch sharding over devices (train.py:238-244)     one process per GPU; TrainEngine.allreduce_grads() = NCCL all-reduce
+
+Device arrays are torch CUDA tensors (torch is the allocator / stream / NCCL provider only); every kernel is in
+libaudio2midi_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .model import OutputSequenceGenerator, _Engine, _default_device, model_config
+from .rope import RopeFreqs
+
+
+@dataclass
+class OptimizerConfig:  # train.py:691-726, 743-749
+    base_learning_rate: float = 1e-4
+    layer_lr_decay: float = 0.7
+    weight_decay: float = 0.005
+    warmup_steps: int = 1000
+    num_steps: int = 200_000
+    eps: float = 1e-3
+    b1: float = 0.9
+    b2: float = 0.999
+    clip_norm: float = 1.0
+
+
+def create_learning_rate_schedule(base_learning_rate: float, warmup_steps: int, cosine_decay_steps: int) -> Callable[[int], float]:
+    """optax.join_schedules([linear 0 -> base over warmup, cosine_decay(base, steps)], [warmup])  (train.py:454-466)."""
+    def schedule(step: int) -> float:
+        if step < warmup_steps:
+            return base_learning_rate * step / max(warmup_steps, 1)
+        t = min(step - warmup_steps, cosine_decay_steps) / max(cosine_decay_steps, 1)
+        return base_learning_rate * 0.5 * (1.0 + math.cos(math.pi * t))
+    return schedule
+
+
+def layer_lr_multipliers(paths, layer_lr_decay: float, depths=None) -> np.ndarray:
+    """Per-leaf learning-rate multiplier of setup_optimizers (train.py:648-704): leaves under `layers.<stage>.layers.<k>`
+    get decay ** (max_depth - depth), depth = sum(depths[:stage]) + k; everything else 1."""
+    depths = model_config["depths"] if depths is None else depths
+    d = []
+    for p in paths:
+        parts = p.split(".")
+        if parts[0] == "layers":
+            d.append(sum(depths[: int(parts[1])]) + int(parts[3]))
+        else:
+            d.append(None)
+    mx = max(x for x in d if x is not None)
+    return np.array([1.0 if x is None else layer_lr_decay ** (mx - x) for x in d], np.float32)
+
+
+class TrainEngine:
+    """Master parameters, AdamW state and activation tape on one GPU (a2m_train_init ...)."""
+
+    def __init__(self, model: OutputSequenceGenerator, device: Optional[int] = None):
+        import torch
+        self.torch = torch
+        self.device = _default_device() if device is None else device
+        self.eng = _Engine.get(self.device)
+        self.L, self.h = self.eng.L, self.eng.h
+        leaves = model.tree_leaves_with_path()
+        self.paths = [p for p, _ in leaves]
+        self.shapes = [tuple(np.shape(a)) for _, a in leaves]
+        n = len(leaves)
+        table = (_lib.LeafDesc * n)()
+        chunks, off, self.offsets = [], 0, []
+        for i, (path, arr) in enumerate(leaves):
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            table[i].path = path.encode()
+            table[i].offset_bytes = off
+            table[i].ndim = a.ndim
+            for d in range(a.ndim):
+                table[i].shape[d] = a.shape[d]
+            chunks.append(a.reshape(-1))
+            self.offsets.append(off // 4)
+            off += a.size * 4
+        blob = np.concatenate(chunks)
+        _lib.check(self.h, self.L.a2m_train_init(self.h, blob.ctypes.data, blob.nbytes, table, n), "a2m_train_init")
+        self.eng.weights_token = None   # the engine's inference weights now belong to the trainer
+        self.eng.owner = self
+        self.n_params = int(self.L.a2m_param_count(self.h))
+        self.tdev = torch.device(f"cuda:{self.device}")
+        self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=self.tdev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.tdev)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=self.tdev)
+        self._rope = None
+        self.step_count = 0
+
+    # ---- helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _rope_tensors(self, rope_freqs: RopeFreqs):
+        if self._rope is None or self._rope[2] is not rope_freqs:
+            t = self.torch
+            cos = t.as_tensor(np.ascontiguousarray(rope_freqs.cos_freq, np.float32)).to(self.tdev)
+            sin = t.as_tensor(np.ascontiguousarray(rope_freqs.sin_freq, np.float32)).to(self.tdev)
+            self._rope = (cos, sin, rope_freqs)
+        return self._rope[0], self._rope[1]
+
+    def set_lr_multipliers(self, per_leaf: Optional[np.ndarray]):
+        if per_leaf is None:
+            _lib.check(self.h, self.L.a2m_set_lr_multipliers(self.h, None, 0), "a2m_set_lr_multipliers")
+            return
+        a = np.ascontiguousarray(per_leaf, np.float32)
+        _lib.check(self.h, self.L.a2m_set_lr_multipliers(self.h, a.ctypes.data, a.size), "a2m_set_lr_multipliers")
+
+    # ---- compute_loss (train.py:48-62): forward with tape + backward, accumulating into self.grads / self.loss
+    def zero_grad(self):
+        self.grads.zero_()
+        self.loss.zero_()
+
+    def forward_backward(self, audio, labels, rope_freqs: RopeFreqs, scale: float = 1.0, want_logits: bool = False):
+        t = self.torch
+        if not (audio.is_cuda and labels.is_cuda):
+            raise _lib.A2mError("training inputs must be CUDA tensors (no CPU path)")
+        audio = audio.to(t.float32).contiguous()
+        labels = labels.to(t.float32).contiguous()
+        B = audio.shape[0]
+        if tuple(audio.shape[1:]) != (2, 80000) or tuple(labels.shape) != (B, 250, 90):
+            raise ValueError(f"audio (B, 2, 80000) / labels (B, 250, 90) expected, got {tuple(audio.shape)} / {tuple(labels.shape)}")
+        cos, sin = self._rope_tensors(rope_freqs)
+        logits = t.empty((B, 250, 90), dtype=t.float32, device=self.tdev) if want_logits else None
+        rc = self.L.a2m_forward_train(self.h, audio.data_ptr(), B, cos.data_ptr(), sin.data_ptr(), cos.shape[0],
+                                      logits.data_ptr() if want_logits else None, None, self._stream())
+        _lib.check(self.h, rc, "a2m_forward_train")
+        rc = self.L.a2m_backward(self.h, labels.data_ptr(), float(scale), self.grads.data_ptr(), self.loss.data_ptr(), self._stream())
+        _lib.check(self.h, rc, "a2m_backward")
+        self._keep = (audio, labels)   # the stem backward reads the audio asynchronously
+        return logits
+
+    def allreduce_grads(self):
+        """Data-parallel gradient exchange (train.py:238-244 shards the batch over devices): NCCL all-reduce (sum)
+        over NVLink, then the mean over ranks.  No-op without an initialised process group."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grads)
+            dist.all_reduce(self.loss)
+            self.grads.mul_(1.0 / dist.get_world_size())
+            self.loss.mul_(1.0 / dist.get_world_size())
+
+    def optimizer_step(self, lr: float, cfg: OptimizerConfig, grad_divisor: float = 1.0):
+        self.step_count += 1
+        rc = self.L.a2m_adamw_step(self.h, self.grads.data_ptr(), float(lr), cfg.b1, cfg.b2, cfg.eps, cfg.weight_decay,
+                                   float(grad_divisor), cfg.clip_norm, self.step_count, self.stats.data_ptr(), self._stream())
+        _lib.check(self.h, rc, "a2m_adamw_step")
+
+    # ---- compute_training_step (train.py:259-332)
+    def training_step(self, audio, labels, rope_freqs: RopeFreqs, cfg: OptimizerConfig, lr: float, grad_scale: float = 1.0,
+                      minibatch_size: Optional[int] = None):
+        """Minibatch scan with fp32 gradient accumulation, unscale by grad_scale x steps, all-reduce, AdamW + clip.
+        Returns (loss, grads_valid, scaled_loss) as device tensors / lazily evaluated values (no host sync here)."""
+        B = audio.shape[0]
+        mb = B if minibatch_size is None else minibatch_size
+        if B % mb != 0:
+            raise ValueError("batch must be a multiple of the minibatch size")
+        steps = B // mb
+        self.zero_grad()
+        for i in range(steps):
+            self.forward_backward(audio[i * mb:(i + 1) * mb], labels[i * mb:(i + 1) * mb], rope_freqs, scale=grad_scale)
+        self.allreduce_grads()
+        self.optimizer_step(lr, cfg, grad_divisor=grad_scale * steps)
+        scaled_loss = self.loss / steps
+        return scaled_loss / grad_scale, self.stats[1] == 0, scaled_loss
+
+    # ---- parameter access
+    def params_flat(self):
+        out = self.torch.empty(self.n_params, dtype=self.torch.float32, device=self.tdev)
+        _lib.check(self.h, self.L.a2m_get_params(self.h, out.data_ptr(), self._stream()), "a2m_get_params")
+        return out
+
+    def _tree(self, flat) -> Dict[str, np.ndarray]:
+        a = flat.detach().cpu().numpy()
+        return {p: a[o:o + int(np.prod(s, dtype=np.int64))].reshape(s) for p, o, s in zip(self.paths, self.offsets, self.shapes)}
+
+    def params_tree(self) -> Dict[str, np.ndarray]:
+        return self._tree(self.params_flat())
+
+    def grads_tree(self) -> Dict[str, np.ndarray]:
+        return self._tree(self.grads)
+
+    def launch_count(self) -> int:
+        return int(self.L.a2m_train_launch_count(self.h))
+
+
+def compute_loss(model: OutputSequenceGenerator, state, audio, rope_freqs: RopeFreqs, expected_outputs, scale, key=None,
+                 engine: Optional[TrainEngine] = None):
+    """Reference call shape of compute_loss (train.py:48-62, under eqx.filter_value_and_grad(has_aux=True)):
+    returns ((loss, state), grads) with grads keyed by pytree path.  Dropout is not applied."""
+    eng = engine or TrainEngine(model)
+    eng.zero_grad()
+    eng.forward_backward(audio, expected_outputs, rope_freqs, scale=float(scale))
+    return (eng.loss.clone(), state), eng.grads_tree()

@@ -123,6 +123,34 @@ int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t 
                    int32_t lda, const void* W_bf16_dev, uint32_t flags, const float* bias_dev,
                    const float* gamma_dev, const float* resid_dev, float* out32_dev, void* out16_dev, void* stream);
 
+/* ---- training path (train.py:39-62 loss + value_and_grad; train.py:259-332 step) -------------------------- */
+/* Master parameters (fp32, in the layout of `blob_host` / the leaf table, = the reference pytree leaves), AdamW moments
+ * and the activation tape live in the handle.  Replaces the model / opt_state hand-off of train.py:246-264.  Also
+ * loads the weights for a2m_forward. */
+int a2m_train_init(A2mHandle* h, const void* blob_host, size_t blob_bytes, const A2mLeafDesc* table, int32_t n_leaves);
+int64_t a2m_param_count(const A2mHandle* h);                          /* floats in the blob */
+int a2m_get_params(A2mHandle* h, float* out_dev, void* stream);       /* current master parameters, blob layout */
+/* One learning-rate multiplier per leaf (layer-wise decay of train.py:646-726); NULL resets to 1. */
+int a2m_set_lr_multipliers(A2mHandle* h, const float* per_leaf_host, int32_t n_leaves);
+/* Forward that records the tape; logits_dev / probs_dev [batch, 250, 90] may be NULL.  Dropout is not applied
+ * (rate 0): see DESIGN.md.  audio_dev must stay valid until a2m_backward has run. */
+int a2m_forward_train(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
+                      const float* rope_sin_dev, int32_t rope_max_pos, float* logits_dev, float* probs_dev, void* stream);
+/* grads_dev [param_count] += d/dparams of  mean_b( sum_{t,c} BCEWithLogits(z, y) * scale )  (compute_loss, train.py:50-62);
+ * loss_dev[0] += that value.  labels_dev [batch, 250, 90] fp32.  Gradient accumulation over minibatches
+ * (train.py:283-293) = repeated forward_train / backward calls on the same grads_dev. */
+int a2m_backward(A2mHandle* h, const float* labels_dev, float scale, float* grads_dev, float* loss_dev, void* stream);
+/* optax.adamw then clip_by_global_norm(clip_norm) on the updates, applied to the master parameters; gradients are
+ * divided by grad_divisor first (train.py:314).  step counts from 1.  stats_dev (optional, 2 floats): squared norm of
+ * the unclipped update, number of non-finite gradient entries (train.py:320-322 grads_valid == 0).  The data-parallel
+ * gradient all-reduce happens between a2m_backward and this call, on grads_dev, by the caller (NCCL). */
+int a2m_adamw_step(A2mHandle* h, const float* grads_dev, float lr, float b1, float b2, float eps, float weight_decay,
+                   float grad_divisor, float clip_norm, int32_t step, float* stats_dev, void* stream);
+int32_t a2m_train_launch_count(const A2mHandle* h);   /* kernels of the last forward_train + backward */
+/* test hook: dW[n_out, k_out] += dY[tokens, n_out]^T X[tokens, k_out] (bf16 operands) on the tcgen05 wgrad kernel */
+int a2m_debug_wgrad(A2mHandle* h, int32_t tokens, int32_t n_out, int32_t k_out, const void* dY_bf16_dev, int32_t ldy,
+                    const void* X_bf16_dev, int32_t ldx, float* dW_dev, void* stream);
+
 /* ---- modelutil: post-processing of the probabilities (host code, like the reference's Rust) ------- */
 /* stitch_probs (common.rs:13-45).  probs [windows, frames, cats] fp32 -> out [out_frames, cats];
  * returns out_frames (= windows*frames - trunc(overlap/dpf)*(windows-1)); out may be NULL to query. */

@@ -1,0 +1,94 @@
+"""-m gpu: the training path through the C ABI vs torch-CPU autograd of the oracle (train.py:39-62, 259-332)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import audio_to_midi_b200 as A
+from audio_to_midi_b200 import _lib
+from audio_to_midi_b200 import train as T
+from gpu_util import engine, make_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tokens,n_out,k_out,pad", [(4096, 128, 256, 0), (1000, 320, 256, 0), (2048, 512, 64, 256), (777, 64, 128, 0),
+                                                     (16384, 1024, 256, 0), (3000, 256, 512, 0), (64, 128, 64, 0)])
+def test_wgrad_gemm(tokens, n_out, k_out, pad):
+    """dW += dY^T X on tcgen05 with both operands MN-major (gemm_wgrad.cuh) vs fp64."""
+    m, _ = make_model(1)
+    eng = engine(m)
+    g = torch.Generator(device="cpu").manual_seed(tokens + n_out)
+    dY = (torch.randn(tokens, n_out, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    Xfull = torch.randn(tokens, k_out + pad, generator=g).to(torch.bfloat16).cuda()
+    X = Xfull[:, pad:]                       # column offset + leading dimension > k_out (the kv_down case)
+    dW = torch.ones(n_out, k_out, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = eng.L.a2m_debug_wgrad(eng.h, tokens, n_out, k_out, dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), dW.data_ptr(),
+                               C.c_void_p(stream))
+    _lib.check(eng.h, rc, "a2m_debug_wgrad")
+    torch.cuda.synchronize()
+    ref = 1.0 + dY.double().T @ X.double()
+    err = (dW.double() - ref).abs().max().item()
+    assert err < 2e-3 * np.sqrt(tokens), err
+
+
+def test_backward_matches_autograd():
+    """Every leaf gradient and the loss of one forward/backward of 2 windows vs torch autograd on the same weights.
+    Operands are bf16 (the reference trains in fp16, train.py:36-38), accumulation fp32: 6 % relative L2 per leaf."""
+    import train_util as U
+    tree, audio, labels = U.setup(2)
+    lref, gref, zref = U.oracle_grads(tree, audio, labels, scale=2.0)
+    lcu, gcu, zcu, eng = U.cuda_grads(tree, audio, labels, scale=2.0)
+    assert abs(lcu - lref) < 2e-3 * abs(lref), (lcu, lref)
+    assert np.abs(zcu - zref).max() < 0.15
+    rows = U.compare(gref, gcu)
+    bad = [(k, round(r, 4)) for k, r, _, _ in rows if not (r < 0.06)]
+    assert not bad, bad[:10]
+    assert eng.launch_count() > 500
+
+
+def test_gradient_accumulation_and_adamw():
+    """Two minibatches of 1 accumulate to the gradient of the batch of 2 (train.py:283-293); AdamW + global-norm clip of
+    the updates (optax.adamw then clip_by_global_norm, train.py:698-726) vs a numpy restatement on the CUDA gradients."""
+    import train_util as U
+    tree, audio, labels = U.setup(2)
+    model, _ = make_model(7, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    eng = T.TrainEngine(model, 0)
+    rope = A.precompute_frequencies(64, 300)
+    a, y = torch.tensor(audio).cuda(), torch.tensor(labels).cuda()
+    eng.zero_grad()
+    eng.forward_backward(a, y, rope)
+    g_full = eng.grads.clone()
+    eng.zero_grad()
+    eng.forward_backward(a[:1], y[:1], rope)
+    eng.forward_backward(a[1:], y[1:], rope)
+    g_acc = eng.grads.clone() / 2
+    rel = ((g_acc - g_full).norm() / g_full.norm()).item()
+    assert rel < 2e-2, rel
+
+    cfg = T.OptimizerConfig()
+    p0 = eng.params_flat().double().cpu().numpy()
+    mult = T.layer_lr_multipliers(eng.paths, cfg.layer_lr_decay)
+    eng.set_lr_multipliers(mult)
+    g = (eng.grads.double().cpu().numpy()) / 2.0
+    eng.optimizer_step(1e-2, cfg, grad_divisor=2.0)
+    torch.cuda.synchronize()
+    p1 = eng.params_flat().double().cpu().numpy()
+    lrm = np.ones_like(p0)
+    for (o, s, m_) in zip(eng.offsets, eng.shapes, mult):
+        lrm[o:o + int(np.prod(s, dtype=np.int64))] = m_
+    m1 = (1 - cfg.b1) * g
+    v1 = (1 - cfg.b2) * g * g
+    u = -(1e-2 * lrm) * ((m1 / (1 - cfg.b1)) / (np.sqrt(v1 / (1 - cfg.b2)) + cfg.eps) + cfg.weight_decay * p0)
+    norm = np.linalg.norm(u)
+    u *= min(1.0, cfg.clip_norm / norm)
+    assert abs(float(eng.stats[0].item()) - norm ** 2) < 1e-3 * norm ** 2
+    assert float(eng.stats[1].item()) == 0.0
+    assert np.abs((p1 - p0) - u).max() < 1e-6 + 1e-4 * np.abs(u).max()
+    # the re-packed kernel weights follow the master parameters: a forward now differs from before the step
+    eng.zero_grad()
+    z2 = eng.forward_backward(a, y, rope, want_logits=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(z2).all()
