@@ -38,7 +38,7 @@ EXPORTS = [
     "a2m_forward_host", "a2m_submit_host", "a2m_collect_host", "a2m_host_alloc", "a2m_host_free",
     "a2m_last_launch_count", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
     "a2m_train_init", "a2m_param_count", "a2m_get_params", "a2m_set_lr_multipliers", "a2m_forward_train", "a2m_backward",
-    "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad",
+    "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
 ]
 
@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     L.a2m_adamw_step.restype = C.c_int
     L.a2m_train_launch_count.argtypes = [vp]
     L.a2m_train_launch_count.restype = i32
+    L.a2m_profile_train_steps.argtypes = [vp, i32, i32, i32, C.POINTER(StepProfile)]
+    L.a2m_profile_train_steps.restype = i32
     L.a2m_debug_wgrad.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, vp]
     L.a2m_debug_wgrad.restype = C.c_int
     L.a2m_stitch_probs.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, f64, f64, vp]

@@ -63,6 +63,28 @@ def layer_lr_multipliers(paths, layer_lr_decay: float, depths=None) -> np.ndarra
     return np.array([1.0 if x is None else layer_lr_decay ** (mx - x) for x in d], np.float32)
 
 
+def shard_batch(global_batch: int, world_size: int, rank: int):
+    """Rows of the global batch owned by `rank`: the batch axis is split evenly over devices (train.py:238-244,
+    PartitionSpec("batch")); the global batch must be divisible by the device count, as in the reference."""
+    if global_batch % world_size != 0:
+        raise ValueError("the batch must be divisible by the number of devices (train.py:744)")
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_mean_(tensors):
+    """In-place mean over ranks of every tensor (sum all-reduce, then 1/world): what jit does for a batch-sharded mean loss
+    (train.py:61-62 under the sharding of train.py:238-244).  NCCL on CUDA tensors, gloo on CPU tensors; no-op for one rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tensors
+    w = dist.get_world_size()
+    for t in tensors:
+        dist.all_reduce(t)
+        t.mul_(1.0 / w)
+    return tensors
+
+
 class TrainEngine:
     """Master parameters, AdamW state and activation tape on one GPU (a2m_train_init ...)."""
 
@@ -146,12 +168,7 @@ class TrainEngine:
     def allreduce_grads(self):
         """Data-parallel gradient exchange (train.py:238-244 shards the batch over devices): NCCL all-reduce (sum)
         over NVLink, then the mean over ranks.  No-op without an initialised process group."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads)
-            dist.all_reduce(self.loss)
-            self.grads.mul_(1.0 / dist.get_world_size())
-            self.loss.mul_(1.0 / dist.get_world_size())
+        allreduce_mean_([self.grads, self.loss])
 
     def optimizer_step(self, lr: float, cfg: OptimizerConfig, grad_divisor: float = 1.0):
         self.step_count += 1
@@ -192,6 +209,17 @@ class TrainEngine:
 
     def grads_tree(self) -> Dict[str, np.ndarray]:
         return self._tree(self.grads)
+
+    def profile_steps(self, which: int, repeats: int = 3):
+        """Per-launch CUDA-event timings of the forward-with-tape (0) or backward (1) plan: (kernel, ms, flops, bytes)."""
+        n = self.L.a2m_profile_train_steps(self.h, which, repeats, 0, None)
+        if n < 0:
+            _lib.check(self.h, n, "a2m_profile_train_steps")
+        buf = (_lib.StepProfile * n)()
+        m = self.L.a2m_profile_train_steps(self.h, which, repeats, n, buf)
+        if m < 0:
+            _lib.check(self.h, m, "a2m_profile_train_steps")
+        return [(buf[i].kernel.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)) for i in range(m)]
 
     def launch_count(self) -> int:
         return int(self.L.a2m_train_launch_count(self.h))

@@ -140,6 +140,103 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_WINDOW   # fwd + dgrad + wgrad, no recompute counted
+
+
+def measure_train(args, A, synth, dev, rank, world, dist, local):
+    """Train step of config 4 (train.py:259-332): forward with tape, backward, NCCL gradient all-reduce, AdamW + clip.
+    B windows per GPU per step (weak scaling, global batch = B x world).  Returns the "train" object of the JSON line."""
+    import torch
+    from audio_to_midi_b200 import train as T
+    B = args.train_batch
+    model = A.OutputSequenceGenerator(A.model_config, key=SEED)
+    eng = T.TrainEngine(model, local)
+    cfg = T.OptimizerConfig()
+    eng.set_lr_multipliers(T.layer_lr_multipliers(eng.paths, cfg.layer_lr_decay))
+    sched = T.create_learning_rate_schedule(cfg.base_learning_rate, cfg.warmup_steps, cfg.num_steps)
+    rope = A.precompute_frequencies(A.model_config["attention_size"], 300)
+    R = 3
+    host = [synth.make_windows_fast(B, SEED + 31 * (rank * R + r)) for r in range(R)]
+    rng = np.random.Generator(np.random.PCG64(SEED + rank))
+    host_y = [np.clip((rng.random((B, 250, 90)) < 0.02).astype(np.float32), 0.005, 0.995) for _ in range(R)]
+    dev_x = [torch.tensor(h, device=dev) for h in host]
+    dev_y = [torch.tensor(h, device=dev) for h in host_y]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(args.warmup, 3), args.train_steps
+    for i in range(W):
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(i + 1))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(W + i + 1))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss_last = float(eng.loss.item())
+    # phase breakdown (one rank's events; separate untimed pass)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    acc = np.zeros(4)
+    cos, sin = eng._rope_tensors(rope)
+    for i in range(3):
+        eng.zero_grad()
+        ev[0].record()
+        eng.L.a2m_forward_train(eng.h, dev_x[i % R].data_ptr(), B, cos.data_ptr(), sin.data_ptr(), 300, None, None, eng._stream())
+        ev[1].record()
+        eng.L.a2m_backward(eng.h, dev_y[i % R].data_ptr(), 1.0, eng.grads.data_ptr(), eng.loss.data_ptr(), eng._stream())
+        ev[2].record()
+        eng.allreduce_grads()
+        ev[3].record()
+        eng.optimizer_step(sched(W + K + i + 1), cfg)
+        ev[4].record()
+        torch.cuda.synchronize()
+        acc += np.array([ev[j].elapsed_time(ev[j + 1]) for j in range(4)])
+    acc /= 3
+    # end to end: pinned host audio + labels copied in every step, loss read back every step
+    pin_x = [torch.tensor(h).pin_memory() for h in host]
+    pin_y = [torch.tensor(h).pin_memory() for h in host_y]
+    bx, by = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        bx.copy_(pin_x[i % R], non_blocking=True)
+        by.copy_(pin_y[i % R], non_blocking=True)
+        loss, valid, _ = eng.training_step(bx, by, rope, cfg, sched(W + K + 3 + i + 1))
+        lv = float(loss.item())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    value = world * B * K / (ms / 1e3)
+    peaks = _peaks()
+    return {
+        "metric": "train samples/sec", "value": value, "unit": "samples/s", "ms_per_step": ms / K, "steps": K, "warmup": W,
+        "batch_per_gpu": B, "global_batch": B * world, "scaling": "weak",
+        "step": "forward with tape + backward + gradient all-reduce (NCCL) + AdamW/clip + weight re-pack (train.py:259-332)",
+        "dtype": "bf16 operands, fp32 accumulate / master weights / optimizer state (reference: fp16 forward+backward, fp32 master)",
+        "dropout": "not applied (rate 0.0; the reference trains with 0.1): see DESIGN.md",
+        "breakdown_ms": {"forward": round(acc[0], 3), "backward": round(acc[1], 3), "allreduce": round(acc[2], 3),
+                         "adamw_repack": round(acc[3], 3)},
+        "tflops": world * B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12,
+        "frac_of_tensor_peak": B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12 / peaks["tensor_sustained"],
+        "e2e": {"value": world * B * K / dt, "unit": "samples/s", "h2d_bytes_per_step": B * (2 * 80000 + 250 * 90) * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": eng.launch_count() * K, "last_loss": lv, "loss_after_timed": loss_last,
+        "allreduce_bytes": eng.n_params * 4,
+    }
+
+
 def run_ours(args):
     import torch
     import audio_to_midi_b200 as A
@@ -225,6 +322,13 @@ def run_ours(args):
         predict(None, host_batches[i % R], rope)
     e2e_sync = B * WINDOW_S * min(args.steps, 5) / (time.perf_counter() - t0)
 
+    # ---- training step (config 4); shares the device with the forward model, runs after it
+    train = None
+    if not args.no_train:
+        del dev_batches
+        torch.cuda.empty_cache()
+        train = measure_train(args, A, synth, dev, rank, world, dist, local)
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -281,6 +385,8 @@ def run_ours(args):
                          "sample": f"{cpu_n} windows x {cpu_iters} iterations ({cpu_s:.2f} s each), PyTorch-CPU fp32 "
                                    f"restatement (oracle/model_torch.py); JAX reference not installable (SURVEY F1)"},
     }
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -293,6 +399,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=64, help="training windows per GPU per step")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

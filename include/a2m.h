@@ -146,6 +146,8 @@ int a2m_backward(A2mHandle* h, const float* labels_dev, float scale, float* grad
  * gradient all-reduce happens between a2m_backward and this call, on grads_dev, by the caller (NCCL). */
 int a2m_adamw_step(A2mHandle* h, const float* grads_dev, float lr, float b1, float b2, float eps, float weight_decay,
                    float grad_divisor, float clip_norm, int32_t step, float* stats_dev, void* stream);
+/* Per-launch profile of the training plans (which = 0 forward-with-tape, 1 backward); contract of a2m_profile_steps. */
+int32_t a2m_profile_train_steps(A2mHandle* h, int32_t which, int32_t repeats, int32_t max_steps, A2mStepProfile* out);
 int32_t a2m_train_launch_count(const A2mHandle* h);   /* kernels of the last forward_train + backward */
 /* test hook: dW[n_out, k_out] += dY[tokens, n_out]^T X[tokens, k_out] (bf16 operands) on the tcgen05 wgrad kernel */
 int a2m_debug_wgrad(A2mHandle* h, int32_t tokens, int32_t n_out, int32_t k_out, const void* dY_bf16_dev, int32_t ldy,

@@ -156,3 +156,47 @@ def test_window_sharding_world2_gloo():
         p.join(timeout=60)
     for _, vals in res:
         assert vals == [float(i + 1) for i in range(37)]
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audio_to_midi_b200 import train as T
+    lo, hi = T.shard_batch(8, world, rank)
+    g = torch.full((5,), float(rank + 1))
+    loss = torch.tensor([float(hi)])
+    T.allreduce_mean_([g, loss])
+    q.put((rank, lo, hi, g.tolist(), loss.item()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """Host logic of the data-parallel training step (batch split + gradient mean) on 2 CPU ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    ps = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert [(g[1], g[2]) for g in got] == [(0, 4), (4, 8)]
+    for g in got:
+        assert g[3] == [1.5] * 5 and g[4] == 6.0
+
+
+def test_lr_schedule_and_multipliers():
+    """create_learning_rate_schedule (train.py:454-466) and the layer-wise decay labels of setup_optimizers (train.py:648-704)."""
+    from audio_to_midi_b200 import train as T
+    sch = T.create_learning_rate_schedule(1e-4, 1000, 200_000)
+    assert sch(0) == 0.0 and abs(sch(500) - 5e-5) < 1e-12 and abs(sch(1000) - 1e-4) < 1e-12
+    assert abs(sch(1000 + 100_000) - 5e-5) < 1e-9 and sch(1000 + 200_000) < 1e-12
+    paths = ["layers.0.layers.0.conv.weight", "layers.0.layers.3.gamma", "layers.6.layers.3.gamma", "norm.weight",
+             "transformer.layers.local_attention.attention_norm.weight"]
+    m = T.layer_lr_multipliers(paths, 0.7)
+    assert m[-1] == 1.0 and m[3] == 1.0 and m[2] == 1.0          # deepest conv layer: decay ** 0
+    assert abs(m[0] - 0.7 ** 39) < 1e-9 and abs(m[1] - 0.7 ** 36) < 1e-9
