@@ -351,48 +351,49 @@ cudaError_t launch_gemm(int BN, int mode, const CUtensorMap& a, const CUtensorMa
 }
 
 template <int BN, int MODE, bool RESID>
-cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int num_sms,
-                           cudaStream_t s) {
+cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& r, const GemmArgs& g,
+                           int num_sms, cudaStream_t s) {
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * (g.N / BN);
   int grid = std::min(tiles, num_sms);
   if (MODE == G2_ROPE) {  // even/odd CTAs own even/odd m-blocks (gemm_tc2.cuh: tile_coords)
     if (((g.M + GEMM_BM - 1) / GEMM_BM) % 2 != 0 || g.rows_per_window != 2 * GEMM_BM) return cudaErrorInvalidValue;
     grid = std::max(2, grid & ~1);
   }
-  return launch_k(PF_GEMM, gemm_tc2_kernel<BN, MODE, RESID>, dim3(grid), dim3(G2_THREADS), gemm2_smem_bytes<BN>(), s, a, b, c, g);
+  return launch_k(PF_GEMM, gemm_tc2_kernel<BN, MODE, RESID>, dim3(grid), dim3(G2_THREADS), gemm2_smem_bytes<BN>(), s, a, b, c, r, g);
 }
 
 cudaError_t launch_gemm2(int BN, int mode, bool resid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
-                         const GemmArgs& g, int num_sms, cudaStream_t s) {
+                         const CUtensorMap& r, const GemmArgs& g, int num_sms, cudaStream_t s) {
   if (g.N % BN != 0 || g.K % GEMM_BK != 0 || g.M <= 0 || g.N > G2_MAXN) return cudaErrorInvalidValue;
   switch (mode * 10000 + BN * 10 + (resid ? 1 : 0)) {
-    case G2_F32 * 10000 + 640: return launch_gemm2_t<64, G2_F32, false>(a, b, c, g, num_sms, s);
-    case G2_F32 * 10000 + 641: return launch_gemm2_t<64, G2_F32, true>(a, b, c, g, num_sms, s);
-    case G2_F32 * 10000 + 1280: return launch_gemm2_t<128, G2_F32, false>(a, b, c, g, num_sms, s);
-    case G2_F32 * 10000 + 1281: return launch_gemm2_t<128, G2_F32, true>(a, b, c, g, num_sms, s);
-    case G2_F32 * 10000 + 2560: return launch_gemm2_t<256, G2_F32, false>(a, b, c, g, num_sms, s);
-    case G2_F32 * 10000 + 2561: return launch_gemm2_t<256, G2_F32, true>(a, b, c, g, num_sms, s);
-    case G2_BF16 * 10000 + 640: return launch_gemm2_t<64, G2_BF16, false>(a, b, c, g, num_sms, s);
-    case G2_BF16 * 10000 + 1280: return launch_gemm2_t<128, G2_BF16, false>(a, b, c, g, num_sms, s);
-    case G2_BF16 * 10000 + 2560: return launch_gemm2_t<256, G2_BF16, false>(a, b, c, g, num_sms, s);
-    case G2_GLU * 10000 + 2560: return launch_gemm2_t<256, G2_GLU, false>(a, b, c, g, num_sms, s);
-    case G2_ROPE * 10000 + 640: return launch_gemm2_t<64, G2_ROPE, false>(a, b, c, g, num_sms, s);
-    case G2_ROPE * 10000 + 1280: return launch_gemm2_t<128, G2_ROPE, false>(a, b, c, g, num_sms, s);
+    case G2_F32 * 10000 + 640: return launch_gemm2_t<64, G2_F32, false>(a, b, c, r, g, num_sms, s);
+    case G2_F32 * 10000 + 641: return launch_gemm2_t<64, G2_F32, true>(a, b, c, r, g, num_sms, s);
+    case G2_F32 * 10000 + 1280: return launch_gemm2_t<128, G2_F32, false>(a, b, c, r, g, num_sms, s);
+    case G2_F32 * 10000 + 1281: return launch_gemm2_t<128, G2_F32, true>(a, b, c, r, g, num_sms, s);
+    case G2_F32 * 10000 + 2560: return launch_gemm2_t<256, G2_F32, false>(a, b, c, r, g, num_sms, s);
+    case G2_F32 * 10000 + 2561: return launch_gemm2_t<256, G2_F32, true>(a, b, c, r, g, num_sms, s);
+    case G2_BF16 * 10000 + 640: return launch_gemm2_t<64, G2_BF16, false>(a, b, c, r, g, num_sms, s);
+    case G2_BF16 * 10000 + 1280: return launch_gemm2_t<128, G2_BF16, false>(a, b, c, r, g, num_sms, s);
+    case G2_BF16 * 10000 + 2560: return launch_gemm2_t<256, G2_BF16, false>(a, b, c, r, g, num_sms, s);
+    case G2_GLU * 10000 + 2560: return launch_gemm2_t<256, G2_GLU, false>(a, b, c, r, g, num_sms, s);
+    case G2_ROPE * 10000 + 640: return launch_gemm2_t<64, G2_ROPE, false>(a, b, c, r, g, num_sms, s);
+    case G2_ROPE * 10000 + 1280: return launch_gemm2_t<128, G2_ROPE, false>(a, b, c, r, g, num_sms, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 // Chooses the v2 kernel (TMA-staged epilogue) for a GemmArgs; returns false if only gemm_tc_kernel can serve it.
-bool gemm2_route(A2mHandle* h, int mode, const GemmArgs& g, int* mode2, bool* resid, CUtensorMap* tc) {
+bool gemm2_route(A2mHandle* h, int mode, const GemmArgs& g, int* mode2, bool* resid, CUtensorMap* tc, CUtensorMap* tr) {
   *resid = false;
+  std::memset(tr, 0, sizeof *tr);
   if (g.N > G2_MAXN) return false;
   if (mode == GEMM_GENERIC) {
     const bool o32 = g.flags & GF_OUT32, o16 = g.flags & GF_OUT16;
     if (o32 == o16) return false;
     if (o32) {
-      if ((g.flags & GF_RESID) && (g.resid != g.out32 || g.ldr != g.ld32)) return false;
       *mode2 = G2_F32;
       *resid = (g.flags & GF_RESID) != 0;
+      if (*resid && !make_tmap_f32(h, tr, g.resid, g.M, g.N, g.ldr, 32, 128)) return false;
       return make_tmap_f32(h, tc, g.out32, g.M, g.N, g.ld32, 32, 128);
     }
     if (g.flags & (GF_GAMMA | GF_RESID)) return false;
@@ -714,10 +715,10 @@ bool add_gemm(A2mHandle* h, Plan* p, int BN, int mode, const __nv_bfloat16* A, i
   }
   int mode2 = 0;
   bool resid = false;
-  CUtensorMap tc;
-  if (h->use_gemm2 && gemm2_route(h, mode, g, &mode2, &resid, &tc)) {
+  CUtensorMap tc, tr;
+  if (h->use_gemm2 && gemm2_route(h, mode, g, &mode2, &resid, &tc, &tr)) {
     st.kernel = "gemm_tc2_kernel";
-    st.run = [=](cudaStream_t s) { return launch_gemm2(BN, mode2, resid, ta, tb, tc, g, sms, s); };
+    st.run = [=](cudaStream_t s) { return launch_gemm2(BN, mode2, resid, ta, tb, tc, tr, g, sms, s); };
   } else {
     st.run = [=](cudaStream_t s) { return launch_gemm(BN, mode, ta, tb, g, sms, s); };
   }
@@ -1377,17 +1378,10 @@ int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t 
   g.out32 = out32; g.ld32 = N;
   g.out16 = static_cast<__nv_bfloat16*>(out16); g.ld16 = N;
   int mode2 = 0;
-  bool resid_inplace = false;
-  CUtensorMap tc;
-  GemmArgs g2 = g;
-  if ((flags & GF_RESID) && (flags & GF_OUT32) && !(flags & GF_OUT16) && h->use_gemm2) {
-    // the production kernel adds the residual in place: seed the output with it
-    CUDA_TRY(cudaMemcpyAsync(out32, resid, sizeof(float) * static_cast<size_t>(M) * N, cudaMemcpyDeviceToDevice,
-                             static_cast<cudaStream_t>(stream)));
-    g2.resid = out32;
-  }
-  if (h->use_gemm2 && gemm2_route(h, GEMM_GENERIC, g2, &mode2, &resid_inplace, &tc)) {
-    CUDA_TRY(launch_gemm2(block_n, mode2, resid_inplace, ta, tb, tc, g2, h->num_sms, static_cast<cudaStream_t>(stream)));
+  bool with_resid = false;
+  CUtensorMap tc, tr;
+  if (h->use_gemm2 && gemm2_route(h, GEMM_GENERIC, g, &mode2, &with_resid, &tc, &tr)) {
+    CUDA_TRY(launch_gemm2(block_n, mode2, with_resid, ta, tb, tc, tr, g, h->num_sms, static_cast<cudaStream_t>(stream)));
   } else {
     CUDA_TRY(launch_gemm(block_n, GEMM_GENERIC, ta, tb, g, h->num_sms, static_cast<cudaStream_t>(stream)));
   }

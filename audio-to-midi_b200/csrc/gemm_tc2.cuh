@@ -3,7 +3,8 @@
 // never touches global memory from the epilogue threads:
 //
 //   * bias / layer-scale vectors are copied to shared memory once per CTA;
-//   * the fp32 residual tile is TMA-loaded by a dedicated producer warp into a ring of 16 KB staging chunks
+//   * the fp32 residual tile (tensor map tmR; may be the output itself for an in-place update, or another buffer
+//     when the training forward must keep its input) is TMA-loaded by a dedicated producer warp into a ring of 16 KB staging chunks
 //     (128 rows x 128 B, 128B-swizzled) while the MMAs of the tile run;
 //   * each epilogue thread (one accumulator row) adds its row chunk in shared memory, in place;
 //   * one elected thread TMA-stores the chunk (bulk async group); rows beyond M are clipped by the tensor map.
@@ -37,7 +38,7 @@ constexpr size_t gemm2_smem_bytes() {
 template <int BN, int MODE, bool RESID>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
   static_assert(!RESID || MODE == G2_F32, "residual add is an fp32-output feature");
   constexpr int STAGES = g2_stages<BN>();
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -89,6 +90,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if constexpr (RESID) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
@@ -166,7 +168,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t cb = ck % G2_NCH, cph = (ck / G2_NCH) & 1;
             mbar_wait(&bar_cempty[cb], cph ^ 1);
             mbar_arrive_expect_tx(&bar_cfull[cb], G2_CHUNK);
-            tma_load_2d(sStage + cb * G2_CHUNK, &tmC, &bar_cfull[cb], n_blk * BN + c * 32, m_blk * GEMM_BM);
+            tma_load_2d(sStage + cb * G2_CHUNK, &tmR, &bar_cfull[cb], n_blk * BN + c * 32, m_blk * GEMM_BM);
           }
         }
       }

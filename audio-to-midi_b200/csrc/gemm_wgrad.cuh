@@ -47,20 +47,29 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_amn(uint32_t m, uint32_t 
   return umma_idesc_bf16(m, n) | (1u << 15);
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// TMA reduction smem -> global: adds a 128B-swizzled [rows x 32 fp32] box into the fp32 tensor behind `m` (element-wise
+// add performed by the L2, one full line per request instead of one 16-byte atomic per thread); rows / columns outside
+// the tensor are clipped.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 
-// tmA: dY [T, N_out] bf16, box {64 cols, 64 rows};  tmB: X [T, K_out] bf16, box {64 cols, 64 rows}.
-// scale multiplies the tile before it is added (1.0 for plain gradients).
+// tmA: dY [T, N_out] bf16, box {64 cols, 64 rows};  tmB: X [T, K_out] bf16, box {64 cols, 64 rows};
+// tmD: dW [N_out, K_out] fp32, box {32 cols, 128 rows} (128B swizzle).
+// bias_out (optional): fp32 [N_out] += column sums of dY (the bias gradient that goes with this weight gradient),
+// computed by the otherwise idle epilogue warps from the staged dY tiles of the CTAs that own column tile 0.
 template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ dW,
-                  int ldw, int n_out, int k_out, int tokens, int splits) {
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmD, float* __restrict__ bias_out, int n_out, int k_out, int tokens, int splits) {
   constexpr int STAGES = wg_stages<BN>();
   constexpr int A_BYTES = 2 * WG_BOX;
   constexpr int B_BYTES = (BN / 64) * WG_BOX;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(STAGES * (A_BYTES + B_BYTES) >= (BN / 32) * 128 * 128, "epilogue staging re-uses the pipeline buffers");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,14 +87,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int nb = (tokens + WG_TOK - 1) / WG_TOK;
   const int tb0 = static_cast<int>(static_cast<long long>(nb) * split / splits);
   const int tb1 = static_cast<int>(static_cast<long long>(nb) * (split + 1) / splits);
+  const bool do_bias = bias_out != nullptr && k_blk == 0;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], do_bias ? 5 : 1);   // MMA commit (+ one lane of each epilogue warp)
     }
     mbar_init(bar_done, 1);
     fence_barrier_init();
@@ -136,22 +147,48 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const int quad = warp & 3;
+    const int r = quad * 32 + lane;          // accumulator row == column of the dY tile
+    if (do_bias) {
+      // column sums of the staged dY tiles: element (tok, r) of chunk r / 64 in the 128B-swizzled box
+      float acc = 0.f;
+      uint32_t s = 0, ph = 0;
+      const uint32_t cbase = (r >> 6) * WG_BOX + (r & 7) * 2, c16 = (r & 63) >> 3;
+      for (int tb = tb0; tb < tb1; ++tb) {
+        mbar_wait(&bar_full[s], ph);
+        const uint8_t* base = sA + s * A_BYTES + cbase;
+#pragma unroll 8
+        for (int t = 0; t < WG_TOK; ++t)
+          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + t * 128 + ((c16 ^ (t & 7)) << 4)));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      const int n = n_blk * 128 + r;
+      if (n < n_out) atomicAdd(bias_out + n, acc);
+    }
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    const int n = n_blk * 128 + quad * 32 + lane;
+    // accumulator -> fp32 staging chunks (128 rows x 32 columns, swizzled) in the drained pipeline buffers -> TMA add
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    float* drow = dW + static_cast<size_t>(n) * ldw + k_blk * BN;
+    const uint32_t rsw = static_cast<uint32_t>(r & 7);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(taddr + c * 32, r);
+      uint32_t v[32];
+      tmem_ld_x32(taddr + c * 32, v);
       tmem_ld_wait();
-      if (n < n_out && k_blk * BN + c * 32 < k_out) {
+      uint8_t* srow = smem + c * (128 * 128) + r * 128;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          red_add_v4(drow + c * 32 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-      }
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(q) ^ rsw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 2 && lane == 0) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c)
+        if (k_blk * BN + c * 32 < k_out) tma_reduce_add_2d(&tmD, smem + c * (128 * 128), k_blk * BN + c * 32, n_blk * 128);
+      bulk_commit();
+      bulk_wait_all<0>();
     }
   }
   tc_fence_before();

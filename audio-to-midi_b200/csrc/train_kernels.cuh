@@ -428,43 +428,39 @@ __global__ void __launch_bounds__(256) block_gamma_finish_kernel(const __nv_bflo
   }
 }
 
-// ------------------------------------------------------------------------------------------ token-reduced outer products
-// acc[i] (+)= sum_tok A[r_i][tok] * B[c_i][tok] for the (r, c) pairs a thread owns: the per-CTA "mini wgrad" of the
-// small-channel stages.  sA [R][ST], sB [Cc][ST] fp32 in shared memory, ST = tokens + 1 (odd stride).
-template <int R, int Cc, int NT, int ST, int THREADS>
-struct OuterAcc {
-  static constexpr int ITEMS = R * Cc;
-  static constexpr int PER = (ITEMS + THREADS - 1) / THREADS;
-  __device__ static __forceinline__ void run(const float* sA, const float* sB, float* acc) {
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int it = threadIdx.x + i * THREADS;
-      if (it < ITEMS) {
-        const float* a = sA + (it / Cc) * ST;
-        const float* b = sB + (it % Cc) * ST;
-        float s = 0.f;
-#pragma unroll 8
-        for (int t = 0; t < NT; ++t) s = fmaf(a[t], b[t], s);
-        acc[i] += s;
-      }
-    }
-  }
-  __device__ static __forceinline__ void flush(float* gdst, const float* acc) {   // gdst [R][Cc]
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int it = threadIdx.x + i * THREADS;
-      if (it < ITEMS) atomicAdd(gdst + it, acc[i]);
-    }
-  }
-};
-
 // ------------------------------------------------------------------------------------------ small Block backward (C <= 32)
 // One thread per token recomputes the Block (block_small_kernel) and its backward; tile = SBB_IN inner tokens + 3 halo
 // tokens on each side whose g = d(dwconv output) is needed by the transposed depthwise conv.  Parameter gradients are
 // written in the SmallBlockLayout image.
+//   * pointwise-conv weight gradients: per-token du / gelu(u) / a / dg2 are staged row-per-token in shared memory (bf16,
+//     like every tensor-core wgrad operand) and reduced over the tile's tokens by register-tiled outer products
+//     (4 x 4 outputs per thread, 2 vector loads per 16 FMAs);
+//   * per-channel gradients (dw taps, biases, LN affine, gamma): butterfly vector reduction over the warp
+//     (1 shuffle per value instead of 5), then one shared-memory atomic per channel per warp.
 constexpr int SBB_THREADS = 128;
 constexpr int SBB_IN = SBB_THREADS - 6;
-constexpr int SBB_ST = SBB_THREADS + 1;
+
+// Sums v[c] over the 32 lanes for every c < C with C-1 (+ log2(32/C)) shuffles.  Returns, in lane l, the total of channel
+// vec_reduce_channel<C>(l); for C < 32 every group of 32/C consecutive lanes holds the same channel.
+template <int C>
+__device__ __forceinline__ int vec_reduce_channel(int lane) { return lane / (32 / C); }
+template <int C>
+__device__ __forceinline__ float warp_vec_reduce(float (&v)[C], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = C; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (int o = (32 / C) / 2; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  return v[0];
+}
 
 template <int C>
 struct SmallBwdSmem {
@@ -474,35 +470,71 @@ struct SmallBwdSmem {
   static constexpr int P = (Lay::TOTAL + 3) & ~3;
   static constexpr int SX = (SBB_THREADS + 6) * RS;        // rows tile0-6 .. tile0+IN+5  (IN + 12 = THREADS + 6)
   static constexpr int SG = SBB_THREADS * RS;              // g rows tile0-3 .. tile0+IN+2
-  static constexpr int SV = (2 * H + 2 * C) * SBB_ST;      // du[H] | gl[H] | a[C] | dg2[C], token-transposed
-  static constexpr size_t BYTES = static_cast<size_t>(P + SX + SG + SV) * 4;
+  static constexpr int HS = H + 4;                         // bf16 row strides (8-byte aligned, bank-staggered)
+  static constexpr int CS = C + 4;
+  static constexpr int SV16 = SBB_THREADS * (2 * HS + 2 * CS);   // du | gl | a | dg2, row per token, bf16
+  static constexpr size_t BYTES = static_cast<size_t>(P + SX + SG) * 4 + static_cast<size_t>(SV16) * 2;
 };
+
+// acc[TH][TC] += sum_tok A[tok][r0 .. r0+TH) x B[tok][c0 .. c0+TC)   (bf16 rows in shared memory)
+template <int TH, int TC, int AS, int BS>
+__device__ __forceinline__ void outer_tile(const __nv_bfloat16* sA, const __nv_bfloat16* sB, int r0, int c0, float (&acc)[TH][TC]) {
+#pragma unroll 4
+  for (int t = 0; t < SBB_THREADS; ++t) {
+    float a[TH], b[TC];
+    if constexpr (TH == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(sA + t * AS + r0);
+      a[0] = bf16lo(v.x); a[1] = bf16hi(v.x); a[2] = bf16lo(v.y); a[3] = bf16hi(v.y);
+    } else if constexpr (TH == 2) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(sA + t * AS + r0);
+      a[0] = bf16lo(v); a[1] = bf16hi(v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < TH; ++i) a[i] = __bfloat162float(sA[t * AS + r0 + i]);
+    }
+    if constexpr (TC == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(sB + t * BS + c0);
+      b[0] = bf16lo(v.x); b[1] = bf16hi(v.x); b[2] = bf16lo(v.y); b[3] = bf16hi(v.y);
+    } else if constexpr (TC == 2) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(sB + t * BS + c0);
+      b[0] = bf16lo(v); b[1] = bf16hi(v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < TC; ++i) b[i] = __bfloat162float(sB[t * BS + c0 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < TH; ++i)
+#pragma unroll
+      for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
 
 template <int C>
 __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int M,
                                                                       const float* __restrict__ params, float* __restrict__ gparams) {
   using Lay = SmallBlockLayout<C>;
   using SM = SmallBwdSmem<C>;
-  constexpr int H = Lay::H, RS = SM::RS, V = C / 4, ST = SBB_ST;
+  constexpr int H = Lay::H, RS = SM::RS, V = C / 4, HS = SM::HS, CS = SM::CS;
+  constexpr int TH = (C >= 8) ? C / 8 : 1, TC = TH;   // outer-product register tile: 4x4 (C = 32), 2x2, 1x1
+  constexpr int NTILE = (H / TH) * (C / TC);          // 128 threads own a tile (32 for C = 4)
   extern __shared__ __align__(16) float smem_f[];
   float* sp = smem_f;
   float* sx = sp + SM::P;
   float* sg = sx + SM::SX;
-  float* sdu = sg + SM::SG;          // [H][ST]
-  float* sgl = sdu + H * ST;         // [H][ST]
-  float* sa = sgl + H * ST;          // [C][ST]
-  float* sdg = sa + C * ST;          // [C][ST]
-  using OA = OuterAcc<H, C, SBB_THREADS, ST, SBB_THREADS>;
-  float accW1[OA::PER], accW2[OA::PER];
-#pragma unroll
-  for (int i = 0; i < OA::PER; ++i) { accW1[i] = 0.f; accW2[i] = 0.f; }
-  // per-channel parameter gradients: warp-shuffle sums per tile into a CTA accumulator  [dw 7C | dwb | lnw | lnb | b2 | gamma]
-  __shared__ float sacc[12 * C];
-  for (int i = threadIdx.x; i < 12 * C; i += SBB_THREADS) sacc[i] = 0.f;
+  __nv_bfloat16* sdu = reinterpret_cast<__nv_bfloat16*>(sg + SM::SG);   // [tok][HS]
+  __nv_bfloat16* sgl = sdu + SBB_THREADS * HS;
+  __nv_bfloat16* sa = sgl + SBB_THREADS * HS;                           // [tok][CS]
+  __nv_bfloat16* sdg = sa + SBB_THREADS * CS;
+  // CTA accumulator of the per-channel gradients  [dw 7C | dwb | lnw | lnb | b2 | gamma | b1 (H)]
+  __shared__ float sacc[12 * C + H];
+  for (int i = threadIdx.x; i < 12 * C + H; i += SBB_THREADS) sacc[i] = 0.f;
   const int lane = threadIdx.x & 31;
-  float gb1_acc[(H + SBB_THREADS - 1) / SBB_THREADS];
+  const int my_r0 = (threadIdx.x / (C / TC)) * TH, my_c0 = (threadIdx.x % (C / TC)) * TC;
+  float accW1[TH][TC], accW2[TH][TC];
 #pragma unroll
-  for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) gb1_acc[i] = 0.f;
+  for (int i = 0; i < TH; ++i)
+#pragma unroll
+    for (int j = 0; j < TC; ++j) { accW1[i][j] = 0.f; accW2[i][j] = 0.f; }
 
   for (int i = threadIdx.x; i < Lay::TOTAL; i += SBB_THREADS) sp[i] = __ldg(params + i);
   const int ntiles = (M + SBB_IN - 1) / SBB_IN;
@@ -521,9 +553,10 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
     const bool inner = threadIdx.x >= 3 && threadIdx.x < SBB_IN + 3 && tok < M;
     const bool live = tok >= 0 && tok < M;
     const int tokc = min(max(tok, 0), M - 1);   // dead threads compute on a clamped token with every contribution masked
+    const float m = inner ? 1.f : 0.f;
+    const int l = tokc % L;
     float g[C];
     {
-      const int l = tokc % L;
       float y[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) y[c] = sp[Lay::DWB + c];
@@ -558,39 +591,69 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
         dg2[c] = dout[c] * sp[Lay::GAMMA + c];
         da[c] = 0.f;
         o[c] = sp[Lay::B2 + c];
-        sa[c * ST + threadIdx.x] = inner ? a[c] : 0.f;
-        sdg[c * ST + threadIdx.x] = inner ? dg2[c] : 0.f;
       }
-#pragma unroll 2
-      for (int h = 0; h < H; ++h) {
-        float u = sp[Lay::B1 + h], dh = 0.f;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        *reinterpret_cast<uint2*>(sa + threadIdx.x * CS + 4 * q) =
+            make_uint2(pack_bf16x2(m * a[4 * q], m * a[4 * q + 1]), pack_bf16x2(m * a[4 * q + 2], m * a[4 * q + 3]));
+        *reinterpret_cast<uint2*>(sdg + threadIdx.x * CS + 4 * q) =
+            make_uint2(pack_bf16x2(m * dg2[4 * q], m * dg2[4 * q + 1]), pack_bf16x2(m * dg2[4 * q + 2], m * dg2[4 * q + 3]));
+      }
+      float b1part = 0.f;   // this lane's share of the b1 gradient is reduced below, 4 hidden units at a time
+#pragma unroll 1
+      for (int h0 = 0; h0 < H; h0 += 4) {
+        float du4[4], gl4[4];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int h = h0 + hh;
+          float u = sp[Lay::B1 + h], dh = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            u = fmaf(sp[Lay::W1 + h * C + c], a[c], u);
+            dh = fmaf(sp[Lay::W2T + h * C + c], dg2[c], dh);
+          }
+          float gl, dgl;
+          gelu_tanh_grad(u, &gl, &dgl);
+          const float du = dh * dgl;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            da[c] = fmaf(sp[Lay::W1 + h * C + c], du, da[c]);
+            o[c] = fmaf(sp[Lay::W2T + h * C + c], gl, o[c]);
+          }
+          du4[hh] = m * du;
+          gl4[hh] = m * gl;
+        }
+        *reinterpret_cast<uint2*>(sdu + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(du4[0], du4[1]), pack_bf16x2(du4[2], du4[3]));
+        *reinterpret_cast<uint2*>(sgl + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(gl4[0], gl4[1]), pack_bf16x2(gl4[2], gl4[3]));
+        // b1 gradient: sum over the warp's tokens of du for these 4 hidden units
+        const float r = warp_vec_reduce<4>(du4, lane);
+        if ((lane & 7) == 0) atomicAdd(&sacc[12 * C + h0 + (lane >> 3)], r);
+        (void)b1part;
+      }
+      // per-channel sums over tokens: lnw, lnb, b2, gamma
+      {
+        float v1[C], v2[C], v3[C], v4[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          u = fmaf(sp[Lay::W1 + h * C + c], a[c], u);
-          dh = fmaf(sp[Lay::W2T + h * C + c], dg2[c], dh);
+          v1[c] = m * da[c] * y[c];
+          v2[c] = m * da[c];
+          v3[c] = m * dg2[c];
+          v4[c] = m * dout[c] * o[c];
         }
-        float gl, dgl;
-        gelu_tanh_grad(u, &gl, &dgl);
-        const float du = dh * dgl;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          da[c] = fmaf(sp[Lay::W1 + h * C + c], du, da[c]);
-          o[c] = fmaf(sp[Lay::W2T + h * C + c], gl, o[c]);
+        const int ch = vec_reduce_channel<C>(lane);
+        const bool lead = (lane % (32 / C)) == 0;
+        const float r1 = warp_vec_reduce<C>(v1, lane), r2 = warp_vec_reduce<C>(v2, lane);
+        const float r3 = warp_vec_reduce<C>(v3, lane), r4 = warp_vec_reduce<C>(v4, lane);
+        if (lead) {
+          atomicAdd(&sacc[8 * C + ch], r1);
+          atomicAdd(&sacc[9 * C + ch], r2);
+          atomicAdd(&sacc[10 * C + ch], r3);
+          atomicAdd(&sacc[11 * C + ch], r4);
         }
-        sdu[h * ST + threadIdx.x] = inner ? du : 0.f;
-        sgl[h * ST + threadIdx.x] = inner ? gl : 0.f;
       }
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float m = inner ? 1.f : 0.f;
-        const float v1 = warp_sum(m * da[c] * y[c]), v2 = warp_sum(m * da[c]), v3 = warp_sum(m * dg2[c]), v4 = warp_sum(m * dout[c] * o[c]);
-        if (lane == 0) {
-          atomicAdd(&sacc[8 * C + c], v1);
-          atomicAdd(&sacc[9 * C + c], v2);
-          atomicAdd(&sacc[10 * C + c], v3);
-          atomicAdd(&sacc[11 * C + c], v4);
-        }
         da[c] *= sp[Lay::LNW + c];
         s1 += da[c];
         s2 += da[c] * y[c];
@@ -599,32 +662,33 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
       s2 *= (1.0f / C);
 #pragma unroll
       for (int c = 0; c < C; ++c) g[c] = live ? inv * (da[c] - s1 - y[c] * s2) : 0.f;
-      {
-        const float m = inner ? 1.f : 0.f;
+    }
+    {
+      // depthwise-conv gradients: dw[t][c] += g[c] x[tok + t - 3][c], dwb[c] += g[c]
+      const int ch = vec_reduce_channel<C>(lane);
+      const bool lead = (lane % (32 / C)) == 0;
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
-          const int ll = l + t - 3;
-          const float mt = (ll >= 0 && ll < L) ? m : 0.f;
-          const float* row = sx + (threadIdx.x + t) * RS;
+      for (int t = 0; t < 7; ++t) {
+        const int ll = l + t - 3;
+        const float mt = (ll >= 0 && ll < L) ? m : 0.f;
+        const float* row = sx + (threadIdx.x + t) * RS;
+        float v[C];
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float v = warp_sum(mt * g[c] * row[c]);
-            if (lane == 0) atomicAdd(&sacc[t * C + c], v);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float v = warp_sum(m * g[c]);
-          if (lane == 0) atomicAdd(&sacc[7 * C + c], v);
-        }
+        for (int c = 0; c < C; ++c) v[c] = mt * g[c] * row[c];
+        const float r = warp_vec_reduce<C>(v, lane);
+        if (lead) atomicAdd(&sacc[t * C + ch], r);
       }
+      float v[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = m * g[c];
+      const float r = warp_vec_reduce<C>(v, lane);
+      if (lead) atomicAdd(&sacc[7 * C + ch], r);
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) sg[threadIdx.x * RS + c] = g[c];
     __syncthreads();
     // dX for the inner tokens
     if (inner) {
-      const int l = tok % L;
       float acc[C];
       const float4* dsrc = reinterpret_cast<const float4*>(dOut + static_cast<size_t>(tok) * C);
 #pragma unroll
@@ -645,32 +709,27 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
 #pragma unroll
       for (int q = 0; q < V; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     }
-    // weight gradients of the two pointwise convs: token-reduced outer products
-    OA::run(sdu, sa, accW1);     // dW1[h][c]  += du[h] a[c]
-    OA::run(sgl, sdg, accW2);    // dW2t[h][c] += gelu(u)[h] dg2[c]
-#pragma unroll
-    for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) {
-      const int h = threadIdx.x + i * SBB_THREADS;
-      if (h < H) {
-        float s = 0.f;
-        for (int t = 0; t < SBB_THREADS; ++t) s += sdu[h * ST + t];
-        gb1_acc[i] += s;
-      }
+    // weight gradients of the two pointwise convs: token-reduced outer products, 4 x 4 outputs per thread
+    if (threadIdx.x < NTILE) {
+      outer_tile<TH, TC, HS, CS>(sdu, sa, my_r0, my_c0, accW1);    // dW1[h][c]  += du[h] a[c]
+      outer_tile<TH, TC, HS, CS>(sgl, sdg, my_r0, my_c0, accW2);   // dW2t[h][c] += gelu(u)[h] dg2[c]
     }
   }
-  OA::flush(gparams + Lay::W1, accW1);
-  OA::flush(gparams + Lay::W2T, accW2);
+  if (threadIdx.x < NTILE) {
 #pragma unroll
-  for (int i = 0; i < (H + SBB_THREADS - 1) / SBB_THREADS; ++i) {
-    const int h = threadIdx.x + i * SBB_THREADS;
-    if (h < H) atomicAdd(gparams + Lay::B1 + h, gb1_acc[i]);
+    for (int i = 0; i < TH; ++i)
+#pragma unroll
+      for (int j = 0; j < TC; ++j) {
+        atomicAdd(gparams + Lay::W1 + (my_r0 + i) * C + my_c0 + j, accW1[i][j]);
+        atomicAdd(gparams + Lay::W2T + (my_r0 + i) * C + my_c0 + j, accW2[i][j]);
+      }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 12 * C; i += SBB_THREADS) {
-    // sacc order: dw[7][C] | dwb | lnw | lnb | b2 | gamma  ->  SmallBlockLayout offsets
+  for (int i = threadIdx.x; i < 12 * C + H; i += SBB_THREADS) {
+    // sacc order: dw[7][C] | dwb | lnw | lnb | b2 | gamma | b1[H]  ->  SmallBlockLayout offsets
     const int seg = i / C, c = i % C;
     const int off = seg < 7 ? Lay::DW + i : seg == 7 ? Lay::DWB + c : seg == 8 ? Lay::LNW + c : seg == 9 ? Lay::LNB + c
-                  : seg == 10 ? Lay::B2 + c : Lay::GAMMA + c;
+                  : seg == 10 ? Lay::B2 + c : seg == 11 ? Lay::GAMMA + c : Lay::B1 + (i - 12 * C);
     atomicAdd(gparams + off, sacc[i]);
   }
 }
@@ -680,22 +739,34 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
 // dY [M_out, COUT] -> dX [2*M_out, CIN]; parameter gradients in the SmallDownLayout image.
 constexpr int SDB_THREADS = 128;
 template <int CIN>
-constexpr size_t small_down_bwd_smem() {
-  return static_cast<size_t>(SmallDownLayout<CIN>::TOTAL + (2 * CIN + 2 * CIN) * (SDB_THREADS + 1)) * 4;
-}
+struct SmallDownBwd {
+  static constexpr int COUT = 2 * CIN, K = 2 * CIN;
+  static constexpr int T = (CIN >= 16) ? 4 : (CIN == 8 ? 2 : 1);          // register tile T x T
+  static constexpr int TILES = (COUT / T) * (K / T);
+  static constexpr int PER = (TILES + SDB_THREADS - 1) / SDB_THREADS;     // tiles per thread (2 for CIN = 32)
+  static constexpr int OS = COUT + 4, KS = K + 4;                         // bf16 row strides
+  static constexpr size_t BYTES = static_cast<size_t>(SmallDownLayout<CIN>::TOTAL) * 4 + static_cast<size_t>(SDB_THREADS) * (OS + KS) * 2;
+};
+template <int CIN>
+constexpr size_t small_down_bwd_smem() { return SmallDownBwd<CIN>::BYTES; }
+
 template <int CIN>
 __global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const float* X, const float* dY, float* dX, int M_out,
                                                                            const float* __restrict__ params, float* __restrict__ gparams) {
   using Lay = SmallDownLayout<CIN>;
-  constexpr int COUT = Lay::COUT, K = 2 * CIN, ST = SDB_THREADS + 1;
+  using SD = SmallDownBwd<CIN>;
+  constexpr int COUT = Lay::COUT, K = 2 * CIN, T = SD::T, OS = SD::OS, KS = SD::KS;
   extern __shared__ __align__(16) float smem_f[];
   float* sp = smem_f;
-  float* sdy = sp + Lay::TOTAL;     // [COUT][ST]
-  float* sn = sdy + COUT * ST;      // [K][ST]
-  using OA = OuterAcc<COUT, K, SDB_THREADS, ST, SDB_THREADS>;
-  float accW[OA::PER];
+  __nv_bfloat16* sdy = reinterpret_cast<__nv_bfloat16*>(sp + Lay::TOTAL);   // [tok][OS]
+  __nv_bfloat16* sn = sdy + SDB_THREADS * OS;                               // [tok][KS]
+  float accW[SD::PER][T][T];
 #pragma unroll
-  for (int i = 0; i < OA::PER; ++i) accW[i] = 0.f;
+  for (int p = 0; p < SD::PER; ++p)
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+      for (int j = 0; j < T; ++j) accW[p][i][j] = 0.f;
   float glw[CIN], glb[CIN], gbo = 0.f;
 #pragma unroll
   for (int c = 0; c < CIN; ++c) { glw[c] = 0.f; glb[c] = 0.f; }
@@ -705,18 +776,12 @@ __global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const
     __syncthreads();
     const int tok = tile * SDB_THREADS + threadIdx.x;
     if (tok < M_out) {
-      float n[K], dy[COUT], dn[K], inv[2];
+      float n[K], dn[K], inv[2];
       const float4* src = reinterpret_cast<const float4*>(X + static_cast<size_t>(tok) * K);
 #pragma unroll
       for (int q = 0; q < K / 4; ++q) {
         const float4 v = src[q];
         n[4 * q] = v.x; n[4 * q + 1] = v.y; n[4 * q + 2] = v.z; n[4 * q + 3] = v.w;
-      }
-      const float4* dsrc = reinterpret_cast<const float4*>(dY + static_cast<size_t>(tok) * COUT);
-#pragma unroll
-      for (int q = 0; q < COUT / 4; ++q) {
-        const float4 v = dsrc[q];
-        dy[4 * q] = v.x; dy[4 * q + 1] = v.y; dy[4 * q + 2] = v.z; dy[4 * q + 3] = v.w;
       }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -732,15 +797,24 @@ __global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const
         for (int c = 0; c < CIN; ++c) n[t * CIN + c] *= inv[t];   // xhat
       }
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
+      for (int k = 0; k < K; k += 2) {
         dn[k] = 0.f;
-        sn[k * ST + threadIdx.x] = n[k] * sp[Lay::LNW + (k % CIN)] + sp[Lay::LNB + (k % CIN)];
+        dn[k + 1] = 0.f;
+        *reinterpret_cast<uint32_t*>(sn + threadIdx.x * KS + k) =
+            pack_bf16x2(n[k] * sp[Lay::LNW + (k % CIN)] + sp[Lay::LNB + (k % CIN)],
+                        n[k + 1] * sp[Lay::LNW + ((k + 1) % CIN)] + sp[Lay::LNB + ((k + 1) % CIN)]);
       }
+      const float4* dsrc = reinterpret_cast<const float4*>(dY + static_cast<size_t>(tok) * COUT);
+#pragma unroll 1
+      for (int q = 0; q < COUT / 4; ++q) {
+        const float4 v = dsrc[q];
+        const float dy[4] = {v.x, v.y, v.z, v.w};
+        *reinterpret_cast<uint2*>(sdy + threadIdx.x * OS + 4 * q) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 #pragma unroll
-      for (int o = 0; o < COUT; ++o) {
-        sdy[o * ST + threadIdx.x] = dy[o];
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) dn[k] = fmaf(sp[Lay::W + o * K + k], dy[o], dn[k]);
+          for (int k = 0; k < K; ++k) dn[k] = fmaf(sp[Lay::W + (4 * q + u) * K + k], dy[u], dn[k]);
+        }
       }
       float* dst = dX + static_cast<size_t>(tok) * K;
 #pragma unroll
@@ -764,20 +838,32 @@ __global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const
       for (int q = 0; q < K / 4; ++q)
         reinterpret_cast<float4*>(dst)[q] = make_float4(dn[4 * q], dn[4 * q + 1], dn[4 * q + 2], dn[4 * q + 3]);
     } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k) sn[k * ST + threadIdx.x] = 0.f;
-#pragma unroll
-      for (int o = 0; o < COUT; ++o) sdy[o * ST + threadIdx.x] = 0.f;
+      for (int k = 0; k < K; k += 2) *reinterpret_cast<uint32_t*>(sn + threadIdx.x * KS + k) = 0u;
+      for (int o = 0; o < COUT; o += 2) *reinterpret_cast<uint32_t*>(sdy + threadIdx.x * OS + o) = 0u;
     }
     __syncthreads();
-    OA::run(sdy, sn, accW);
+#pragma unroll
+    for (int p = 0; p < SD::PER; ++p) {
+      const int it = threadIdx.x + p * SDB_THREADS;
+      if (it < SD::TILES) outer_tile<T, T, OS, KS>(sdy, sn, (it / (K / T)) * T, (it % (K / T)) * T, accW[p]);
+    }
     if (threadIdx.x < COUT) {
       float s = 0.f;
-      for (int t = 0; t < SDB_THREADS; ++t) s += sdy[threadIdx.x * ST + t];
+      for (int t = 0; t < SDB_THREADS; ++t) s += __bfloat162float(sdy[t * OS + threadIdx.x]);
       gbo += s;
     }
   }
-  OA::flush(gparams + Lay::W, accW);
+#pragma unroll
+  for (int p = 0; p < SD::PER; ++p) {
+    const int it = threadIdx.x + p * SDB_THREADS;
+    if (it < SD::TILES) {
+      const int r0 = (it / (K / T)) * T, c0 = (it % (K / T)) * T;
+#pragma unroll
+      for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) atomicAdd(gparams + Lay::W + (r0 + i) * K + c0 + j, accW[p][i][j]);
+    }
+  }
   if (threadIdx.x < COUT) atomicAdd(gparams + Lay::B + threadIdx.x, gbo);
   const int lane = threadIdx.x & 31;
 #pragma unroll
