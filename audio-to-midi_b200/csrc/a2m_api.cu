@@ -195,6 +195,10 @@ struct Step {
   double flops = 0.0;       // algorithmic matmul/conv FLOPs of this launch (2 * MACs)
   double bytes = 0.0;       // algorithmic bytes this launch must move (operands in + results out)
   std::function<cudaError_t(cudaStream_t)> run;
+  // training plans: steps off the critical path (weight gradients) run on a side stream
+  bool side = false;    // launch on the side stream, after everything enqueued on the main stream so far
+  int rec_mark = -1;    // side steps: record completion mark k after this step
+  int join_mark = -1;   // main steps: wait for completion mark k before this step (buffer re-use)
 };
 
 struct Plan {
