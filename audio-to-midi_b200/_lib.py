@@ -37,7 +37,7 @@ EXPORTS = [
     "a2m_create", "a2m_destroy", "a2m_last_error", "a2m_load_weights", "a2m_workspace_bytes", "a2m_forward",
     "a2m_forward_host", "a2m_submit_host", "a2m_collect_host", "a2m_host_alloc", "a2m_host_free",
     "a2m_last_launch_count", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_forward_tap", "a2m_debug_gemm",
-    "a2m_train_init", "a2m_param_count", "a2m_get_params", "a2m_set_lr_multipliers", "a2m_forward_train", "a2m_backward",
+    "a2m_train_init", "a2m_set_dropout", "a2m_param_count", "a2m_get_params", "a2m_set_lr_multipliers", "a2m_forward_train", "a2m_backward",
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
 ]
@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     f32 = C.c_float
     L.a2m_train_init.argtypes = [vp, vp, sz, C.POINTER(LeafDesc), i32]
     L.a2m_train_init.restype = C.c_int
+    L.a2m_set_dropout.argtypes = [vp, f32, u64]
+    L.a2m_set_dropout.restype = C.c_int
     L.a2m_param_count.argtypes = [vp]
     L.a2m_param_count.restype = C.c_int64
     L.a2m_get_params.argtypes = [vp, vp, vp]

@@ -887,7 +887,8 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (!make_tmap_3d(h, &tv, kv, kKV, kT, B, kKV, kTP, 64, AL_NK)) return false;
       // as written in the reference: 31 windows x 4 heads x (QK^T + PV) of 16 x 16 x 64
       add_step(p, Meta{"attn_local_tc_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
-        return launch_k(PF_ATTN, attn_local_tc_kernel, dim3(2, ATT_HEADS, B), dim3(AL_THREADS), AL_SMEM, st, tq, tk, tv, o16, kD, 256);
+        return launch_k(PF_ATTN, attn_local_tc_kernel, dim3(2, ATT_HEADS, B), dim3(AL_THREADS), AL_SMEM, st, tq, tk, tv, o16, kD, 256,
+                        static_cast<const DropParams*>(nullptr), 0u);
       });
     } else {
       GemmArgs g = gemm_args(Mt, kQC, kD);
@@ -905,7 +906,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (!make_tmap(h, &tk, kv, Mt, 256, kKV, 64, 256)) return false;
       if (!make_tmap(h, &tv, kv, Mt, kKV, kKV, 64, 256)) return false;   // V = columns 256..511, row-major [key][d]
       add_step(p, Meta{"attn_global_kernel", 2.0 * B * ATT_HEADS * (2.0 * kT * kT * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
-        return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256, static_cast<float*>(nullptr));
+        return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256, static_cast<float*>(nullptr), static_cast<const DropParams*>(nullptr), 0u);
       });
     }
     {

@@ -36,7 +36,7 @@ constexpr uint32_t AG_TMEM_COLS = 256;    // S: 256 columns; O re-uses columns 0
 __global__ void __launch_bounds__(AG_THREADS, 2)
 attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int v_col0,
-                   float* __restrict__ lse) {
+                   float* __restrict__ lse, const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -94,6 +94,11 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t t_row = (static_cast<uint32_t>(warp * 32) << 16);
   // softmax((q / 8) . k): scale folded into the exponent; exp2 with log2(e) pre-multiplied
   const float kscale = 0.125f * 1.4426950408889634f;
+  // training: dropout of the attention weights (model.py:254-255), after the normalisation
+  const uint32_t dthresh = drop ? drop->thresh : 0u;
+  const float dinv = drop ? drop->inv_keep : 1.f;
+  const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
+  const uint32_t dbase = ((static_cast<uint32_t>(b) * ATT_HEADS + h) * ATT_TP + mt * 128 + row) * ATT_TP;
   float mx = -INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {
@@ -128,6 +133,13 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // the row sum must match what the tensor core will see: accumulate the ROUNDED probabilities
       sum += __low2float(h0) + __high2float(h0) + __low2float(h1) + __high2float(h1) + __low2float(h2) +
              __high2float(h2) + __low2float(h3) + __high2float(h3);
+      if (dthresh != 0u) {   // the P.V operand is the dropped-out weights; the normaliser above is not
+        const uint32_t i0 = dbase + c * 32 + 8 * q;
+        h0 = __floats2bfloat162_rn(p[8 * q] * drop_mul(dkey, i0, dthresh, dinv), p[8 * q + 1] * drop_mul(dkey, i0 + 1, dthresh, dinv));
+        h1 = __floats2bfloat162_rn(p[8 * q + 2] * drop_mul(dkey, i0 + 2, dthresh, dinv), p[8 * q + 3] * drop_mul(dkey, i0 + 3, dthresh, dinv));
+        h2 = __floats2bfloat162_rn(p[8 * q + 4] * drop_mul(dkey, i0 + 4, dthresh, dinv), p[8 * q + 5] * drop_mul(dkey, i0 + 5, dthresh, dinv));
+        h3 = __floats2bfloat162_rn(p[8 * q + 6] * drop_mul(dkey, i0 + 6, dthresh, dinv), p[8 * q + 7] * drop_mul(dkey, i0 + 7, dthresh, dinv));
+      }
       uint4 v;
       v.x = *reinterpret_cast<uint32_t*>(&h0);
       v.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -223,7 +235,8 @@ constexpr uint32_t AL_TMEM_COLS = 256;     // S: columns 0..143, O: columns 192.
 // tmQ / tmK / tmV are 3-D maps {cols, 250 rows, B} over the q||c and k||v projection buffers.
 __global__ void __launch_bounds__(AL_THREADS, 2)
 attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* O, int ldo, int v_col0) {
+                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* O, int ldo, int v_col0,
+                     const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -317,13 +330,30 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const float wn = (has_a && has_b) ? 0.5f : 1.0f;      // divide by the number of covering windows
   const float ia = has_a ? __fdividef(wn, suma) : 0.f;
   const float ib = has_b ? __fdividef(wn, sumb) : 0.f;
+  // training: each window's attention weights are dropped out independently (model.py:443 -> 254-255);
+  // element index ((b, h, window, row in window), key in window)
+  const uint32_t dthresh = drop ? drop->thresh : 0u;
+  const float dinv = drop ? drop->inv_keep : 1.f;
+  const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
+  const int wa = (j >> 3) - 1, wb = j >> 3;
+  const uint32_t bh = static_cast<uint32_t>(b) * ATT_HEADS + h;
+  const uint32_t da0 = ((bh * 31u + static_cast<uint32_t>(wa)) * 16u + static_cast<uint32_t>(j - 8 * wa)) * 16u;
+  const uint32_t db0 = ((bh * 31u + static_cast<uint32_t>(wb)) * 16u + static_cast<uint32_t>(j - 8 * wb)) * 16u;
 #pragma unroll
   for (int c = 0; c < 48; ++c) {
     const bool in_a = static_cast<unsigned>(c - off) < 16u;
     const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
     float p = 0.f;
-    if (in_a) p += exp2f((s[c] - ma) * kscale) * ia;
-    if (in_b) p += exp2f((s[c] - mb) * kscale) * ib;
+    if (in_a) {
+      float pa = exp2f((s[c] - ma) * kscale) * ia;
+      if (dthresh != 0u) pa *= drop_mul(dkey, da0 + static_cast<uint32_t>(c - off), dthresh, dinv);
+      p += pa;
+    }
+    if (in_b) {
+      float pb = exp2f((s[c] - mb) * kscale) * ib;
+      if (dthresh != 0u) pb *= drop_mul(dkey, db0 + static_cast<uint32_t>(c - off - 8), dthresh, dinv);
+      p += pb;
+    }
     s[c] = p;
   }
   // P row (144 keys = 18 chunks of 8) into the swizzled K-major layout; this warp's slab is chunks 4w .. 4w+5

@@ -36,7 +36,8 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                        const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, int ldo,
                        const float* __restrict__ lse, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
-                       __nv_bfloat16* __restrict__ dQ, int lddq, __nv_bfloat16* __restrict__ dKV, int lddkv, int v_col0) {
+                       __nv_bfloat16* __restrict__ dQ, int lddq, __nv_bfloat16* __restrict__ dKV, int lddkv, int v_col0,
+                       const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -180,6 +181,10 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   };
 
   const float kscale = 0.125f * 1.4426950408889634f;
+  // dropout of the attention weights (forward: attention.cuh): O = (P o m) V, so dV uses P o m and dP is masked too
+  const uint32_t dthresh = drop ? drop->thresh : 0u;
+  const float dinv = drop ? drop->inv_keep : 1.f;
+  const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
 #pragma unroll 1
   for (int blk = 0; blk < 4; ++blk) {
     const int j = blk >> 1, i = blk & 1;
@@ -207,8 +212,11 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int key = j * 128 + col0 + 2 * t + u;
           float p = exp2f(__uint_as_float(rs[2 * t + u]) * kscale - Lr);
           p = (key < ATT_T && qreal) ? p : 0.f;
-          p2[u] = p;
-          d2[u] = p * (__uint_as_float(rp[2 * t + u]) - Dr) * 0.125f;
+          float mk = 1.f;
+          if (dthresh != 0u)
+            mk = drop_mul(dkey, ((static_cast<uint32_t>(b) * ATT_HEADS + h) * ATT_TP + i * 128 + row) * ATT_TP + key, dthresh, dinv);
+          p2[u] = p * mk;
+          d2[u] = p * (__uint_as_float(rp[2 * t + u]) * mk - Dr) * 0.125f;
         }
         pp[t] = pack_bf16x2_att(p2[0], p2[1]);
         ps[t] = pack_bf16x2_att(d2[0], d2[1]);
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(ALB_THREADS, 2)
 attn_local_bwd_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ KV, int ldkv, int v_col0,
                       const __nv_bfloat16* __restrict__ dOut, int ldo, const float* __restrict__ rope_cos,
                       const float* __restrict__ rope_sin, __nv_bfloat16* __restrict__ dQ, int lddq,
-                      __nv_bfloat16* __restrict__ dKV, int lddkv) {
+                      __nv_bfloat16* __restrict__ dKV, int lddkv, const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sk = sq + ALB_ROWS * ALB_LD;
@@ -335,14 +343,24 @@ attn_local_bwd_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_b
 #pragma unroll
     for (int k = 0; k < 16; ++k) { s[k] = __expf((s[k] - mx) * 0.125f); sum += s[k]; }
     const float inv = wn / sum;
+    // dropout of this window's attention weights (forward: attn_local_tc_kernel): mask the weights used for dV and dP
+    float mk[16];
+    {
+      const uint32_t dthresh = drop ? drop->thresh : 0u;
+      const float dinv = drop ? drop->inv_keep : 1.f;
+      const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
+      const uint32_t i0 = (((static_cast<uint32_t>(b) * ATT_HEADS + h) * 31u + static_cast<uint32_t>(w)) * 16u + static_cast<uint32_t>(r)) * 16u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) mk[k] = (dthresh != 0u) ? drop_mul(dkey, i0 + k, dthresh, dinv) : 1.f;
+    }
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { s[k] *= inv; dot = fmaf(s[k], dp[k], dot); }   // s = wn * p
+    for (int k = 0; k < 16; ++k) { s[k] *= inv; dp[k] *= mk[k]; dot = fmaf(s[k], dp[k], dot); }   // s = wn * p, dp masked
     // d logit_k = wn p_k (dp_k - sum_k' p_k' dp_k') / 8, and dot = wn * sum p dp  ->  s_k (dp_k - dot / wn) / 8
     const float mean = (wn > 0.f) ? dot / wn : 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      sP[wr * 16 + k] = s[k];
+      sP[wr * 16 + k] = s[k] * mk[k];
       sS[wr * 16 + k] = s[k] * (dp[k] - mean) * 0.125f;
     }
   }

@@ -51,6 +51,9 @@ struct GemmArgs {
   float* probs;
   int valid_rows;  // 250
   int valid_cols;  // 90
+  // training: dropout of (acc + bias) before the residual add (FeedForwardBlock, model.py:237); gemm_tc2 G2_F32 only
+  const DropParams* drop;
+  uint32_t drop_site;
 };
 
 constexpr int GEMM_BM = 128;

@@ -180,6 +180,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t rsw = static_cast<uint32_t>(r & 7);
     uint32_t a = 0, aph = 0, ck = 0;
+    uint32_t drop_k = 0u, drop_thresh = 0u;
+    float drop_inv = 1.f;
+    if (MODE == G2_F32 && g.drop != nullptr) {
+      drop_thresh = g.drop->thresh;
+      drop_inv = g.drop->inv_keep;
+      drop_k = drop_key(g.drop->seed, g.drop_site);
+    }
     float rc[MODE == G2_ROPE ? 32 : 1], rs[MODE == G2_ROPE ? 32 : 1];  // this row's cos / sin (all 32 pairs)
     int rope_mblk = -1;
     int m_blk, n_blk;
@@ -227,6 +234,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (g.flags & GF_GAMMA) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= sGamma[col0 + j];
+          }
+          if (g.drop != nullptr && drop_thresh != 0u) {
+            const uint32_t base = static_cast<uint32_t>(row0 + r) * static_cast<uint32_t>(g.N) + static_cast<uint32_t>(col0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= drop_mul(drop_k, base + j, drop_thresh, drop_inv);
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {

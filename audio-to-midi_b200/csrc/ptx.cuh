@@ -28,6 +28,28 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- dropout (training)
+// eqx.nn.Dropout (model.py:224, 335): keep with probability 1 - p, scale kept values by 1 / (1 - p).  Counter based:
+// the decision for element `idx` of dropout site `site` is a pure function of (seed, site, idx), so the backward
+// kernels regenerate the forward's mask instead of storing it.  The parameters live in device memory (one struct per
+// handle, rewritten before every forward) so that CUDA graphs need no re-capture when the seed changes.
+struct DropParams {
+  uint32_t seed;
+  uint32_t thresh;    // drop iff hash < thresh;  thresh = round(p * 2^32), 0 = dropout off
+  float inv_keep;     // 1 / (1 - p)
+  uint32_t pad;
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {   // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t site) { return mix32(seed ^ (site * 0x85ebca6bu + 0x9e3779b9u)); }
+// multiplier of element idx: 1 / (1 - p) if kept, 0 if dropped
+__device__ __forceinline__ float drop_mul(uint32_t key, uint32_t idx, uint32_t thresh, float inv_keep) {
+  return mix32((idx * 0x9e3779b1u) ^ key) >= thresh ? inv_keep : 0.f;
+}
+enum DropSite : uint32_t { DROP_FFN = 0, DROP_GLOBAL = 1, DROP_LOCAL = 2 };   // site id = layer * 4 + kind
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

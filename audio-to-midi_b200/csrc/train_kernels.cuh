@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 template <int C, bool ACCUMULATE>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* X, const float* dY, int nB, int Lx, int Ly,
                                                      const float* __restrict__ lnw, float* dX, __nv_bfloat16* dX16,
-                                                     float* __restrict__ gw, float* __restrict__ gb) {
+                                                     float* __restrict__ gw, float* __restrict__ gb,
+                                                     const DropParams* __restrict__ drop, uint32_t drop_site) {
   using RM = RowMap<C>;
   constexpr int PER = RM::PER;
   pdl_launch_dependents();
@@ -138,7 +139,20 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* X, const float
       for (int j = 0; j < PER; ++j) dx[j] += old[j];
     }
     RM::store_f32(dst, lane, dx);
-    if (dX16 != nullptr) RM::store_bf16(dX16 + static_cast<size_t>(r) * C, lane, dx);
+    if (dX16 != nullptr) {
+      // the bf16 copy feeds the FFN of the layer below, whose output went through dropout (model.py:237):
+      // d(pre-dropout) = mask / (1 - p) * d(post-dropout); the fp32 copy is the residual path and stays unmasked
+      if (drop != nullptr && drop->thresh != 0u) {
+        const uint32_t key = drop_key(drop->seed, drop_site), th = drop->thresh;
+        const float inv_keep = drop->inv_keep;
+#pragma unroll
+        for (int g = 0; g < RM::G; ++g)
+#pragma unroll
+          for (int j = 0; j < RM::VW; ++j)
+            dx[g * RM::VW + j] *= drop_mul(key, static_cast<uint32_t>(r) * C + RM::chan(lane, g) + j, th, inv_keep);
+      }
+      RM::store_bf16(dX16 + static_cast<size_t>(r) * C, lane, dx);
+    }
   }
   __shared__ float sw[8][C], sb[8][C];
 #pragma unroll
@@ -238,6 +252,10 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* U, co
     *reinterpret_cast<uint4*>(dU + uo) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
     *reinterpret_cast<uint4*>(dU + uo + 128) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
   }
+}
+
+__global__ void set_drop_params_kernel(DropParams* p, uint32_t seed, uint32_t thresh, float inv_keep) {
+  p->seed = seed; p->thresh = thresh; p->inv_keep = inv_keep; p->pad = 0u;
 }
 
 // fp32 -> bf16 copy (n4 = elements / 4)

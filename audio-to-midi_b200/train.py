@@ -141,6 +141,11 @@ class TrainEngine:
         a = np.ascontiguousarray(per_leaf, np.float32)
         _lib.check(self.h, self.L.a2m_set_lr_multipliers(self.h, a.ctypes.data, a.size), "a2m_set_lr_multipliers")
 
+    def set_dropout(self, rate: float, seed: int = 0):
+        """transformer_dropout_rate of the following forward/backward pairs (model.py:30; the reference trains with 0.1)
+        and the seed that stands in for the PRNG key of train.py:53."""
+        _lib.check(self.h, self.L.a2m_set_dropout(self.h, float(rate), int(seed) & 0xFFFFFFFFFFFFFFFF), "a2m_set_dropout")
+
     # ---- compute_loss (train.py:48-62): forward with tape + backward, accumulating into self.grads / self.loss
     def zero_grad(self):
         self.grads.zero_()
@@ -178,7 +183,7 @@ class TrainEngine:
 
     # ---- compute_training_step (train.py:259-332)
     def training_step(self, audio, labels, rope_freqs: RopeFreqs, cfg: OptimizerConfig, lr: float, grad_scale: float = 1.0,
-                      minibatch_size: Optional[int] = None):
+                      minibatch_size: Optional[int] = None, dropout_rate: float = 0.0, key: int = 0):
         """Minibatch scan with fp32 gradient accumulation, unscale by grad_scale x steps, all-reduce, AdamW + clip.
         Returns (loss, grads_valid, scaled_loss) as device tensors / lazily evaluated values (no host sync here)."""
         B = audio.shape[0]
@@ -188,6 +193,7 @@ class TrainEngine:
         steps = B // mb
         self.zero_grad()
         for i in range(steps):
+            self.set_dropout(dropout_rate, (int(key) * 0x9E3779B97F4A7C15 + self.step_count * 1315423911 + i) & 0xFFFFFFFFFFFFFFFF)
             self.forward_backward(audio[i * mb:(i + 1) * mb], labels[i * mb:(i + 1) * mb], rope_freqs, scale=grad_scale)
         self.allreduce_grads()
         self.optimizer_step(lr, cfg, grad_divisor=grad_scale * steps)
@@ -228,8 +234,10 @@ class TrainEngine:
 def compute_loss(model: OutputSequenceGenerator, state, audio, rope_freqs: RopeFreqs, expected_outputs, scale, key=None,
                  engine: Optional[TrainEngine] = None):
     """Reference call shape of compute_loss (train.py:48-62, under eqx.filter_value_and_grad(has_aux=True)):
-    returns ((loss, state), grads) with grads keyed by pytree path.  Dropout is not applied."""
+    returns ((loss, state), grads) with grads keyed by pytree path.  `key` (an int) seeds dropout at the model's
+    transformer_dropout_rate, as enable_dropout=True does in the reference; key=None runs without dropout."""
     eng = engine or TrainEngine(model)
     eng.zero_grad()
+    eng.set_dropout(model_config["transformer_dropout_rate"] if key is not None else 0.0, 0 if key is None else int(key))
     eng.forward_backward(audio, expected_outputs, rope_freqs, scale=float(scale))
     return (eng.loss.clone(), state), eng.grads_tree()

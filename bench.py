@@ -140,6 +140,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+DROPOUT = 0.1   # transformer_dropout_rate (model.py:30), applied as in train.py:56-58 (enable_dropout=True)
 TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_WINDOW   # fwd + dgrad + wgrad, no recompute counted
 
 
@@ -169,12 +170,12 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
 
     W, K = max(args.warmup, 3), args.train_steps
     for i in range(W):
-        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(i + 1))
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(i + 1), dropout_rate=DROPOUT, key=SEED)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(W + i + 1))
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(W + i + 1), dropout_rate=DROPOUT, key=SEED)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -189,6 +190,7 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
     cos, sin = eng._rope_tensors(rope)
     for i in range(3):
         eng.zero_grad()
+        eng.set_dropout(DROPOUT, SEED + i)
         ev[0].record()
         eng.L.a2m_forward_train(eng.h, dev_x[i % R].data_ptr(), B, cos.data_ptr(), sin.data_ptr(), 300, None, None, eng._stream())
         ev[1].record()
@@ -210,7 +212,7 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
     for i in range(K):
         bx.copy_(pin_x[i % R], non_blocking=True)
         by.copy_(pin_y[i % R], non_blocking=True)
-        loss, valid, _ = eng.training_step(bx, by, rope, cfg, sched(W + K + 3 + i + 1))
+        loss, valid, _ = eng.training_step(bx, by, rope, cfg, sched(W + K + 3 + i + 1), dropout_rate=DROPOUT, key=SEED)
         lv = float(loss.item())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -225,7 +227,7 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
         "batch_per_gpu": B, "global_batch": B * world, "scaling": "weak",
         "step": "forward with tape + backward + gradient all-reduce (NCCL) + AdamW/clip + weight re-pack (train.py:259-332)",
         "dtype": "bf16 operands, fp32 accumulate / master weights / optimizer state (reference: fp16 forward+backward, fp32 master)",
-        "dropout": "not applied (rate 0.0; the reference trains with 0.1): see DESIGN.md",
+        "dropout": DROPOUT,
         "breakdown_ms": {"forward": round(acc[0], 3), "backward": round(acc[1], 3), "allreduce": round(acc[2], 3),
                          "adamw_repack": round(acc[3], 3)},
         "tflops": world * B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12,

@@ -132,8 +132,14 @@ int64_t a2m_param_count(const A2mHandle* h);                          /* floats 
 int a2m_get_params(A2mHandle* h, float* out_dev, void* stream);       /* current master parameters, blob layout */
 /* One learning-rate multiplier per leaf (layer-wise decay of train.py:646-726); NULL resets to 1. */
 int a2m_set_lr_multipliers(A2mHandle* h, const float* per_leaf_host, int32_t n_leaves);
-/* Forward that records the tape; logits_dev / probs_dev [batch, 250, 90] may be NULL.  Dropout is not applied
- * (rate 0): see DESIGN.md.  audio_dev must stay valid until a2m_backward has run. */
+/* Dropout of the following a2m_forward_train / a2m_backward pairs: `rate` = transformer_dropout_rate (model.py:30) applied
+ * to the attention weights (model.py:254-255, per window for the local layers) and to the FeedForwardBlock output
+ * (model.py:237), kept values scaled by 1 / (1 - rate); 0 disables it (the state after a2m_train_init).  `seed` plays
+ * the role of the PRNG key (train.py:53): masks are a counter-based hash of (seed, site, element), regenerated in the
+ * backward; the random stream is NOT jax's threefry. */
+int a2m_set_dropout(A2mHandle* h, float rate, uint64_t seed);
+/* Forward that records the tape; logits_dev / probs_dev [batch, 250, 90] may be NULL.  audio_dev must stay valid until
+ * a2m_backward has run. */
 int a2m_forward_train(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
                       const float* rope_sin_dev, int32_t rope_max_pos, float* logits_dev, float* probs_dev, void* stream);
 /* grads_dev [param_count] += d/dparams of  mean_b( sum_{t,c} BCEWithLogits(z, y) * scale )  (compute_loss, train.py:50-62);

@@ -59,7 +59,49 @@ def _rope(x, rope):
     return torch.stack([x1 * cos - x2 * sin, x1 * sin + x2 * cos], dim=-1).flatten(-2)
 
 
-def _self_attention(x, p, rope, heads, dropout_p=0.0):
+def _mix32(x):
+    """numpy restatement of the CUDA path's counter-based dropout hash (csrc/ptx.cuh mix32)."""
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def dropout_masks(seed: int, rate: float, batch: int, num_layers: int = 8):
+    """The masks (already scaled by 1 / (1 - rate)) the CUDA training path applies for (seed, rate): a pure function of
+    (seed, site, element index), csrc/ptx.cuh.  Returns {("ffn" | "global" | "local", layer): torch.Tensor}; layer counts
+    TransformerLayers 0..15 (even = local, odd = global)."""
+    p = min(max(float(rate), 0.0), 0.999)
+    thresh = np.uint32(min(int(p * 4294967296.0), 4294967295))
+    inv_keep = np.float32(1.0 / (1.0 - p))
+    seed32 = np.uint32((seed & 0xffffffff) ^ (((seed >> 32) * 0x9e3779b9) & 0xffffffff))
+
+    def mul(site, idx):
+        key = _mix32(np.array([seed32 ^ np.uint32((site * 0x85ebca6b + 0x9e3779b9) & 0xffffffff)], np.uint32))[0]
+        h = _mix32((idx.astype(np.uint32) * np.uint32(0x9e3779b1)) ^ key)
+        return torch.tensor(np.where(h >= thresh, inv_keep, np.float32(0.0)).astype(np.float32))
+
+    out = {}
+    with np.errstate(over="ignore"):
+        b = np.arange(batch, dtype=np.int64)
+        for i in range(2 * num_layers):
+            idx = ((b[:, None, None] * 256 + np.arange(250)[None, :, None]) * 256 + np.arange(256)[None, None, :])
+            out[("ffn", i)] = mul(i * 4 + 0, idx)
+            bh = b[:, None] * 4 + np.arange(4)[None, :]
+            if i % 2 == 1:
+                idx = ((bh[:, :, None, None] * 256 + np.arange(250)[None, None, :, None]) * 256 + np.arange(250)[None, None, None, :])
+                out[("global", i)] = mul(i * 4 + 1, idx)
+            else:
+                idx = (((bh[:, :, None, None, None] * 31 + np.arange(31)[None, None, :, None, None]) * 16
+                        + np.arange(16)[None, None, None, :, None]) * 16 + np.arange(16)[None, None, None, None, :])
+                out[("local", i)] = mul(i * 4 + 2, idx).permute(0, 2, 1, 3, 4)   # (B, window, head, row, key)
+    return out
+
+
+def _self_attention(x, p, rope, heads, dropout_p=0.0, wmask=None):
     """model.py:340-374 on (..., S, D)."""
     s = x.shape[-2]
     lead = x.shape[:-2]
@@ -70,13 +112,15 @@ def _self_attention(x, p, rope, heads, dropout_p=0.0):
     q, k, v = (t.transpose(-3, -2) for t in (q, k, v))              # (..., H, S, hd)
     logits = (q / math.sqrt(q.shape[-1])) @ k.transpose(-1, -2)
     w = torch.softmax(logits.float(), dim=-1).to(logits.dtype)
-    if dropout_p > 0.0:
+    if wmask is not None:
+        w = w * wmask
+    elif dropout_p > 0.0:
         w = F.dropout(w, dropout_p, training=True)
     a = (w @ v).transpose(-3, -2).reshape(*lead, s, -1)
     return F.linear(a, p["output_proj"]["weight"])
 
 
-def _local_self_attention(x, p, rope, heads, window=LOCAL_CONTEXT, dropout_p=0.0):
+def _local_self_attention(x, p, rope, heads, window=LOCAL_CONTEXT, dropout_p=0.0, wmask=None):
     """model.py:409-471 on (B, S, D)."""
     b, seq_len, d = x.shape
     stride = window // 2
@@ -88,7 +132,7 @@ def _local_self_attention(x, p, rope, heads, window=LOCAL_CONTEXT, dropout_p=0.0
         xin = F.pad(x, (0, 0, lo, hi))
     nw = (xin.shape[1] - window) // stride + 1
     wins = xin.unfold(1, window, stride).permute(0, 1, 3, 2)         # (B, nw, window, D)
-    ow = _self_attention(wins, p["self_attention"], rope, heads, dropout_p)
+    ow = _self_attention(wins, p["self_attention"], rope, heads, dropout_p, wmask)
     idx = (torch.arange(nw)[:, None] * stride + torch.arange(window)[None, :]).reshape(-1)
     keep = idx < seq_len                                             # out-of-range scatter updates dropped
     flat = ow.reshape(b, nw * window, d)
@@ -97,24 +141,26 @@ def _local_self_attention(x, p, rope, heads, window=LOCAL_CONTEXT, dropout_p=0.0
     return out / count[None, :, None]
 
 
-def _feed_forward(x, p, dropout_p=0.0):
+def _feed_forward(x, p, dropout_p=0.0, omask=None):
     u = F.linear(x, p["attention_to_intermediate_proj"]["weight"], p["attention_to_intermediate_proj"]["bias"])
     x1, x2 = u.chunk(2, dim=-1)
     y = F.linear(_gelu(x1) * x2, p["intermediate_to_attention_proj"]["weight"],
                  p["intermediate_to_attention_proj"]["bias"])
-    if dropout_p > 0.0:
+    if omask is not None:
+        y = y * omask
+    elif dropout_p > 0.0:
         y = F.dropout(y, dropout_p, training=True)
     return y
 
 
-def _transformer_layer(x, p, rope, heads, local, dropout_p=0.0):
+def _transformer_layer(x, p, rope, heads, local, dropout_p=0.0, wmask=None, omask=None):
     d = x.shape[-1]
     n = F.layer_norm(x, (d,), p["attention_norm"]["weight"], p["attention_norm"]["bias"], 1e-5)
-    r = (_local_self_attention(n, p["attention_block"], rope, heads, dropout_p=dropout_p) if local
-         else _self_attention(n, p["attention_block"], rope, heads, dropout_p))
+    r = (_local_self_attention(n, p["attention_block"], rope, heads, dropout_p=dropout_p, wmask=wmask) if local
+         else _self_attention(n, p["attention_block"], rope, heads, dropout_p, wmask))
     h = x + r
     n2 = F.layer_norm(h, (d,), p["feed_forward_norm"]["weight"], p["feed_forward_norm"]["bias"], 1e-5)
-    return h + _feed_forward(n2, p["feed_forward_block"], dropout_p)
+    return h + _feed_forward(n2, p["feed_forward_block"], dropout_p, omask)
 
 
 def _slice(tree, i):
@@ -123,7 +169,7 @@ def _slice(tree, i):
     return tree[i]
 
 
-def forward(params, samples, rope=None, conf=None, dropout_p=0.0, taps=None):
+def forward(params, samples, rope=None, conf=None, dropout_p=0.0, taps=None, masks=None):
     """Batched OutputSequenceGenerator forward: samples (B, 2, N) -> logits, probs (B, T, 90)."""
     conf = MODEL_CONFIG if conf is None else conf
     if rope is None:
@@ -154,10 +200,12 @@ def forward(params, samples, rope=None, conf=None, dropout_p=0.0, taps=None):
     tl = params["transformer"]["layers"]
     for i in range(conf["num_transformer_layers"]):
         lp = _slice(tl, i)
-        h = _transformer_layer(h, lp["local_attention"], rope, heads, True, dropout_p)
+        mk = masks or {}
+        h = _transformer_layer(h, lp["local_attention"], rope, heads, True, dropout_p, mk.get(("local", 2 * i)), mk.get(("ffn", 2 * i)))
         if taps is not None:
             taps[f"tl{i}_local"] = h
-        h = _transformer_layer(h, lp["global_attention"], rope, heads, False, dropout_p)
+        h = _transformer_layer(h, lp["global_attention"], rope, heads, False, dropout_p, mk.get(("global", 2 * i + 1)),
+                               mk.get(("ffn", 2 * i + 1)))
         if taps is not None:
             taps[f"tl{i}_global"] = h
     dec = params["decoder"]
@@ -166,8 +214,9 @@ def forward(params, samples, rope=None, conf=None, dropout_p=0.0, taps=None):
     return logits, torch.sigmoid(logits)
 
 
-def loss_fn(params, samples, targets, scale=1.0, rope=None, conf=None):
-    """train.py:39-62 with dropout off: per-sample sum of BCE-with-logits x scale, mean over batch."""
-    logits, _ = forward(params, samples, rope, conf)
+def loss_fn(params, samples, targets, scale=1.0, rope=None, conf=None, masks=None):
+    """train.py:39-62: per-sample sum of BCE-with-logits x scale, mean over batch.  Dropout is off unless `masks`
+    (dropout_masks) replays the CUDA path's masks."""
+    logits, _ = forward(params, samples, rope, conf, masks=masks)
     per = F.binary_cross_entropy_with_logits(logits.float(), targets, reduction="none").sum(dim=(1, 2)) * scale
     return per.mean(), logits

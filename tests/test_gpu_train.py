@@ -49,6 +49,27 @@ def test_backward_matches_autograd():
     assert eng.launch_count() > 500
 
 
+def test_backward_with_dropout_matches_autograd():
+    """Dropout 0.1 on the attention weights (global and per-window local) and on the FFN output (model.py:237, 254-255):
+    the oracle replays the CUDA path's counter-based masks, so losses and every leaf gradient must agree as without dropout."""
+    import train_util as U
+    from oracle import model_torch as MT
+    tree, audio, labels = U.setup(2)
+    seed = 0x1234_5678_9ABC
+    masks = MT.dropout_masks(seed, 0.1, 2)
+    keep = float((masks[("global", 1)] > 0).float().mean())
+    assert abs(keep - 0.9) < 5e-3, keep
+    lref, gref, zref = U.oracle_grads(tree, audio, labels, masks=masks)
+    lcu, gcu, zcu, _ = U.cuda_grads(tree, audio, labels, dropout=0.1, seed=seed)
+    l0, _, z0, _ = U.cuda_grads(tree, audio, labels)
+    assert np.abs(zcu - z0).max() > 1e-2          # dropout really changes the forward
+    assert abs(lcu - lref) < 2e-3 * abs(lref), (lcu, lref)
+    assert np.abs(zcu - zref).max() < 0.15
+    rows = U.compare(gref, gcu)
+    bad = [(k, round(r, 4)) for k, r, _, _ in rows if not (r < 0.06)]
+    assert not bad, bad[:10]
+
+
 def test_gradient_accumulation_and_adamw():
     """Two minibatches of 1 accumulate to the gradient of the batch of 2 (train.py:283-293); AdamW + global-norm clip of
     the updates (optax.adamw then clip_by_global_norm, train.py:698-726) vs a numpy restatement on the CUDA gradients."""

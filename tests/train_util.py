@@ -10,7 +10,7 @@ from oracle import params as P
 from oracle import synth
 
 
-def oracle_grads(tree, audio, labels, scale=1.0):
+def oracle_grads(tree, audio, labels, scale=1.0, masks=None):
     tp = MT.to_torch(tree, requires_grad=False)
     leaves = {}
 
@@ -25,17 +25,18 @@ def oracle_grads(tree, audio, labels, scale=1.0):
         return t
 
     tp = mark(tp)
-    loss, logits = MT.loss_fn(tp, torch.tensor(audio), torch.tensor(labels), scale=scale)
+    loss, logits = MT.loss_fn(tp, torch.tensor(audio), torch.tensor(labels), scale=scale, masks=masks)
     loss.backward()
     return float(loss), {k: (v.grad.numpy() if v.grad is not None else None) for k, v in leaves.items()}, logits.detach().numpy()
 
 
-def cuda_grads(tree, audio, labels, scale=1.0, device=0):
+def cuda_grads(tree, audio, labels, scale=1.0, device=0, dropout=0.0, seed=0):
     model = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
     eng = T.TrainEngine(model, device)
     rope = A.precompute_frequencies(64, 300)
     dev = torch.device(f"cuda:{device}")
     eng.zero_grad()
+    eng.set_dropout(dropout, seed)
     logits = eng.forward_backward(torch.tensor(audio, device=dev), torch.tensor(labels, device=dev), rope, scale=scale, want_logits=True)
     torch.cuda.synchronize()
     return float(eng.loss.item()), eng.grads_tree(), logits.cpu().numpy(), eng
