@@ -450,8 +450,10 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(block_fused_kernel<64>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(block_fused_kernel<128>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<64, true>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_fused_kernel<128, true>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
   if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -813,11 +815,13 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         const int tiles = (M + FB_TOK - 1) / FB_TOK;
         if (C == 64)
           add_step(p, mf, [=](cudaStream_t st) {
-            return launch_k(PF_FUSED, block_fused_kernel<64>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<64>::SMEM, st, t1, t2, in, out, L, M, prm);
+            return launch_k(PF_FUSED, block_fused_kernel<64, false>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<64>::SMEM, st, t1, t2, in, out, L, M, prm,
+                            t1, t1, static_cast<__nv_bfloat16*>(nullptr));
           }, label, out, static_cast<size_t>(M) * C);
         else
           add_step(p, mf, [=](cudaStream_t st) {
-            return launch_k(PF_FUSED, block_fused_kernel<128>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<128>::SMEM, st, t1, t2, in, out, L, M, prm);
+            return launch_k(PF_FUSED, block_fused_kernel<128, false>, dim3(tiles), dim3(FB_THREADS), FusedBlockCfg<128>::SMEM, st, t1, t2, in, out, L, M, prm,
+                            t1, t1, static_cast<__nv_bfloat16*>(nullptr));
           }, label, out, static_cast<size_t>(M) * C);
         cur ^= 1;
       } else {

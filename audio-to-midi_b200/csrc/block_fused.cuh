@@ -46,10 +46,16 @@ struct FusedBlockCfg {
 };
 
 // Packed fp32 parameters: dw[7][C] | dwb[C] | lnw[C] | lnb[C] | b1[H] | b2g[C] (= gamma * b2)
-template <int C>
+// TAPE (training forward): additionally writes what the backward needs -- the LN output A1 (bf16 [M, C]) and the GELU
+// output A2 (bf16 [M, 2C]) by TMA store straight from their swizzled operand tiles (tmA16 / tmH16, boxes {64, 128}),
+// and the pw1 pre-activation u (bf16 [M, 2C]) by per-row vector stores from the GELU phase.  The elected thread issues
+// each store before the MMAs that read the same tile and waits for the store's shared-memory reads before it commits
+// those MMAs to the barrier the other threads wait on, so a tile is never overwritten while a store still reads it.
+template <int C, bool TAPE>
 __global__ void __launch_bounds__(FB_THREADS, 2)
 block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                   const float* X, float* Y, int L, int M, const float* __restrict__ params) {
+                   const float* X, float* Y, int L, int M, const float* __restrict__ params,
+                   const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmH16, __nv_bfloat16* U16) {
   using Cfg = FusedBlockCfg<C>;
   using RM = RowMap<C>;
   constexpr int H = Cfg::H;
@@ -158,6 +164,11 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
 
   // ---------------------------------------------------------------- phase 2: D1 = A1 . W1^T (NH halves of N = 128)
   if (threadIdx.x == 0) {
+    if constexpr (TAPE) {
+#pragma unroll
+      for (int kb = 0; kb < Cfg::KB1; ++kb) tma_store_2d(&tmA16, sA + kb * (FB_TOK * 128), kb * 64, tile0);
+      bulk_commit();
+    }
     mbar_wait(bar_w1, 0);
     tc_fence_after();
     constexpr uint32_t idesc1 = umma_idesc_bf16(128, Cfg::HH);
@@ -173,6 +184,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
                     (kb | k) != 0 ? 1u : 0u);
       }
     }
+    if constexpr (TAPE) bulk_wait_read<0>();
     umma_commit(bar_d1);
   }
   __syncwarp();
@@ -200,6 +212,17 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       uint32_t r[32];
       tmem_ld_x32(tmem_base + t_row + col0, r);
       tmem_ld_wait();
+      if constexpr (TAPE) {
+        uint32_t pre[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pre[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + sB1[col0 + 2 * j], __uint_as_float(r[2 * j + 1]) + sB1[col0 + 2 * j + 1]);
+        if (tile0 + row < M) {
+          uint4* dst = reinterpret_cast<uint4*>(U16 + static_cast<size_t>(tile0 + row) * H + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         packed[c * 16 + j] = pack_bf16x2(gelu_tanh_f(__uint_as_float(r[2 * j]) + sB1[col0 + 2 * j]),
@@ -218,6 +241,11 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
+      if constexpr (TAPE) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_store_2d(&tmH16, sA + j * (FB_TOK * 128), hh * Cfg::HH + j * 64, tile0);
+        bulk_commit();
+      }
       if (hh == 0) mbar_wait(bar_w2, 0);
       tc_fence_after();
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, C);
@@ -230,6 +258,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           umma_bf16(tmem_d2, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc2,
                     (hh | j | k) != 0 ? 1u : 0u);
       }
+      if constexpr (TAPE) bulk_wait_read<0>();
       umma_commit(&bar_m2[hh]);
     }
     __syncwarp();
@@ -282,6 +311,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
     }
   }
+  if constexpr (TAPE)
+    if (threadIdx.x == 0) bulk_wait_all<0>();   // the tape stores must have landed before the grid may be considered complete
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
