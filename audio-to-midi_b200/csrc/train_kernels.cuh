@@ -274,21 +274,40 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* X, __nv_bfl
 //     dX = dOut + dwconv7^T( LN'(dA) )      (fp32 + bf16 copy)
 // and accumulates the parameter gradients in the packed image layout  dw[7][C] | dwb[C] | lnw[C] | lnb[C].
 // Tile of DWB_TOK tokens per iteration; g = LN'(dA) is recomputed for 3 halo rows on each side.
-constexpr int DWB_TOK = 32;
-constexpr int DWB_THREADS = 256;
+// Each tile's inputs (x rows with a 6-row halo, dA rows with a 3-row halo, dOut rows) are contiguous byte ranges of global
+// memory: one elected thread fetches them with three 1-D bulk async copies (cp.async.bulk, mbarrier completion) into a
+// two-stage shared-memory ring, one tile ahead of the warps that consume them, so the loop never waits on a dependent
+// global load (the first version did three times per tile: 80 % of its stall samples, profiles/r01d_dwconv_bwd.txt).
 template <int C>
-constexpr size_t dwconv_ln_bwd_smem() { return static_cast<size_t>((DWB_TOK + 12) + (DWB_TOK + 6)) * C * 4 + 8 * 10 * C * 4; }
+struct DwBwd {
+  static constexpr int THREADS = (C == 256) ? 256 : 512;     // 16 warps hide the shuffle / smem latency of the row reductions
+  static constexpr int NW = THREADS / 32;
+  static constexpr int TOK = 4096 / C;                      // 64 / 32 / 16 tokens per tile: ~58 KB per stage
+  static constexpr int XR = TOK + 12, AR = TOK + 6;         // rows of x / dA per tile
+  static constexpr int STAGE_FLOATS = (XR + AR + TOK) * C;
+  static constexpr size_t SMEM = static_cast<size_t>(2 * STAGE_FLOATS + AR * C) * 4 + 64;   // + g rows + 2 mbarriers
+  static_assert(NW * 10 * C * 4 <= 2 * STAGE_FLOATS * 4, "the final reduction re-uses the stage buffers");
+};
+template <int C>
+constexpr size_t dwconv_ln_bwd_smem() { return DwBwd<C>::SMEM; }
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 template <int C>
-__global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float* X, const float* dA, const float* dOut, float* dX,
+__global__ void __launch_bounds__(DwBwd<C>::THREADS) dwconv_ln_bwd_kernel(const float* X, const float* dA, const float* dOut, float* dX,
                                                                     __nv_bfloat16* dX16, int L, int M,
                                                                     const float* __restrict__ params, float* __restrict__ gparams) {
   using RM = RowMap<C>;
-  constexpr int PER = RM::PER;
-  extern __shared__ __align__(16) float smem_f[];
-  float* sx = smem_f;                          // rows tile0-6 .. tile0+TOK+5
-  float* sg = sx + (DWB_TOK + 12) * C;         // rows tile0-3 .. tile0+TOK+2
-  float* sred = sg + (DWB_TOK + 6) * C;        // [8 warps][10][C]
+  using D = DwBwd<C>;
+  constexpr int PER = RM::PER, TOK = D::TOK, XR = D::XR, AR = D::AR, DWB_THREADS = D::THREADS;
+  extern __shared__ __align__(128) float smem_f[];
+  float* stage0 = smem_f;
+  float* sg = smem_f + 2 * D::STAGE_FLOATS;              // g rows tile0-3 .. tile0+TOK+2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sg + AR * C);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   float w[7][PER], bias[PER], lw[PER];
@@ -303,22 +322,50 @@ __global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float*
 #pragma unroll
     for (int t = 0; t < 7; ++t) gdw[t][j] = 0.f;
   }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   pdl_wait();
-  const int ntiles = (M + DWB_TOK - 1) / DWB_TOK;
-  constexpr int V = C / 4;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tile0 = tile * DWB_TOK;
-    __syncthreads();   // previous iteration finished reading sx / sg
-    for (int i = threadIdx.x; i < (DWB_TOK + 12) * V; i += DWB_THREADS) {
-      const int r = i / V, q = i - r * V;
-      const int g = tile0 - 6 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(X + static_cast<size_t>(g) * C)[q];
-      reinterpret_cast<float4*>(sx + r * C)[q] = v;
+  const int ntiles = (M + TOK - 1) / TOK;
+  // issues the three bulk copies of `tile` into stage `s`; rows outside [0, M) are not copied (zero-filled by the consumer)
+  auto issue = [&](int tile, int s) {
+    const int tile0 = tile * TOK;
+    float* sx = stage0 + s * D::STAGE_FLOATS;
+    float* sda = sx + XR * C;
+    float* sdo = sda + AR * C;
+    const int x0 = max(tile0 - 6, 0), x1 = min(tile0 + TOK + 6, M);
+    const int a0 = max(tile0 - 3, 0), a1 = min(tile0 + TOK + 3, M);
+    const int o0 = tile0, o1 = min(tile0 + TOK, M);
+    const uint32_t bytes = static_cast<uint32_t>((x1 - x0) + (a1 - a0) + (o1 - o0)) * C * 4u;
+    mbar_arrive_expect_tx(&bars[s], bytes);
+    bulk_load_1d(sx + (x0 - (tile0 - 6)) * C, X + static_cast<size_t>(x0) * C, static_cast<uint32_t>(x1 - x0) * C * 4u, &bars[s]);
+    bulk_load_1d(sda + (a0 - (tile0 - 3)) * C, dA + static_cast<size_t>(a0) * C, static_cast<uint32_t>(a1 - a0) * C * 4u, &bars[s]);
+    bulk_load_1d(sdo, dOut + static_cast<size_t>(o0) * C, static_cast<uint32_t>(o1 - o0) * C * 4u, &bars[s]);
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int tile0 = tile * TOK;
+    float* sx = stage0 + s * D::STAGE_FLOATS;
+    float* sda = sx + XR * C;
+    float* sdo = sda + AR * C;
+    // prefetch the next tile into the other stage: its previous contents were consumed before the barrier that ended
+    // the previous iteration
+    if (threadIdx.x == 0 && tile + static_cast<int>(gridDim.x) < ntiles) issue(tile + gridDim.x, s ^ 1);
+    mbar_wait(&bars[s], (it >> 1) & 1);
+    if (tile0 < 6 || tile0 + TOK + 6 > M) {   // edge tiles: rows outside the tensor were not copied
+      for (int i = threadIdx.x; i < XR * (C / 4); i += DWB_THREADS) {
+        const int r = i / (C / 4), g = tile0 - 6 + r;
+        if (g < 0 || g >= M) reinterpret_cast<float4*>(sx + r * C)[i % (C / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // phase A: g rows tile0-3 .. tile0+TOK+2
-    for (int lr = warp; lr < DWB_TOK + 6; lr += DWB_THREADS / 32) {
+    for (int lr = warp; lr < AR; lr += DWB_THREADS / 32) {
       const int tok = tile0 - 3 + lr;
       float g[PER];
 #pragma unroll
@@ -340,17 +387,19 @@ __global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float*
             for (int j = 0; j < PER; ++j) xr[t][j] = 0.f;
           }
         }
-        float s = 0.f;
+        // single-pass statistics (two independent shuffle reductions instead of two dependent ones)
+        float sm = 0.f, sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) s += y[j];
-        const float mean = warp_sum(s) * (1.0f / C);
-        float v = 0.f;
+        for (int j = 0; j < PER; ++j) { sm += y[j]; sq = fmaf(y[j], y[j], sq); }
+        sm = warp_sum(sm);
+        sq = warp_sum(sq);
+        const float mean = sm * (1.0f / C);
+        const float inv = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + kLnEps);
 #pragma unroll
-        for (int j = 0; j < PER; ++j) { y[j] -= mean; v += y[j] * y[j]; }
-        const float inv = rsqrtf(warp_sum(v) * (1.0f / C) + kLnEps);
+        for (int j = 0; j < PER; ++j) y[j] -= mean;
         float da[PER];
-        RM::load(dA + static_cast<size_t>(tok) * C, lane, da);
-        const bool inner = lr >= 3 && lr < DWB_TOK + 3;
+        RM::load(sda + lr * C, lane, da);
+        const bool inner = lr >= 3 && lr < TOK + 3;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
@@ -377,12 +426,12 @@ __global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float*
     }
     __syncthreads();
     // phase B: dX[m] = dOut[m] + sum_t w[t] g[m - t + 3]  (conv positions inside the same window only)
-    for (int lr = warp; lr < DWB_TOK; lr += DWB_THREADS / 32) {
+    for (int lr = warp; lr < TOK; lr += DWB_THREADS / 32) {
       const int tok = tile0 + lr;
       if (tok >= M) break;
       const int l = tok % L;
       float acc[PER];
-      RM::load(dOut + static_cast<size_t>(tok) * C, lane, acc);
+      RM::load(sdo + lr * C, lane, acc);
 #pragma unroll
       for (int t = 0; t < 7; ++t) {
         const int ll = l - t + 3;
@@ -396,8 +445,10 @@ __global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float*
       RM::store_f32(dX + static_cast<size_t>(tok) * C, lane, acc);
       if (dX16 != nullptr) RM::store_bf16(dX16 + static_cast<size_t>(tok) * C, lane, acc);
     }
+    __syncthreads();   // stage s and sg are free again
   }
-  // parameter gradients: registers -> smem [warp][10][C] -> atomics
+  // parameter gradients: registers -> smem [warp][10][C] (re-using the stage buffers) -> atomics
+  float* sred = stage0;
   float* mine = sred + warp * 10 * C;
 #pragma unroll
   for (int g = 0; g < RM::G; ++g)
@@ -414,7 +465,7 @@ __global__ void __launch_bounds__(DWB_THREADS) dwconv_ln_bwd_kernel(const float*
   for (int i = threadIdx.x; i < 10 * C; i += DWB_THREADS) {
     float t = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += sred[wv * 10 * C + i];
+    for (int wv = 0; wv < D::NW; ++wv) t += sred[wv * 10 * C + i];
     atomicAdd(gparams + i, t);
   }
 }
