@@ -19,6 +19,7 @@
 
 #include "../../include/a2m.h"
 #include "attention.cuh"
+#include "audio_prep.cuh"
 #include "block_fused.cuh"
 #include "cnn_kernels.cuh"
 #include "gemm_tc.cuh"
@@ -132,6 +133,7 @@ struct BigDownW {
 struct TLayerW {
   size_t ln1w, ln1b, wqc, wkv, wo, ln2w, ln2b, w1, b1, w2, b2;
   size_t wqct, wkvt, wot, w1t, w2t;   // training: transposed bf16 copies (dgrad B operands)
+  size_t wqkv;                        // inference: bf16 [768, 256] = Wq ; Wk Wc ; Wv Wc  (compressed-kv projection folded)
 };
 
 struct Weights {
@@ -145,6 +147,7 @@ struct Weights {
   size_t dlnw, dlnb, dw, db;      // decoder: bf16 [128, 256] zero padded, fp32 [128]
   size_t dwt;                     // training: bf16 [256, 128]
   size_t stem_img;                // training: fp32 w[4][2][5] | b[4] | lnw[4] | lnb[4]  (stem_train_kernel)
+  bool folded_kv = false;         // tl[i].wqkv is valid (plain inference load)
 };
 
 struct Workspace {
@@ -157,6 +160,7 @@ struct Workspace {
   __nv_bfloat16* KV16;
   __nv_bfloat16* Vt16;
   __nv_bfloat16* O16;
+  __nv_bfloat16* QKV16;   // folded path: q | k | v, [B*256, 768]
 };
 
 size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
@@ -172,6 +176,7 @@ size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
   const size_t xt = take(b * 65536 * 4);
   const size_t qc = take(b * kTP * kQC * 2), kv = take(b * kTP * kKV * 2);
   const size_t vt = take(b * 65536 * 2), o16 = take(b * 65536 * 2);
+  const size_t qkv = take(b * kTP * 768 * 2);
   if (ws) {
     ws->base = base;
     ws->X[0] = reinterpret_cast<float*>(base + x0);
@@ -183,6 +188,7 @@ size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
     ws->KV16 = reinterpret_cast<__nv_bfloat16*>(base + kv);
     ws->Vt16 = reinterpret_cast<__nv_bfloat16*>(base + vt);
     ws->O16 = reinterpret_cast<__nv_bfloat16*>(base + o16);
+    ws->QKV16 = reinterpret_cast<__nv_bfloat16*>(base + qkv);
   }
   return off;
 }
@@ -251,6 +257,7 @@ struct A2mHandle {
   std::vector<float> rope_host_cache;
   cudaStream_t own_stream = nullptr;
   TrainState* train = nullptr;   // training path (a2m_train.inc)
+  void* clip_stats = nullptr;    // device ClipStats of a2m_prepare_windows
 };
 
 namespace {
@@ -514,6 +521,7 @@ std::vector<float> vec(const LeafView& l, size_t offset = 0, size_t n = 0) {
 }
 
 void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
+  w->folded_kv = !train;
   // ---- stem (model.py:84-100)
   {
     const std::string p = "layers.0.layers.0.";
@@ -664,6 +672,23 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
       t.b1 = ar->put_f32(b1p);
       t.w2 = ar->put_bf16(vec(f2w, li * kD * kFF, kD * kFF));
       t.b2 = ar->put_f32(vec(f2b, li * kD, kD));
+      if (!train) {
+        // k = (x Wc^T) Wk^T = x (Wk Wc)^T and likewise v (model.py:353-358): the inference path skips the 64-wide
+        // intermediate and runs q, k, v as ONE projection.  (The training path keeps c: its gradient needs it.)
+        std::vector<float> qkv(static_cast<size_t>(768) * kD);
+        std::memcpy(qkv.data(), wq.p + li * 256 * kD, sizeof(float) * 256 * kD);
+        for (int part = 0; part < 2; ++part) {
+          const float* up = (part == 0 ? wk.p : wv.p) + li * 256 * 64;     // [256, 64]
+          const float* dn = wc.p + li * 64 * kD;                            // [64, 256]
+          for (int o = 0; o < 256; ++o)
+            for (int in = 0; in < kD; ++in) {
+              double acc = 0.0;
+              for (int r = 0; r < 64; ++r) acc += static_cast<double>(up[o * 64 + r]) * dn[r * kD + in];
+              qkv[(static_cast<size_t>(256 + part * 256 + o)) * kD + in] = static_cast<float>(acc);
+            }
+        }
+        t.wqkv = ar->put_bf16(qkv);
+      }
       if (train) {
         t.wqct = ar->put_bf16(transposed(qc, kQC, kD));
         t.wkvt = ar->put_bf16(transposed(kv, kKV, 64));
@@ -872,7 +897,36 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       const float* lb = dev_ptr<float>(h, t.ln1b);
       add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
     }
-    if (local) {
+    if (w.folded_kv) {
+      // one projection for q, k, v (compressed-kv product folded at load), RoPE on q and k with the ABSOLUTE row index:
+      // RoPE logits depend only on position differences, so this equals the reference's per-window positions (attention.cuh)
+      __nv_bfloat16* qkv = ws.QKV16;
+      __nv_bfloat16* kvb = qkv + 256;    // k | v view, leading dimension 768
+      GemmArgs g = gemm_args(Mt, 768, kD);
+      g.out16 = qkv; g.ld16 = 768;
+      g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.rope_cols = 512; g.rows_per_window = kTP;
+      g.vt_out = nullptr; g.vt_col0 = 1 << 30;
+      if (!add_gemm(h, p, 128, GEMM_ROPE, a16, kD, t.wqkv, g)) return false;
+      p->steps.back().flops = 2.0 * Mt * (static_cast<double>(kQC) * kD + static_cast<double>(kKV) * 64);   // algorithmic (unfolded) count
+      CUtensorMap tq, tk, tv;
+      if (local) {
+        if (!make_tmap_3d(h, &tq, qkv, 256, kT, B, 768, kTP, 64, 128)) return false;
+        if (!make_tmap_3d(h, &tk, kvb, 256, kT, B, 768, kTP, 64, AL_NK)) return false;
+        if (!make_tmap_3d(h, &tv, kvb, 512, kT, B, 768, kTP, 64, AL_NK)) return false;
+        add_step(p, Meta{"attn_local_tc_kernel", 2.0 * B * ATT_HEADS * 31 * (2.0 * 16 * 16 * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
+          return launch_k(PF_ATTN, attn_local_tc_kernel, dim3(2, ATT_HEADS, B), dim3(AL_THREADS), AL_SMEM, st, tq, tk, tv, o16, kD, 256,
+                          static_cast<const DropParams*>(nullptr), 0u);
+        });
+      } else {
+        if (!make_tmap(h, &tq, qkv, Mt, 256, 768, 64, 128)) return false;
+        if (!make_tmap(h, &tk, kvb, Mt, 256, 768, 64, 256)) return false;
+        if (!make_tmap(h, &tv, kvb, Mt, 512, 768, 64, 256)) return false;
+        add_step(p, Meta{"attn_global_kernel", 2.0 * B * ATT_HEADS * (2.0 * kT * kT * 64), 2.0 * Mt * 256 * 4}, [=](cudaStream_t st) {
+          return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256,
+                          static_cast<float*>(nullptr), static_cast<const DropParams*>(nullptr), 0u);
+        });
+      }
+    } else if (local) {
       // q / k are rotated with their ABSOLUTE row index, exactly like the global layers: RoPE logits depend
       // only on position differences, so this equals the reference's per-window positions (attention.cuh)
       GemmArgs g = gemm_args(Mt, kQC, kD);
@@ -1133,6 +1187,7 @@ void a2m_destroy(A2mHandle* h) {
   if (h->pin_rope) cudaFreeHost(h->pin_rope);
   if (h->dev_rope_in) cudaFree(h->dev_rope_in);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->clip_stats) cudaFree(h->clip_stats);
   train_free(h);
   delete h;
 }
@@ -1328,6 +1383,36 @@ void a2m_host_free(void* p) {
 }
 
 int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }
+
+int64_t a2m_window_count(int64_t n_samples, double overlap_s) {
+  const int64_t window = A2M_WINDOW_SAMPLES;
+  const int64_t ov = static_cast<int64_t>(std::nearbyint(overlap_s * 16000.0));
+  const int64_t step = window - ov;
+  if (n_samples <= 0 || step <= 0) return 0;
+  return (n_samples - ov + step - 1) / step;   // ceil((N - overlap) / step), audio_to_midi_dataset.py:286
+}
+
+int a2m_prepare_windows(A2mHandle* h, const float* clip_dev, int64_t n_samples, double overlap_s, float* windows_dev,
+                        int64_t max_windows, void* stream_v) {
+  if (!h) return A2M_EINVAL;
+  const int64_t nw = a2m_window_count(n_samples, overlap_s);
+  if (!clip_dev || !windows_dev || nw <= 0 || nw > max_windows) { h->err = "bad prepare_windows arguments"; return A2M_EINVAL; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->clip_stats) CUDA_TRY(cudaMalloc(&h->clip_stats, sizeof(ClipStats)));
+  CUDA_TRY(cudaMemsetAsync(h->clip_stats, 0, sizeof(ClipStats), stream));
+  const long long n_total = 2ll * n_samples;
+  const int grid1 = static_cast<int>(std::min<long long>((n_total + 255) / 256, h->num_sms * 8ll));
+  clip_stats_kernel<<<grid1, 256, 0, stream>>>(clip_dev, n_total, static_cast<ClipStats*>(h->clip_stats));
+  CUDA_TRY(cudaGetLastError());
+  const int step = A2M_WINDOW_SAMPLES - static_cast<int>(std::nearbyint(overlap_s * 16000.0));
+  const long long total = nw * 2ll * A2M_WINDOW_SAMPLES;
+  const int grid2 = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16ll));
+  slice_normalize_kernel<<<grid2, 256, 0, stream>>>(clip_dev, n_samples, step, A2M_WINDOW_SAMPLES, static_cast<int>(nw),
+                                                    static_cast<const ClipStats*>(h->clip_stats), windows_dev);
+  CUDA_TRY(cudaGetLastError());
+  return A2M_OK;
+}
 
 int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t max_steps, A2mStepProfile* out) {
   if (!h || batch <= 0 || repeats <= 0) return A2M_EINVAL;

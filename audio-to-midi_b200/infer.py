@@ -44,3 +44,47 @@ def predict_and_stitch(model, state, samples, window_duration: float, overlap: f
     probs = np.concatenate(chunks).astype(np.float32)
     duration_per_frame = window_duration / probs.shape[1]
     return probs, modelutil.stitch_probs(probs, overlap, duration_per_frame), duration_per_frame
+
+
+def prepare_windows_device(model, audio_samples, overlap: float = 0.25, device=None):
+    """Device-side load_full_audio normalisation (python.rs:235-264) + load_and_slice_full_audio slicing
+    (audio_to_midi_dataset.py:277-294): raw decoded clip (2, N) fp32 (numpy or torch CUDA) -> torch CUDA (W, 2, 80000)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .model import _default_device
+    dev = _default_device() if device is None else device
+    eng = model._engine(dev)
+    tdev = torch.device(f"cuda:{dev}")
+    clip = torch.as_tensor(np.ascontiguousarray(audio_samples, np.float32) if isinstance(audio_samples, np.ndarray) else audio_samples)
+    clip = clip.to(tdev, torch.float32).contiguous()
+    if clip.ndim != 2 or clip.shape[0] != 2:
+        raise ValueError(f"audio must be (2, N), got {tuple(clip.shape)}")
+    n = int(clip.shape[1])
+    nw = int(eng.L.a2m_window_count(n, float(overlap)))
+    if nw <= 0:
+        raise ValueError("clip shorter than the overlap")
+    out = torch.empty((nw, 2, 80000), dtype=torch.float32, device=tdev)
+    stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
+    rc = eng.L.a2m_prepare_windows(eng.h, clip.data_ptr(), n, float(overlap), out.data_ptr(), nw, stream)
+    _lib.check(eng.h, rc, "a2m_prepare_windows")
+    return out
+
+
+def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 64, rank: int = 0, world_size: int = 1):
+    """Long-audio transcription (BASELINE config 5; infer.py:339 / audio_to_midi.py:38-53): normalise + slice on the
+    device, batched forward of this rank's block of windows, then (rank 0 / single process) stitch and eventize.
+    Returns (events, stitched_probs, probs_of_this_rank)."""
+    import torch
+    windows = prepare_windows_device(model, audio_samples, overlap)
+    lo, hi = shard_windows(windows.shape[0], world_size, rank)
+    rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
+    chunks = []
+    for i in range(lo, hi, max_batch):
+        _lg, p = model.predict(None, windows[i:min(i + max_batch, hi)], rope_freqs)
+        chunks.append(p)
+    probs = torch.cat(chunks).cpu().numpy().astype(np.float32) if chunks else np.zeros((0, 250, 90), np.float32)
+    if world_size > 1:
+        return None, None, probs          # the caller gathers the per-rank blocks in rank order, then stitches
+    stitched = modelutil.stitch_probs(probs, overlap, MODEL_AUDIO_LENGTH / probs.shape[1])
+    return modelutil.extract_events(stitched), stitched, probs

@@ -93,6 +93,17 @@ int a2m_collect_host(A2mHandle* h, int32_t slot);
 void* a2m_host_alloc(size_t bytes);
 void a2m_host_free(void* p);
 
+/* ---- the step before the path, on the device ------------------------------------------------ */
+/* Windows a clip of n_samples per channel is cut into: ceil((N - overlap) / (80000 - overlap)), overlap in SECONDS at
+ * 16 kHz (load_and_slice_full_audio, audio_to_midi_dataset.py:277-294). */
+int64_t a2m_window_count(int64_t n_samples, double overlap_s);
+/* clip_dev [2, n_samples] fp32 (raw decoded audio) -> windows_dev [a2m_window_count, 2, 80000] fp32: loudness
+ * normalisation of the whole clip exactly as load_full_audio does (python.rs:235-264: untouched if the peak is <= 0.05,
+ * else x / sqrt(mean square over both channels) in f64; rounded to f16) fused with the window slicing; the last window
+ * is zero padded.  The result is the `samples` argument of a2m_forward. */
+int a2m_prepare_windows(A2mHandle* h, const float* clip_dev, int64_t n_samples, double overlap_s, float* windows_dev,
+                        int64_t max_windows, void* stream);
+
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
 /* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between
