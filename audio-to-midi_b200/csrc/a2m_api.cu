@@ -1384,6 +1384,15 @@ void a2m_host_free(void* p) {
 
 int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }
 
+int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels_dev, int32_t batch, float* losses_dev, void* stream) {
+  if (!h) return A2M_EINVAL;
+  if (!logits_dev || !labels_dev || !losses_dev || batch <= 0) { h->err = "bad window_losses arguments"; return A2M_EINVAL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  bce_window_loss_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, labels_dev, losses_dev, A2M_FRAMES * A2M_VOCAB);
+  CUDA_TRY(cudaGetLastError());
+  return A2M_OK;
+}
+
 int64_t a2m_window_count(int64_t n_samples, double overlap_s) {
   const int64_t window = A2M_WINDOW_SAMPLES;
   const int64_t ov = static_cast<int64_t>(std::nearbyint(overlap_s * 16000.0));

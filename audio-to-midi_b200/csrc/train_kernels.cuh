@@ -53,6 +53,26 @@ __global__ void __launch_bounds__(256) bce_grad_kernel(const float* __restrict__
   }
 }
 
+// Per-window validation loss (train.py:99-102 testset_loss_function): out[b] = sum_{t,c} BCEWithLogits(z, y), one CTA per window.
+__global__ void __launch_bounds__(256) bce_window_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                              float* __restrict__ out, int per_window) {
+  const size_t base = static_cast<size_t>(blockIdx.x) * per_window;
+  float l = 0.f;
+  for (int i = threadIdx.x; i < per_window; i += 256) {
+    const float z = logits[base + i], y = labels[base + i];
+    l += fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)));
+  }
+  l = warp_sum(l);
+  __shared__ float sl[8];
+  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sl[i];
+    out[blockIdx.x] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ column sums (bias grads)
 // out[n] += sum_rows dY[row, n]   (bf16 [M, N], N % 8 == 0, N <= 1024)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, int ld, int M, int N,

@@ -88,3 +88,47 @@ def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int 
         return None, None, probs          # the caller gathers the per-rank blocks in rank order, then stitches
     stitched = modelutil.stitch_probs(probs, overlap, MODEL_AUDIO_LENGTH / probs.shape[1])
     return modelutil.extract_events(stitched), stitched, probs
+
+
+def detailed_event_loss(output_probs: np.ndarray, expected: np.ndarray) -> dict:
+    """infer.py:94-158 without the plot: eventize the probabilities, rasterise them back to frames and compare with the
+    annotation: full_diff, phantom / missed note mass, notes hit, hit_rate = hit / (hit + phantom + missed)."""
+    output_probs = np.ascontiguousarray(output_probs, np.float32)
+    predicted = modelutil.to_frame_events([modelutil.extract_events(output_probs)], output_probs.shape[0])[0]
+    expected = np.asarray(expected)[: predicted.shape[0]]
+    pp, pe = predicted > 0, expected > 0
+    phantom = float(np.sum(pp & ~pe))
+    missed = float(np.sum(expected[pe & ~pp]))
+    hit = float(np.sum(pp & pe))
+    denom = hit + phantom + missed
+    return {"full_diff": float(np.sum(np.abs(predicted - expected))), "phantom_notes_diff": phantom,
+            "missed_notes_diff": missed, "notes_hit": hit, "hit_rate": hit / denom if denom > 0 else 1.0}
+
+
+def compute_testset_loss(model, audio, events, rank: int = 0, world_size: int = 1, max_batch: int = 64):
+    """Validation pass of config 3 (compute_testset_loss_individual, train.py:86-209; infer.py:94-158): the annotated
+    windows are batch-partitioned over ranks (contiguous blocks, no collective); each rank runs the batched forward on
+    its block, the per-window BCE sum on the device (a2m_window_losses) and the event metrics on the host.
+    audio (N, 2, 80000), events (N, 250, 90), numpy.  Returns (lo, hi, losses[hi-lo], [detailed_event_loss dict])."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .model import _default_device
+    lo, hi = shard_windows(audio.shape[0], world_size, rank)
+    dev = _default_device()
+    eng = model._engine(dev)
+    tdev = torch.device(f"cuda:{dev}")
+    rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
+    losses, details = [], []
+    for i in range(lo, hi, max_batch):
+        j = min(i + max_batch, hi)
+        x = torch.as_tensor(np.ascontiguousarray(audio[i:j], np.float32)).to(tdev)
+        y = torch.as_tensor(np.ascontiguousarray(events[i:j], np.float32)).to(tdev)
+        logits, probs = model.predict(None, x, rope_freqs)
+        out = torch.empty(j - i, dtype=torch.float32, device=tdev)
+        stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
+        _lib.check(eng.h, eng.L.a2m_window_losses(eng.h, logits.data_ptr(), y.data_ptr(), j - i, out.data_ptr(), stream), "a2m_window_losses")
+        losses.append(out.cpu().numpy())
+        pr = probs.cpu().numpy()
+        details.extend(detailed_event_loss(pr[k], events[i + k]) for k in range(j - i))
+    return lo, hi, (np.concatenate(losses) if losses else np.zeros(0, np.float32)), details

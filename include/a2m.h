@@ -104,6 +104,10 @@ int64_t a2m_window_count(int64_t n_samples, double overlap_s);
 int a2m_prepare_windows(A2mHandle* h, const float* clip_dev, int64_t n_samples, double overlap_s, float* windows_dev,
                         int64_t max_windows, void* stream);
 
+/* Per-window validation loss (testset_loss_function, train.py:99-102): losses_dev[b] = sum_{t,c} BCEWithLogits(logits, labels)
+ * over the [250, 90] frame grid of window b.  logits_dev / labels_dev [batch, 250, 90] fp32. */
+int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels_dev, int32_t batch, float* losses_dev, void* stream);
+
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
 /* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between

@@ -54,3 +54,31 @@ def test_transcribe_clip_pipeline():
     fa = A.modelutil.to_frame_events([events], stitched.shape[0])[0]
     fb = A.modelutil.to_frame_events([ev_ref], stitched.shape[0])[0]
     assert np.mean((fa > 0) != (fb > 0)) < 0.05
+
+
+def test_validation_loss_and_hit_rate():
+    """Config 3 in miniature: per-window BCE sums and event metrics of a batch-partitioned annotated set vs the oracle."""
+    import torch.nn.functional as F
+    from audio_to_midi_b200 import infer as I
+    from gpu_util import make_model
+    from oracle import events as E
+    from oracle import model_torch as T
+    from oracle import synth
+    model, tree = make_model(99, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    audio, labels = synth.make_windows(6, 11, with_labels=True)
+    with torch.no_grad():
+        zref, pref = T.forward(T.to_torch(tree), torch.tensor(audio))
+        lref = F.binary_cross_entropy_with_logits(zref, torch.tensor(labels), reduction="none").sum(dim=(1, 2)).numpy()
+    got = {}
+    for rank in range(2):                       # two "ranks" in one process: the partition is what is tested
+        lo, hi, losses, details = I.compute_testset_loss(model, audio, labels, rank=rank, world_size=2, max_batch=2)
+        assert (lo, hi) == ((0, 3), (3, 6))[rank]
+        for k in range(hi - lo):
+            got[lo + k] = (losses[k], details[k])
+    for k in range(6):
+        assert abs(got[k][0] - lref[k]) < 5e-3 * abs(lref[k]) + 1.0, (k, got[k][0], lref[k])
+        ref = E.detailed_event_loss(pref[k].numpy(), labels[k])
+        d = got[k][1]
+        assert set(d) == set(ref)
+        # event metrics are threshold decisions: equal unless a probability sits within tolerance of a threshold
+        assert abs(d["hit_rate"] - ref["hit_rate"]) < 0.2
