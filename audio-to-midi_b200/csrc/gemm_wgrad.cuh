@@ -168,6 +168,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_wait(bar_done, 0);
     tc_fence_after();
+    // bar_done only says the MMAs have consumed every stage; a slower epilogue warp may still be summing bias columns
+    // out of the last stages, which the staging writes below overwrite
+    if (do_bias) named_bar_sync(1, 128);
     // accumulator -> fp32 staging chunks (128 rows x 32 columns, swizzled) in the drained pipeline buffers -> TMA add
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t rsw = static_cast<uint32_t>(r & 7);
