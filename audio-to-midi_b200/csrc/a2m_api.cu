@@ -22,6 +22,7 @@
 #include "audio_prep.cuh"
 #include "block_fused.cuh"
 #include "cnn_kernels.cuh"
+#include "ffn_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_wgrad.cuh"
@@ -134,6 +135,7 @@ struct TLayerW {
   size_t ln1w, ln1b, wqc, wkv, wo, ln2w, ln2b, w1, b1, w2, b2;
   size_t wqct, wkvt, wot, w1t, w2t;   // training: transposed bf16 copies (dgrad B operands)
   size_t wqkv;                        // inference: bf16 [768, 256] = Wq ; Wk Wc ; Wv Wc  (compressed-kv projection folded)
+  size_t w1f, b1f;                    // ffn_fused_kernel: FFN-1 rows in chunks of 64 "gelu" rows + their 64 "gate" rows
 };
 
 struct Weights {
@@ -319,6 +321,7 @@ bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows
 static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
+static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
 enum PdlFamily { PF_SMALL = 0, PF_LN = 1, PF_GEMM = 2, PF_FUSED = 3, PF_ATTN = 4 };
 
 template <class... KArgs, class... Args>
@@ -456,6 +459,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<64, G2_ROPE, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -670,6 +674,18 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
         }
       t.w1 = ar->put_bf16(w1p);
       t.b1 = ar->put_f32(b1p);
+      {
+        // the same pairing at 64-unit granularity for the fused FFN kernel (ffn_fused.cuh)
+        std::vector<float> w1f(static_cast<size_t>(2 * kFF) * kD), b1f(2 * kFF);
+        for (int c = 0; c < kFF / 64; ++c)
+          for (int r = 0; r < 128; ++r) {
+            const int src = (r < 64) ? c * 64 + r : kFF + c * 64 + (r - 64);
+            std::memcpy(&w1f[(static_cast<size_t>(c) * 128 + r) * kD], f1w.p + (li * 2 * kFF + src) * kD, sizeof(float) * kD);
+            b1f[c * 128 + r] = f1b.p[li * 2 * kFF + src];
+          }
+        t.w1f = ar->put_bf16(w1f);
+        t.b1f = ar->put_f32(b1f);
+      }
       t.w2 = ar->put_bf16(vec(f2w, li * kD * kFF, kD * kFF));
       t.b2 = ar->put_f32(vec(f2b, li * kD, kD));
       if (!train) {
@@ -973,24 +989,41 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
       if (!add_gemm(h, p, 128, GEMM_GENERIC, o16, kD, t.wo, g)) return false;
     }
-    {
+    if (g_fuse_ffn) {
+      // LN + FFN-1 + GLU + FFN-2 + residual in one launch (ffn_fused.cuh); x is updated in place
+      CUtensorMap tw1, tw2;
+      if (!make_tmap(h, &tw1, dev_ptr<__nv_bfloat16>(h, t.w1f), 2 * kFF, kD, kD, 64, 128)) return false;
+      if (!make_tmap(h, &tw2, dev_ptr<__nv_bfloat16>(h, t.w2), kD, kFF, kFF, 64, 256)) return false;
       const float* lw = dev_ptr<float>(h, t.ln2w);
       const float* lb = dev_ptr<float>(h, t.ln2b);
-      add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
-    }
-    {
-      GemmArgs g = gemm_args(Mt, 2 * kFF, kD);
-      g.bias = dev_ptr<float>(h, t.b1);
-      g.out16 = h16; g.ld16 = kFF;
-      if (!add_gemm(h, p, 256, GEMM_GLU, a16, kD, t.w1, g)) return false;
-    }
-    {
-      GemmArgs g = gemm_args(Mt, kD, kFF);
-      g.flags = GF_BIAS | GF_RESID | GF_OUT32;
-      g.bias = dev_ptr<float>(h, t.b2);
-      g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
+      const float* b1f = dev_ptr<float>(h, t.b1f);
+      const float* b2 = dev_ptr<float>(h, t.b2);
       const std::string label = "tl" + std::to_string(i / 2) + (local ? "_local" : "_global");
-      if (!add_gemm(h, p, 128, GEMM_GENERIC, h16, kFF, t.w2, g, label, xt, static_cast<size_t>(Mt) * kD)) return false;
+      add_step(p, Meta{"ffn_fused_kernel", 2.0 * Mt * (2.0 * kFF * kD + static_cast<double>(kD) * kFF), 8.0 * Mt * kD + 2.0 * 3 * kFF * kD},
+               [=](cudaStream_t st) {
+                 return launch_k(PF_FUSED, ffn_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(FF_THREADS), FF_SMEM, st, tw1, tw2, xt, Mt,
+                                 lw, lb, b1f, b2);
+               }, label, xt, static_cast<size_t>(Mt) * kD);
+    } else {
+      {
+        const float* lw = dev_ptr<float>(h, t.ln2w);
+        const float* lb = dev_ptr<float>(h, t.ln2b);
+        add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
+      }
+      {
+        GemmArgs g = gemm_args(Mt, 2 * kFF, kD);
+        g.bias = dev_ptr<float>(h, t.b1);
+        g.out16 = h16; g.ld16 = kFF;
+        if (!add_gemm(h, p, 256, GEMM_GLU, a16, kD, t.w1, g)) return false;
+      }
+      {
+        GemmArgs g = gemm_args(Mt, kD, kFF);
+        g.flags = GF_BIAS | GF_RESID | GF_OUT32;
+        g.bias = dev_ptr<float>(h, t.b2);
+        g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
+        const std::string label = "tl" + std::to_string(i / 2) + (local ? "_local" : "_global");
+        if (!add_gemm(h, p, 128, GEMM_GENERIC, h16, kFF, t.w2, g, label, xt, static_cast<size_t>(Mt) * kD)) return false;
+      }
     }
   }
   // ---- decoder norm (model.py:190); the decoder GEMM itself is launched per call (user output pointers)
@@ -1162,6 +1195,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_PDL")) h->use_pdl = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_PDL_MASK")) g_pdl_mask = static_cast<unsigned>(std::strtoul(e, nullptr, 0));
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   return A2M_OK;
 }
 
