@@ -23,6 +23,7 @@
 #include "block_fused.cuh"
 #include "cnn_kernels.cuh"
 #include "ffn_fused.cuh"
+#include "qkv_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_wgrad.cuh"
@@ -271,13 +272,14 @@ T* dev_ptr(const A2mHandle* h, size_t off) {
 
 // ------------------------------------------------------------------------------------------ tensor maps
 bool make_tmap_t(A2mHandle* h, CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t rows,
-                 uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
+                 uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows,
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_elems * static_cast<uint64_t>(esize)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = h->encode(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     std::snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u base=%p",
@@ -321,6 +323,7 @@ bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows
 static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
+static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
 enum PdlFamily { PF_SMALL = 0, PF_LN = 1, PF_GEMM = 2, PF_FUSED = 3, PF_ATTN = 4 };
 
@@ -460,6 +463,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -908,7 +912,8 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     const TLayerW& t = w.tl[i];
     float* xt = ws.Xt;
     __nv_bfloat16 *a16 = ws.A16, *qc = ws.QC16, *kv = ws.KV16, *vt = ws.Vt16, *o16 = ws.O16, *h16 = ws.H16;
-    {
+    const bool fused_qkv = w.folded_kv && g_fuse_qkv;
+    if (!fused_qkv) {
       const float* lw = dev_ptr<float>(h, t.ln1w);
       const float* lb = dev_ptr<float>(h, t.ln1b);
       add_step(p, Meta{"ln_rows_kernel", 0.0, 6.0 * Mt * kD}, [=](cudaStream_t st) { return launch_ln<256>(xt, Mt, Mt, Mt, lw, lb, a16, nullptr, st); });
@@ -922,7 +927,20 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       g.out16 = qkv; g.ld16 = 768;
       g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.rope_cols = 512; g.rows_per_window = kTP;
       g.vt_out = nullptr; g.vt_col0 = 1 << 30;
-      if (!add_gemm(h, p, 128, GEMM_ROPE, a16, kD, t.wqkv, g)) return false;
+      if (fused_qkv) {
+        // attention_norm + q|k|v projection + RoPE in one launch (qkv_fused.cuh)
+        CUtensorMap tw, to;
+        if (!make_tmap(h, &tw, dev_ptr<__nv_bfloat16>(h, t.wqkv), 768, kD, kD, 64, 256)) return false;
+        if (!make_tmap_t(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, Mt, 768, 768, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+        const float* lw = dev_ptr<float>(h, t.ln1w);
+        const float* lb = dev_ptr<float>(h, t.ln1b);
+        add_step(p, Meta{"qkv_fused_kernel", 0.0, 4.0 * Mt * kD + 2.0 * Mt * 768 + 2.0 * 768 * kD}, [=](cudaStream_t st) {
+          return launch_k(PF_FUSED, qkv_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(QF_THREADS), QF_SMEM, st, tw, to,
+                          static_cast<const float*>(xt), Mt, lw, lb, rope_cos, rope_sin, kTP);
+        });
+      } else if (!add_gemm(h, p, 128, GEMM_ROPE, a16, kD, t.wqkv, g)) {
+        return false;
+      }
       p->steps.back().flops = 2.0 * Mt * (static_cast<double>(kQC) * kD + static_cast<double>(kKV) * 64);   // algorithmic (unfolded) count
       CUtensorMap tq, tk, tv;
       if (local) {
@@ -1196,6 +1214,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_PDL_MASK")) g_pdl_mask = static_cast<unsigned>(std::strtoul(e, nullptr, 0));
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
   return A2M_OK;
 }
 
@@ -1492,6 +1511,17 @@ int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return std::min(n, max_steps);
+}
+
+// Debug: phase timeline of CTA 0 of the last ffn_fused_kernel launch (only in builds with -DA2M_FFN_TIMING; otherwise -1).
+int a2m_debug_read_timing(long long* out, int32_t n) {
+#ifdef A2M_FFN_TIMING
+  if (n > 128) n = 128;
+  return cudaMemcpyFromSymbol(out, g_ffn_timing, sizeof(long long) * n) == cudaSuccess ? n : -2;
+#else
+  (void)out; (void)n;
+  return -1;
+#endif
 }
 
 int a2m_set_use_graph(A2mHandle* h, int32_t enable) {

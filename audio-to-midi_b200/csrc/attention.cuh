@@ -38,7 +38,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int v_col0,
                    float* __restrict__ lse, const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AG_SQ;
   uint8_t* sP = smem;            // overwrites Q/K after the S MMAs have completed
@@ -238,7 +238,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* O, int ldo, int v_col0,
                      const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AL_SQ;
   uint8_t* sV = sK + AL_SK;

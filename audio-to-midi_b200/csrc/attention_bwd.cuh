@@ -39,7 +39,7 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        __nv_bfloat16* __restrict__ dQ, int lddq, __nv_bfloat16* __restrict__ dKV, int lddkv, int v_col0,
                        const DropParams* __restrict__ drop, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AGB_OPER;
   uint8_t* sV = sK + AGB_OPER;

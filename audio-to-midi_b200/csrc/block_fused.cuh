@@ -64,7 +64,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   static_assert(RM::G == 1, "one vector of channels per lane");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sA = smem;                               // A1, then A2 halves
   uint8_t* sW = smem + Cfg::A_BYTES;                // W1, then W2'
   float* sStage = reinterpret_cast<float*>(smem);   // aliases sA/sW after the last MMA has completed

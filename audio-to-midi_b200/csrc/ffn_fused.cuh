@@ -23,6 +23,15 @@
 
 namespace a2m {
 
+// Optional in-kernel timeline (build with -DA2M_FFN_TIMING): CTA 0 records clock64() at its phase boundaries into
+// g_ffn_timing, read back with a2m_debug_read_timing().  Compiled out of the product build.
+#ifdef A2M_FFN_TIMING
+__device__ long long g_ffn_timing[128];
+#define FF_STAMP(i) do { if (blockIdx.x == 0) g_ffn_timing[(i)] = clock64(); } while (0)
+#else
+#define FF_STAMP(i) do { } while (0)
+#endif
+
 constexpr int FF_CWARPS = 16;                    // compute warps: TMEM quadrant = warp & 3, column quarter = (warp - 2) >> 2
 constexpr int FF_CTHREADS = FF_CWARPS * 32;
 constexpr int FF_THREADS = 64 + FF_CTHREADS;
@@ -41,6 +50,42 @@ static_assert(FF_ROWS * FF_STAGE_STRIDE * 4 <= FF_MAIN_BYTES, "final staging re-
 constexpr int FF_AUX_BYTES = (2 * FF_F + FF_D) * 4 + 256;   // b1, b2, barriers, tmem slot
 constexpr size_t FF_SMEM = 1024 + FF_MAIN_BYTES + FF_AUX_BYTES;
 
+// LayerNorm of the 128-row tile, one warp per row (8 rows per compute warp, all their loads in flight at once), written
+// as the bf16 A operand: 4 k-blocks of [128 rows x 64 channels], 128B-swizzled.  Rows beyond M are treated as zeros.
+__device__ __forceinline__ void ff_layer_norm_to_operand(const float* __restrict__ X, int M, int tile0, const float* __restrict__ lnw,
+                                                         const float* __restrict__ lnb, uint8_t* sA, int cw, int lane) {
+  using RM = RowMap<FF_D>;
+  pdl_wait();   // x is produced by the previous kernel
+  if (threadIdx.x == 64) FF_STAMP(2);
+  float xv[8][RM::PER];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = cw * 8 + i;
+    if (tile0 + r < M) {
+      RM::load(X + static_cast<size_t>(tile0 + r) * FF_D, lane, xv[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < RM::PER; ++j) xv[i][j] = 0.f;
+    }
+  }
+  float lw[RM::PER], lb[RM::PER];
+  RM::load(lnw, lane, lw);
+  RM::load(lnb, lane, lb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = cw * 8 + i;
+    RM::layer_norm(xv[i], lw, lb);
+#pragma unroll
+    for (int g = 0; g < RM::G; ++g) {
+      const int col = RM::chan(lane, g);
+      uint2 q;
+      q.x = pack_bf16x2(xv[i][4 * g], xv[i][4 * g + 1]);
+      q.y = pack_bf16x2(xv[i][4 * g + 2], xv[i][4 * g + 3]);
+      *reinterpret_cast<uint2*>(sA + (col >> 6) * (FF_ROWS * 128) + sw128_offset(r, col & 63)) = q;
+    }
+  }
+}
+
 // tmW1: packed W1 [1024, 256] bf16, box {64, 128};  tmW2: W2 [256, 512] bf16, box {64, 256}.
 // X: fp32 [M, 256] residual stream, updated in place.  lnw / lnb: feed_forward_norm.  b1p: packed like W1's rows.
 __global__ void __launch_bounds__(FF_THREADS, 1)
@@ -49,7 +94,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                  const float* __restrict__ b2) {
   using RM = RowMap<FF_D>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sA = smem;
   uint8_t* sH = sA + FF_A_BYTES;
   uint8_t* sW = sH + 2 * FF_H_BYTES;
@@ -70,6 +115,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   const int tile0 = blockIdx.x * FF_ROWS;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) FF_STAMP(0);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -99,6 +145,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base;             // columns 0..255
   const uint32_t tmem_d1 = tmem_base + 256;       // two accumulators of 128 columns
+  if (threadIdx.x == 0) FF_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (constants: no pdl_wait needed)
@@ -130,10 +177,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       uint32_t s = 0, ph = 0;
       mbar_wait(bar_a, 0);
       tc_fence_after();
+      FF_STAMP(4);
       for (int c = 0; c <= FF_NCH; ++c) {
         if (c < FF_NCH) {
           mbar_wait(&bar_d1free[c & 1], ((c >> 1) & 1) ^ 1);
           tc_fence_after();
+          FF_STAMP(8 + c * 4);
           const uint32_t d1 = tmem_d1 + (c & 1) * 128;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -151,12 +200,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             if (++s == FF_NST) { s = 0; ph ^= 1; }
           }
           umma_commit(&bar_d1full[c & 1]);
+          FF_STAMP(8 + c * 4 + 1);
         }
         if (c >= 1) {
           const int cc = c - 1;
           mbar_wait(&bar_hfull[cc & 1], (cc >> 1) & 1);
+          FF_STAMP(8 + cc * 4 + 2);
           mbar_wait(&bar_full[s], ph);
           tc_fence_after();
+          FF_STAMP(8 + cc * 4 + 3);
           const uint64_t da = umma_desc_sw128(smem_u32(sH + (cc & 1) * FF_H_BYTES));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * FF_STAGE));
 #pragma unroll
@@ -177,48 +229,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const int row = quad * 32 + lane;
     const uint32_t t_row = static_cast<uint32_t>(quad * 32) << 16;
 
-    // (a) LayerNorm -> A operand.  8 rows per warp, all loads in flight at once.
-    {
-      float lw[RM::PER], lb[RM::PER];
-      RM::load(lnw, lane, lw);
-      RM::load(lnb, lane, lb);
-      pdl_wait();   // x is produced by the previous kernel
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        float xv[4][RM::PER];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = cw * 8 + pass * 4 + i;
-          if (tile0 + r < M) {
-            RM::load(X + static_cast<size_t>(tile0 + r) * FF_D, lane, xv[i]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < RM::PER; ++j) xv[i][j] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = cw * 8 + pass * 4 + i;
-          RM::layer_norm(xv[i], lw, lb);
-#pragma unroll
-          for (int g = 0; g < RM::G; ++g) {
-            const int col = RM::chan(lane, g);
-            uint2 q;
-            q.x = pack_bf16x2(xv[i][4 * g], xv[i][4 * g + 1]);
-            q.y = pack_bf16x2(xv[i][4 * g + 2], xv[i][4 * g + 3]);
-            *reinterpret_cast<uint2*>(sA + (col >> 6) * (FF_ROWS * 128) + sw128_offset(r, col & 63)) = q;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_a);
-    }
+    // (a) LayerNorm -> A operand
+    ff_layer_norm_to_operand(X, M, tile0, lnw, lnb, sA, cw, lane);
+    fence_proxy_async_smem();
+    mbar_arrive(bar_a);
+    if (threadIdx.x == 64) FF_STAMP(3);
 
     // (b) gate every hidden chunk: this thread owns 16 of the chunk's 64 hidden units of its row
 #pragma unroll 1
     for (int c = 0; c < FF_NCH; ++c) {
       mbar_wait(&bar_d1full[c & 1], (c >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) FF_STAMP(48 + c * 3);
       const uint32_t d1 = tmem_d1 + (c & 1) * 128 + t_row;
       uint32_t r1[16], r2[16];
       tmem_ld_x16(d1 + cq * 16, r1);
@@ -226,6 +248,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar_d1free[c & 1]);
+      if (threadIdx.x == 64) FF_STAMP(48 + c * 3 + 1);
       const float4* bg = reinterpret_cast<const float4*>(sB1 + c * 128 + cq * 16);   // gelu-row biases; gate rows 64 further
       uint32_t packed[8];
 #pragma unroll
@@ -246,11 +269,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
       fence_proxy_async_smem();
       mbar_arrive(&bar_hfull[c & 1]);
+      if (threadIdx.x == 64) FF_STAMP(48 + c * 3 + 2);
     }
 
     // (c) D2 + b2 -> staging (all operand bytes are dead once bar_done fires), then coalesced x += stage
     mbar_wait(bar_done, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) FF_STAMP(5);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col0 = cq * 64 + c * 32;
@@ -265,6 +290,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                         __uint_as_float(r[4 * q + 2]) + sB2[col0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + sB2[col0 + 4 * q + 3]);
     }
     named_bar_sync(1, FF_CTHREADS);
+    if (threadIdx.x == 64) FF_STAMP(6);
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       float xv[4][RM::PER];
@@ -289,6 +315,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FF_STAMP(7);
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();

@@ -46,7 +46,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * A_BYTES;
   uint8_t* sStage = sB + STAGES * B_BYTES;

@@ -72,7 +72,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   static_assert(STAGES * (A_BYTES + B_BYTES) >= (BN / 32) * 128 * 128, "epilogue staging re-uses the pipeline buffers");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * A_BYTES;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);

@@ -126,6 +126,9 @@ int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t 
 int a2m_set_use_graph(A2mHandle* h, int32_t enable);
 
 /* ---- test hooks (used by tests/ only) ------------------------------------------------------------ */
+/* Phase timeline (clock64 stamps of CTA 0) of the last ffn_fused_kernel launch; only in builds compiled with
+ * -DA2M_FFN_TIMING (tools/ffn_timeline.py), returns -1 in the product build. */
+int a2m_debug_read_timing(long long* out, int32_t n);
 /* Runs the forward up to and including the step labelled `label` ("stage0".."stage6", "cnn_out",
  * "tl<i>_local", "tl<i>_global") and copies the fp32 residual stream at that point to out_dev:
  * stage taps are [batch * L_stage, C_stage]; the others are [batch * 256, 256] (rows 250..255 padding). */
