@@ -24,6 +24,7 @@
 #include "cnn_kernels.cuh"
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
+#include "postattn_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_wgrad.cuh"
@@ -324,6 +325,7 @@ static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
+static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
 enum PdlFamily { PF_SMALL = 0, PF_LN = 1, PF_GEMM = 2, PF_FUSED = 3, PF_ATTN = 4 };
 
@@ -464,6 +466,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -1001,6 +1004,27 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256, static_cast<float*>(nullptr), static_cast<const DropParams*>(nullptr), 0u);
       });
     }
+    if (g_fuse_ffn && g_fuse_post) {
+      // output projection + residual + feed_forward_norm + FFN + residual in one launch (postattn_fused.cuh)
+      CUtensorMap to, two, tx, tw1, tw2;
+      if (!make_tmap(h, &to, o16, Mt, kD, kD, 64, 128)) return false;
+      if (!make_tmap(h, &two, dev_ptr<__nv_bfloat16>(h, t.wo), kD, 256, 256, 64, 256)) return false;
+      if (!make_tmap_f32(h, &tx, xt, Mt, kD, kD, 32, 128)) return false;
+      if (!make_tmap(h, &tw1, dev_ptr<__nv_bfloat16>(h, t.w1f), 2 * kFF, kD, kD, 64, 128)) return false;
+      if (!make_tmap(h, &tw2, dev_ptr<__nv_bfloat16>(h, t.w2), kD, kFF, kFF, 64, 256)) return false;
+      const float* lw = dev_ptr<float>(h, t.ln2w);
+      const float* lb = dev_ptr<float>(h, t.ln2b);
+      const float* b1f = dev_ptr<float>(h, t.b1f);
+      const float* b2 = dev_ptr<float>(h, t.b2);
+      const std::string label = "tl" + std::to_string(i / 2) + (local ? "_local" : "_global");
+      add_step(p, Meta{"postattn_fused_kernel", 2.0 * Mt * (static_cast<double>(kD) * 256 + 2.0 * kFF * kD + static_cast<double>(kD) * kFF),
+                       8.0 * Mt * kD + 2.0 * Mt * kD + 2.0 * (3 * kFF * kD + kD * 256)},
+               [=](cudaStream_t st) {
+                 return launch_k(PF_FUSED, postattn_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(FF_THREADS), PA_SMEM, st, to, two, tx,
+                                 tw1, tw2, xt, Mt, lw, lb, b1f, b2);
+               }, label, xt, static_cast<size_t>(Mt) * kD);
+      continue;
+    }
     {
       GemmArgs g = gemm_args(Mt, kD, 256);
       g.flags = GF_RESID | GF_OUT32;
@@ -1215,6 +1239,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   return A2M_OK;
 }
 

@@ -23,6 +23,12 @@
 
 namespace a2m {
 
+#ifdef A2M_FFN_TIMING
+#define FB_STAMP(i) do { if (blockIdx.x == 0 && C == 128) g_ffn_timing[(i)] = clock64(); } while (0)
+#else
+#define FB_STAMP(i) do { } while (0)
+#endif
+
 constexpr int FB_THREADS = 256;  // 8 warps: TMEM quadrant = warp & 3, column half = warp >> 2
 constexpr int FB_TOK = 128;
 
@@ -81,6 +87,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   const int tile0 = blockIdx.x * FB_TOK;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) FB_STAMP(112);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -105,6 +112,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     RM::load(params + 8 * C, lane, lw);
     RM::load(params + 9 * C, lane, lb);
     pdl_wait();  // weights / parameters above are constants; x is produced by the previous kernel
+    if (threadIdx.x == 0) FB_STAMP(113);
     constexpr int TPP = 8;                                   // tokens per pass
     constexpr int PASSES = FB_TOK / (FB_THREADS / 32) / TPP;  // 2
     const int col = RM::chan(lane, 0);
@@ -155,12 +163,14 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
     }
   }
+  if (threadIdx.x == 0) FB_STAMP(114);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + Cfg::D2_COL;
+  if (threadIdx.x == 0) FB_STAMP(115);
 
   // ---------------------------------------------------------------- phase 2: D1 = A1 . W1^T (NH halves of N = 128)
   if (threadIdx.x == 0) {
@@ -190,6 +200,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   __syncwarp();
   mbar_wait(bar_d1, 0);
   tc_fence_after();
+  if (threadIdx.x == 0) FB_STAMP(116);
   if (threadIdx.x == 0) {
     // the MMAs above have finished reading A1 and W1: stage gamma-scaled W2 into W1's bytes
     mbar_arrive_expect_tx(bar_w2, Cfg::W_BYTES);
@@ -225,9 +236,10 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        packed[c * 16 + j] = pack_bf16x2(gelu_tanh_f(__uint_as_float(r[2 * j]) + sB1[col0 + 2 * j]),
-                                         gelu_tanh_f(__uint_as_float(r[2 * j + 1]) + sB1[col0 + 2 * j + 1]));
+        packed[c * 16 + j] = pack_bf16x2(gelu_tanh_fast(__uint_as_float(r[2 * j]) + sB1[col0 + 2 * j]),
+                                         gelu_tanh_fast(__uint_as_float(r[2 * j + 1]) + sB1[col0 + 2 * j + 1]));
     }
+    if (threadIdx.x == 0) FB_STAMP(117 + hh * 2);
     if (hh > 0) {
       mbar_wait(&bar_m2[hh - 1], 0);   // the previous half's MMAs have finished reading the A2 bytes
       tc_fence_after();
@@ -248,6 +260,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       if (hh == 0) mbar_wait(bar_w2, 0);
       tc_fence_after();
+      FB_STAMP(118 + hh * 2);
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, C);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -265,6 +278,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   }
   mbar_wait(&bar_m2[NH - 1], 0);
   tc_fence_after();
+  if (threadIdx.x == 0) FB_STAMP(121);
 
   // ---------------------------------------------------------------- phase 5: stage (D2 + b2'), then out = stage + x
   {
@@ -285,6 +299,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FB_STAMP(122);
   {
     // coalesced residual add: each warp owns rows warp, warp+8, ...; lanes span the channels
     constexpr int NW = FB_THREADS / 32;
@@ -311,6 +326,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
     }
   }
+  if (threadIdx.x == 0) FB_STAMP(123);
   if constexpr (TAPE)
     if (threadIdx.x == 0) bulk_wait_all<0>();   // the tape stores must have landed before the grid may be considered complete
   if (warp == 1) {

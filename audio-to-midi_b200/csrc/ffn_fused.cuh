@@ -23,10 +23,7 @@
 
 namespace a2m {
 
-// Optional in-kernel timeline (build with -DA2M_FFN_TIMING): CTA 0 records clock64() at its phase boundaries into
-// g_ffn_timing, read back with a2m_debug_read_timing().  Compiled out of the product build.
 #ifdef A2M_FFN_TIMING
-__device__ long long g_ffn_timing[128];
 #define FF_STAMP(i) do { if (blockIdx.x == 0) g_ffn_timing[(i)] = clock64(); } while (0)
 #else
 #define FF_STAMP(i) do { } while (0)

@@ -9,6 +9,12 @@
 
 namespace a2m {
 
+// Optional in-kernel timelines (build with -DA2M_FFN_TIMING): CTA 0 of the instrumented kernels records clock64() at its
+// phase boundaries, read back with a2m_debug_read_timing() (tools/ffn_timeline.py).  Compiled out of the product build.
+#ifdef A2M_FFN_TIMING
+__device__ long long g_ffn_timing[128];
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

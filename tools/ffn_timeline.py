@@ -39,3 +39,8 @@ rel = lambda i: t[i] - t0
 print(f"qkv: setup done {rel(81)}  LN done {rel(82)}  MMA sees A {rel(83)}")
 for n in range(3):
     print(f"chunk {n}: MMA dfree {rel(84 + n * 6):6d}  weights ready kb0..3 {[rel(84 + n * 6 + 1 + k) for k in range(4)]} | epi dfull {rel(104 + 2 * n):6d} stored {rel(105 + 2 * n):6d}")
+
+t0 = t[112]
+rel = lambda i: t[i] - t0
+print(f"block_fused<128>: pdl_wait passed {rel(113)}  dwconv+LN done {rel(114)}  synced {rel(115)}  D1 ready {rel(116)}  "
+      f"gelu0 done {rel(117)} mma2_0 issue {rel(118)}  gelu1 done {rel(119)} mma2_1 issue {rel(120)}  D2 ready {rel(121)}  staged {rel(122)}  end {rel(123)}")
