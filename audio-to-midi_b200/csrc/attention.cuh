@@ -12,10 +12,23 @@
 
 namespace a2m {
 
+#ifdef A2M_FFN_TIMING
+#define AT_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_ffn_timing[(i)] = clock64(); } while (0)
+#else
+#define AT_STAMP(i) do { } while (0)
+#endif
+
 constexpr int ATT_T = 250;    // real frames per window
 constexpr int ATT_TP = 256;   // padded rows per window
 constexpr int ATT_HD = 64;    // head dim
 constexpr int ATT_HEADS = 4;
+
+// 2^x, flush-to-zero, one MUFU op (exp2f() adds a denormal-range rescale around it)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2_att(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -23,12 +36,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_att(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------ global
-constexpr int AG_THREADS = 128;
+constexpr int AG_THREADS = 256;           // 8 warps: TMEM quadrant = warp & 3, key half = warp >> 2
 constexpr int AG_SQ = 128 * 64 * 2;       // 16 KB
 constexpr int AG_SK = 256 * 64 * 2;       // 32 KB
 constexpr int AG_SV = 256 * 64 * 2;       // 32 KB: V[key][d], MN-major B operand of P.V
 constexpr int AG_SP = 4 * 128 * 64 * 2;   // 64 KB: 4 k-blocks of P [128 q x 64 keys]; ALIASES Q and K (dead after S)
-constexpr size_t AG_SMEM = 1024 + AG_SP + AG_SV + 128;   // ~98 KB -> two CTAs per SM
+constexpr size_t AG_SMEM = 1024 + AG_SP + AG_SV + 4 * 128 * 4 + 128;   // ~100 KB -> two CTAs per SM
 constexpr uint32_t AG_TMEM_COLS = 256;    // S: 256 columns; O re-uses columns 0..63 once S has been consumed
 
 // grid = (2 m-tiles, heads, B).  tmQ: Q  [B*256, ldq] box {64,128}; tmK: K [B*256, ldkv] box {64,256};
@@ -43,15 +56,19 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sK = sQ + AG_SQ;
   uint8_t* sP = smem;            // overwrites Q/K after the S MMAs have completed
   uint8_t* sV = smem + AG_SP;
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sV + AG_SV);
+  float* sMax = reinterpret_cast<float*>(sV + AG_SV);   // [2 key halves][128 rows]
+  float* sSum = sMax + 2 * 128;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sSum + 2 * 128);
   uint64_t* bar_s = bar_load + 1;
   uint64_t* bar_o = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
 
   const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, kh = warp >> 2;   // this thread: query row quad * 32 + lane, keys kh * 128 .. + 127
 
   pdl_launch_dependents();
+  AT_STAMP(64);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -69,6 +86,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_S = tmem_base;  // 256 columns
   const uint32_t tmem_O = tmem_base;  // 64 columns, written only after every thread has read S
   pdl_wait();
+  AT_STAMP(65);
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_load, AG_SQ + AG_SK + AG_SV);
@@ -77,6 +95,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_2d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, b * ATT_TP);
     mbar_wait(bar_load, 0);
     tc_fence_after();
+    AT_STAMP(66);
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
     const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
     const uint64_t dk = umma_desc_sw128(smem_u32(sK));
@@ -90,8 +109,9 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // ---- softmax over keys: one query row per thread (TMEM lane = row) ----
   mbar_wait(bar_s, 0);
   tc_fence_after();
-  const int row = warp * 32 + lane;  // query row inside the tile
-  const uint32_t t_row = (static_cast<uint32_t>(warp * 32) << 16);
+  AT_STAMP(67);
+  const int row = quad * 32 + lane;  // query row inside the tile
+  const uint32_t t_row = (static_cast<uint32_t>(quad * 32) << 16);
   // softmax((q / 8) . k): scale folded into the exponent; exp2 with log2(e) pre-multiplied
   const float kscale = 0.125f * 1.4426950408889634f;
   // training: dropout of the attention weights (model.py:254-255), after the normalisation
@@ -101,29 +121,36 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t dbase = ((static_cast<uint32_t>(b) * ATT_HEADS + h) * ATT_TP + mt * 128 + row) * ATT_TP;
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
+    const int key0 = kh * 128 + c * 32;
     uint32_t r[32];
-    tmem_ld_x32(tmem_S + t_row + c * 32, r);
+    tmem_ld_x32(tmem_S + t_row + key0, r);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < ATT_T) mx = fmaxf(mx, __uint_as_float(r[j]));
+      if (key0 + j < ATT_T) mx = fmaxf(mx, __uint_as_float(r[j]));
   }
+  // the two threads of a row exchange their half-row maxima (keys 0..127 always hold real keys: never -inf)
+  sMax[kh * 128 + row] = mx;
+  __syncthreads();
+  mx = fmaxf(sMax[row], sMax[128 + row]);
+  const float mxk = mx * kscale;
   float sum = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
+    const int key0 = kh * 128 + c * 32;
     uint32_t r[32];
-    tmem_ld_x32(tmem_S + t_row + c * 32, r);
+    tmem_ld_x32(tmem_S + t_row + key0, r);
     tmem_ld_wait();
     float p[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float e = exp2f((__uint_as_float(r[j]) - mx) * kscale);
-      p[j] = (c * 32 + j < ATT_T) ? e : 0.f;  // padded keys 250..255 are masked out
+      const float e = ex2_ftz(fmaf(__uint_as_float(r[j]), kscale, -mxk));
+      p[j] = (key0 + j < ATT_T) ? e : 0.f;  // padded keys 250..255 are masked out
     }
     // P (bf16) into the K-major 128B-swizzled A-operand layout: k-block = key / 64
-    uint8_t* pb = sP + (c >> 1) * (128 * 64 * 2);
-    const int colb = (c & 1) * 32;
+    uint8_t* pb = sP + (key0 >> 6) * (128 * 64 * 2);
+    const int colb = key0 & 63;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(p[8 * q], p[8 * q + 1]);
@@ -134,7 +161,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       sum += __low2float(h0) + __high2float(h0) + __low2float(h1) + __high2float(h1) + __low2float(h2) +
              __high2float(h2) + __low2float(h3) + __high2float(h3);
       if (dthresh != 0u) {   // the P.V operand is the dropped-out weights; the normaliser above is not
-        const uint32_t i0 = dbase + c * 32 + 8 * q;
+        const uint32_t i0 = dbase + key0 + 8 * q;
         h0 = __floats2bfloat162_rn(p[8 * q] * drop_mul(dkey, i0, dthresh, dinv), p[8 * q + 1] * drop_mul(dkey, i0 + 1, dthresh, dinv));
         h1 = __floats2bfloat162_rn(p[8 * q + 2] * drop_mul(dkey, i0 + 2, dthresh, dinv), p[8 * q + 3] * drop_mul(dkey, i0 + 3, dthresh, dinv));
         h2 = __floats2bfloat162_rn(p[8 * q + 4] * drop_mul(dkey, i0 + 4, dthresh, dinv), p[8 * q + 5] * drop_mul(dkey, i0 + 5, dthresh, dinv));
@@ -148,6 +175,8 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       *reinterpret_cast<uint4*>(pb + sw128_offset(row, colb + 8 * q)) = v;
     }
   }
+  sSum[kh * 128 + row] = sum;
+  AT_STAMP(68);
   fence_proxy_async_smem();  // generic-proxy smem writes -> visible to tcgen05.mma
   tc_fence_before();
   __syncthreads();
@@ -170,14 +199,16 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   mbar_wait(bar_o, 0);
   tc_fence_after();
-  const float inv = __fdividef(1.0f, sum);
+  AT_STAMP(69);
+  const float inv = __fdividef(1.0f, sSum[row] + sSum[128 + row]);
   // training: natural-log softmax denominator per (row, head), P = exp(s / 8 - lse)  (attention_bwd.cuh)
-  if (lse != nullptr) lse[static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ATT_HEADS + h] = mx * 0.125f + __logf(sum);
-  __nv_bfloat16* dst = O + static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ldo + h * ATT_HD;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  if (lse != nullptr && kh == 0)
+    lse[static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ATT_HEADS + h] = mx * 0.125f + __logf(sSum[row] + sSum[128 + row]);
+  // head-dim half kh of this row: 32 bf16 = 64 bytes
+  __nv_bfloat16* dst = O + static_cast<size_t>(b * ATT_TP + mt * 128 + row) * ldo + h * ATT_HD + kh * 32;
+  {
     uint32_t r[32];
-    tmem_ld_x32(tmem_O + t_row + c * 32, r);
+    tmem_ld_x32(tmem_O + t_row + kh * 32, r);
     tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -190,9 +221,10 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       v.y = *reinterpret_cast<uint32_t*>(&h1);
       v.z = *reinterpret_cast<uint32_t*>(&h2);
       v.w = *reinterpret_cast<uint32_t*>(&h3);
-      reinterpret_cast<uint4*>(dst + c * 32)[q] = v;
+      reinterpret_cast<uint4*>(dst)[q] = v;
     }
   }
+  AT_STAMP(70);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -252,6 +284,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
+  AT_STAMP(72);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -269,6 +302,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 192;
   pdl_wait();
+  AT_STAMP(73);
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_load, AL_SQ + AL_SK + AL_SV);
@@ -278,6 +312,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_load_3d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, mt * 128 - 8 - 3, b);
     mbar_wait(bar_load, 0);
     tc_fence_after();
+    AT_STAMP(74);
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, AL_NK);
     const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
     const uint64_t dk = umma_desc_sw128(smem_u32(sK));
@@ -290,6 +325,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  AT_STAMP(75);
   const int row = warp * 32 + lane;        // query row in the tile
   const int j = mt * 128 + row;            // padded row == output row
   const uint32_t t_row = static_cast<uint32_t>(warp * 32) << 16;
@@ -313,48 +349,86 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const float kscale = 0.125f * 1.4426950408889634f;   // (q / sqrt(64)) . k, exp2 domain
   float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < 48; ++c) {
-    const bool in_a = static_cast<unsigned>(c - off) < 16u;
-    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
-    if (in_a) ma = fmaxf(ma, s[c]);
-    if (in_b) mb = fmaxf(mb, s[c]);
-  }
-  float suma = 0.f, sumb = 0.f;
+  for (int k = 0; k < 6; ++k) {   // per 8-column chunk, then the two chunks of each window
+    float cm = s[8 * k];
 #pragma unroll
-  for (int c = 0; c < 48; ++c) {
-    const bool in_a = static_cast<unsigned>(c - off) < 16u;
-    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
-    if (in_a) suma += exp2f((s[c] - ma) * kscale);
-    if (in_b) sumb += exp2f((s[c] - mb) * kscale);
+    for (int i = 1; i < 8; ++i) cm = fmaxf(cm, s[8 * k + i]);
+    const int rk = k - (off >> 3);
+    if (rk == 0 || rk == 1) ma = fmaxf(ma, cm);
+    if (rk == 1 || rk == 2) mb = fmaxf(mb, cm);
   }
   const float wn = (has_a && has_b) ? 0.5f : 1.0f;      // divide by the number of covering windows
-  const float ia = has_a ? __fdividef(wn, suma) : 0.f;
-  const float ib = has_b ? __fdividef(wn, sumb) : 0.f;
-  // training: each window's attention weights are dropped out independently (model.py:443 -> 254-255);
-  // element index ((b, h, window, row in window), key in window)
   const uint32_t dthresh = drop ? drop->thresh : 0u;
-  const float dinv = drop ? drop->inv_keep : 1.f;
-  const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
-  const int wa = (j >> 3) - 1, wb = j >> 3;
-  const uint32_t bh = static_cast<uint32_t>(b) * ATT_HEADS + h;
-  const uint32_t da0 = ((bh * 31u + static_cast<uint32_t>(wa)) * 16u + static_cast<uint32_t>(j - 8 * wa)) * 16u;
-  const uint32_t db0 = ((bh * 31u + static_cast<uint32_t>(wb)) * 16u + static_cast<uint32_t>(j - 8 * wb)) * 16u;
+  if (dthresh == 0u) {
+    // Inference path.  Window A covers the 8-column chunks off/8 and off/8 + 1 of the slab, window B off/8 + 1 and
+    // off/8 + 2: every element is exponentiated once per window with the exponent clamped to <= 0 (in-band elements
+    // never exceed their window's maximum, out-of-band ones are multiplied by a zero chunk weight afterwards), so the
+    // per-lane band position only enters through six per-chunk weights instead of per-element predicates.
+    const int k0 = off >> 3;
+    const float mak = ma * kscale, mbk = mb * kscale;
+    float suma = 0.f, sumb = 0.f;
+    float ea[48];
 #pragma unroll
-  for (int c = 0; c < 48; ++c) {
-    const bool in_a = static_cast<unsigned>(c - off) < 16u;
-    const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
-    float p = 0.f;
-    if (in_a) {
-      float pa = exp2f((s[c] - ma) * kscale) * ia;
-      if (dthresh != 0u) pa *= drop_mul(dkey, da0 + static_cast<uint32_t>(c - off), dthresh, dinv);
-      p += pa;
+    for (int k = 0; k < 6; ++k) {
+      const bool ua = (k == k0) || (k == k0 + 1), ub = (k == k0 + 1) || (k == k0 + 2);
+      float ca = 0.f, cb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = s[8 * k + i] * kscale;
+        const float a = ex2_ftz(fminf(x - mak, 0.f)), bb = ex2_ftz(fminf(x - mbk, 0.f));
+        ea[8 * k + i] = a;
+        s[8 * k + i] = bb;
+        ca += a;
+        cb += bb;
+      }
+      if (ua) suma += ca;
+      if (ub) sumb += cb;
     }
-    if (in_b) {
-      float pb = exp2f((s[c] - mb) * kscale) * ib;
-      if (dthresh != 0u) pb *= drop_mul(dkey, db0 + static_cast<uint32_t>(c - off - 8), dthresh, dinv);
-      p += pb;
+    const float ia = has_a ? __fdividef(wn, suma) : 0.f;
+    const float ib = has_b ? __fdividef(wn, sumb) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float wa_k = ((k == k0) || (k == k0 + 1)) ? ia : 0.f;
+      const float wb_k = ((k == k0 + 1) || (k == k0 + 2)) ? ib : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[8 * k + i] = fmaf(ea[8 * k + i], wa_k, s[8 * k + i] * wb_k);
     }
-    s[c] = p;
+  } else {
+    float suma = 0.f, sumb = 0.f;
+  #pragma unroll
+    for (int c = 0; c < 48; ++c) {
+      const bool in_a = static_cast<unsigned>(c - off) < 16u;
+      const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
+      if (in_a) suma += exp2f((s[c] - ma) * kscale);
+      if (in_b) sumb += exp2f((s[c] - mb) * kscale);
+    }
+    const float ia = has_a ? __fdividef(wn, suma) : 0.f;
+    const float ib = has_b ? __fdividef(wn, sumb) : 0.f;
+    // training: each window's attention weights are dropped out independently (model.py:443 -> 254-255);
+    // element index ((b, h, window, row in window), key in window)
+    const float dinv = drop ? drop->inv_keep : 1.f;
+    const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
+    const int wa = (j >> 3) - 1, wb = j >> 3;
+    const uint32_t bh = static_cast<uint32_t>(b) * ATT_HEADS + h;
+    const uint32_t da0 = ((bh * 31u + static_cast<uint32_t>(wa)) * 16u + static_cast<uint32_t>(j - 8 * wa)) * 16u;
+    const uint32_t db0 = ((bh * 31u + static_cast<uint32_t>(wb)) * 16u + static_cast<uint32_t>(j - 8 * wb)) * 16u;
+  #pragma unroll
+    for (int c = 0; c < 48; ++c) {
+      const bool in_a = static_cast<unsigned>(c - off) < 16u;
+      const bool in_b = static_cast<unsigned>(c - off - 8) < 16u;
+      float p = 0.f;
+      if (in_a) {
+        float pa = exp2f((s[c] - ma) * kscale) * ia;
+        if (dthresh != 0u) pa *= drop_mul(dkey, da0 + static_cast<uint32_t>(c - off), dthresh, dinv);
+        p += pa;
+      }
+      if (in_b) {
+        float pb = exp2f((s[c] - mb) * kscale) * ib;
+        if (dthresh != 0u) pb *= drop_mul(dkey, db0 + static_cast<uint32_t>(c - off - 8), dthresh, dinv);
+        p += pb;
+      }
+      s[c] = p;
+    }
   }
   // P row (144 keys = 18 chunks of 8) into the swizzled K-major layout; this warp's slab is chunks 4w .. 4w+5
   {
@@ -375,6 +449,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       *reinterpret_cast<uint4*>(sP + (cc >> 3) * (128 * 128) + sw128_offset(row, (cc & 7) * 8)) = v;
     }
   }
+  AT_STAMP(76);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -394,6 +469,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   mbar_wait(bar_o, 0);
   tc_fence_after();
+  AT_STAMP(77);
   __nv_bfloat16* dst = O + static_cast<size_t>(b * ATT_TP + j) * ldo + h * ATT_HD;
   const bool real = j < ATT_T;   // rows 250..255 are written as zeros (kept finite for the padded projections)
 #pragma unroll
@@ -411,6 +487,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       reinterpret_cast<uint4*>(dst + c * 32)[q] = v;
     }
   }
+  AT_STAMP(78);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -44,3 +44,7 @@ t0 = t[112]
 rel = lambda i: t[i] - t0
 print(f"block_fused<128>: pdl_wait passed {rel(113)}  dwconv+LN done {rel(114)}  synced {rel(115)}  D1 ready {rel(116)}  "
       f"gelu0 done {rel(117)} mma2_0 issue {rel(118)}  gelu1 done {rel(119)} mma2_1 issue {rel(120)}  D2 ready {rel(121)}  staged {rel(122)}  end {rel(123)}")
+
+for name, b in (("attn_global", 64), ("attn_local", 72)):
+    t0 = t[b]
+    print(f"{name}: pdl_wait passed {t[b+1]-t0}  loaded {t[b+2]-t0}  S ready {t[b+3]-t0}  softmax done {t[b+4]-t0}  O ready {t[b+5]-t0}  stored {t[b+6]-t0}")
