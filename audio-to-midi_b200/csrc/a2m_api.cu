@@ -21,6 +21,7 @@
 #include "attention.cuh"
 #include "audio_prep.cuh"
 #include "block_fused.cuh"
+#include "block_mid.cuh"
 #include "cnn_kernels.cuh"
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
@@ -143,6 +144,7 @@ struct TLayerW {
 struct Weights {
   StemParams stem;
   size_t small_block[4][3];
+  size_t mid_p[4][3], mid_w[4][3];   // block_mid_kernel (stages 1-3): fp32 parameter image, bf16 pre-swizzled W1 | gamma*W2 tiles
   size_t small_down[5];           // index = output stage 1..4
   BigBlockW big_block[kStages][21];
   BigDownW big_down[kStages];     // stages 5, 6
@@ -324,6 +326,7 @@ bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows
 static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
+static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
@@ -439,7 +442,7 @@ cudaError_t set_smem(K kernel, size_t bytes) {
 template <int C>
 size_t small_block_smem() {
   constexpr int RS = (C == 4) ? 4 : C + 4;
-  return (((SmallBlockLayout<C>::TOTAL + 3) & ~3) + (SB_TOK + 6) * RS) * sizeof(float);
+  return (((SmallBlockLayout<C>::TOTAL + 3) & ~3) + (SB_TOK * small_block_tpt<C>() + 6) * RS) * sizeof(float);
 }
 
 cudaError_t configure_kernels() {
@@ -473,13 +476,17 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(block_fused_kernel<64, true>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, true>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
+  if ((e = set_smem(block_mid_kernel<8>, MidBlockCfg<8>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_mid_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_mid_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 template <int C>
 cudaError_t launch_small_block(const float* in, float* out, int L, int M, const float* params, cudaStream_t s) {
-  return launch_k(PF_SMALL, block_small_kernel<C>, dim3((M + SB_TOK - 1) / SB_TOK), dim3(SB_TOK), small_block_smem<C>(), s, in, out, L,
+  constexpr int tile = SB_TOK * small_block_tpt<C>();
+  return launch_k(PF_SMALL, block_small_kernel<C>, dim3((M + tile - 1) / tile), dim3(SB_TOK), small_block_smem<C>(), s, in, out, L,
                   M, params);
 }
 template <int CIN>
@@ -605,6 +612,27 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
           for (int hh = 0; hh < H; ++hh) w2t[static_cast<size_t>(hh) * C + c] = w2.p[static_cast<size_t>(c) * H + hh];
         app(w2t); app(vec(b2)); app(vec(gm));
         w->small_block[s][j] = ar->put_f32(img);
+        if (s >= 1) {
+          // tensor-core variant (block_mid.cuh): dw | dwb | lnw | lnb | b1 | gamma*b2, and the two weight tiles laid out as
+          // 128B-swizzled K-major rows of 64 bf16 (zero padded), exactly as they sit in shared memory
+          const float kNone = std::nanf("");
+          std::vector<float> pimg, pmul;
+          auto appm = [&](const std::vector<float>& v) { pimg.insert(pimg.end(), v.begin(), v.end()); pmul.insert(pmul.end(), v.size(), kNone); };
+          appm(dwt); appm(vec(dwb)); appm(vec(lw)); appm(vec(lb)); appm(vec(b1));
+          for (int c = 0; c < C; ++c) { pimg.push_back(b2.p[c]); pmul.push_back(gm.p[c]); }
+          w->mid_p[s][j] = ar->put(pimg, false, pmul);
+          const int N1 = H, N2 = C < 16 ? 16 : C;
+          std::vector<float> wimg(static_cast<size_t>(N1 + N2) * 64, 0.f), wmul(static_cast<size_t>(N1 + N2) * 64, kNone);
+          auto swz = [](int n, int k) { return static_cast<size_t>(n) * 64 + (((k >> 3) ^ (n & 7)) << 3) + (k & 7); };
+          for (int n = 0; n < H; ++n)
+            for (int k = 0; k < C; ++k) wimg[swz(n, k)] = w1.p[static_cast<size_t>(n) * C + k];
+          for (int n = 0; n < C; ++n)
+            for (int k = 0; k < H; ++k) {
+              wimg[static_cast<size_t>(N1) * 64 + swz(n, k)] = w2.p[static_cast<size_t>(n) * H + k];
+              wmul[static_cast<size_t>(N1) * 64 + swz(n, k)] = gm.p[n];
+            }
+          w->mid_w[s][j] = ar->put(wimg, true, wmul);
+        }
       } else {
         BigBlockW& bw = w->big_block[s][j];
         std::vector<float> img;
@@ -843,6 +871,18 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         const float* prm = dev_ptr<float>(h, w.small_block[s][j]);
         const size_t te = static_cast<size_t>(M) * C;
         const Meta mb{"block_small_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
+        if (s >= 2 && g_mid_tc) {   // C = 8 stays on the CUDA cores: per-tile set-up outweighs its 128 x 16 x 16 products
+          // pointwise convolutions on tcgen05 (block_mid.cuh)
+          const float* mp = dev_ptr<float>(h, w.mid_p[s][j]);
+          const uint4* mw = dev_ptr<uint4>(h, w.mid_w[s][j]);
+          const Meta mm{"block_mid_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
+          const dim3 grid((M + BM_TOK - 1) / BM_TOK);
+          switch (s) {
+            case 1: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<8>, grid, dim3(BM_TOK), MidBlockCfg<8>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
+            case 2: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<16>, grid, dim3(BM_TOK), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
+            default: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<32>, grid, dim3(BM_TOK), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
+          }
+        } else
         switch (s) {
           case 0: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te); break;
           case 1: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te); break;
@@ -1240,6 +1280,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
   return A2M_OK;
 }
 

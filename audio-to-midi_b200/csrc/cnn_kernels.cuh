@@ -26,9 +26,15 @@ namespace a2m {
 
 constexpr float kLnEps = 1e-5f;
 
+// jax.nn.gelu (tanh form) through the hardware tanh: one MUFU op and 5 FMA-pipe ops per element.  The narrow stages spend
+// most of their instructions here (2C activations per token, every stage), so the ex2 + rcp form cost 2x the issue slots.
 __device__ __forceinline__ float gelu_tanh_cc(float x) {
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+  const float x2 = x * x;
+  const float u = x * fmaf(0.0356774081f, x2, 0.7978845608f);   // sqrt(2/pi) (x + 0.044715 x^3)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -99,34 +105,54 @@ struct SmallBlockLayout {
   static constexpr int TOTAL = GAMMA + C;
 };
 
-constexpr int SB_TOK = 128;  // tokens (= threads) per CTA
+constexpr int SB_TOK = 128;  // threads per CTA
+// Tokens per thread (a CTA covers SB_TOK * small_block_tpt<C>() consecutive tokens).
+template <int C>
+__host__ __device__ constexpr int small_block_tpt() { return 1; }   // measured: 8 / 4 tokens per thread at C = 4 / 8 were 30 % SLOWER (fewer resident warps)
 
 template <int C>
 __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, float* Xout,
                                                              int L, int M, const float* __restrict__ params) {
   using Lay = SmallBlockLayout<C>;
   constexpr int H = Lay::H;
+  constexpr int TPT = small_block_tpt<C>();
+  constexpr int TILE = SB_TOK * TPT;
   constexpr int RS = (C == 4) ? 4 : C + 4;  // padded row stride (floats): conflict-free 128-bit row reads
   extern __shared__ __align__(16) float smem_f[];
   float* sp = smem_f;                          // parameters
-  float* sx = smem_f + ((Lay::TOTAL + 3) & ~3);  // (SB_TOK + 6) rows of input
+  float* sx = smem_f + ((Lay::TOTAL + 3) & ~3);  // (TILE + 6) rows of input
 
   pdl_launch_dependents();
   for (int i = threadIdx.x; i < Lay::TOTAL; i += SB_TOK) sp[i] = __ldg(params + i);
   pdl_wait();  // parameters are constants; activations of the previous kernel are read below
-  const int tile0 = blockIdx.x * SB_TOK;
-  // rows tile0-3 .. tile0+SB_TOK+2, zero outside [0, M)
+  const int tile0 = blockIdx.x * TILE;
+  // rows tile0-3 .. tile0+TILE+2, zero outside [0, M): every load of a thread is issued before its first store
   constexpr int V = C / 4;
-  for (int i = threadIdx.x; i < (SB_TOK + 6) * V; i += SB_TOK) {
-    const int r = i / V, q = i - r * V;
-    const int g = tile0 - 3 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g >= 0 && g < M) v = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];
-    reinterpret_cast<float4*>(sx + r * RS)[q] = v;
+  {
+    constexpr int NV = (TILE + 6) * V;
+    constexpr int PER = (NV + SB_TOK - 1) / SB_TOK;
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * SB_TOK;
+      const int r = i / V, q = i - r * V;
+      const int g = tile0 - 3 + r;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < NV && g >= 0 && g < M) v[k] = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];   // plain load: never hoisted above pdl_wait
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * SB_TOK;
+      const int r = i / V, q = i - r * V;
+      if (i < NV) reinterpret_cast<float4*>(sx + r * RS)[q] = v[k];
+    }
   }
   __syncthreads();
 
-  const int tok = tile0 + threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < TPT; ++it) {
+  const int trow = it * SB_TOK + threadIdx.x;   // row of this token inside the tile
+  const int tok = tile0 + trow;
   if (tok >= M) return;
   const int l = tok % L;
 
@@ -138,7 +164,7 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
   for (int t = 0; t < 7; ++t) {
     const int ll = l + t - 3;
     if (ll >= 0 && ll < L) {
-      const float* row = sx + (threadIdx.x + t) * RS;
+      const float* row = sx + (trow + t) * RS;
 #pragma unroll
       for (int q = 0; q < V; ++q) {
         const float4 xv = reinterpret_cast<const float4*>(row)[q];
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
     }
   }
   // layer scale + residual.  Out of place: neighbouring CTAs read rows of this tile as their halo.
-  const float* xr = sx + (threadIdx.x + 3) * RS;
+  const float* xr = sx + (trow + 3) * RS;
   float* dst = Xout + static_cast<size_t>(tok) * C;
 #pragma unroll
   for (int q = 0; q < V; ++q) {
@@ -200,6 +226,7 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
     r.z = fmaf(sp[Lay::GAMMA + 4 * q + 2], o[4 * q + 2], xr[4 * q + 2]);
     r.w = fmaf(sp[Lay::GAMMA + 4 * q + 3], o[4 * q + 3], xr[4 * q + 3]);
     reinterpret_cast<float4*>(dst)[q] = r;
+  }
   }
 }
 

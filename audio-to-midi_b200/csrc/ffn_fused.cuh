@@ -49,7 +49,7 @@ constexpr size_t FF_SMEM = 1024 + FF_MAIN_BYTES + FF_AUX_BYTES;
 
 // LayerNorm of the 128-row tile, one warp per row (8 rows per compute warp, all their loads in flight at once), written
 // as the bf16 A operand: 4 k-blocks of [128 rows x 64 channels], 128B-swizzled.  Rows beyond M are treated as zeros.
-__device__ __forceinline__ void ff_layer_norm_to_operand(const float* __restrict__ X, int M, int tile0, const float* __restrict__ lnw,
+__device__ __forceinline__ void ff_layer_norm_to_operand(const float* X, int M, int tile0, const float* __restrict__ lnw,
                                                          const float* __restrict__ lnb, uint8_t* sA, int cw, int lane) {
   using RM = RowMap<FF_D>;
   pdl_wait();   // x is produced by the previous kernel

@@ -30,7 +30,7 @@ constexpr size_t QF_SMEM = 1024 + QF_MAIN_BYTES + QF_OUT_BYTES + QF_ROPE_BYTES +
 // tmW: Wqkv [768, 256] bf16, box {64, 256}.  tmO: out [M, 768] bf16, box {32, 128}, 64B swizzle.  X: fp32 [M, 256].
 // rope_cos / rope_sin: [>= 256, 32].
 __global__ void __launch_bounds__(QF_THREADS, 1)
-qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ X, int M,
+qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const float* X, int M,
                  const float* __restrict__ lnw, const float* __restrict__ lnb, const float* __restrict__ rope_cos,
                  const float* __restrict__ rope_sin, int rows_per_window) {
   using RM = RowMap<FF_D>;

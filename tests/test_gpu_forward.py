@@ -1,7 +1,7 @@
 """Forward parity of the CUDA path against the fp64 oracle, through the C ABI.
 
-Tolerances (stated per SURVEY.md §7 "fp16 vs bf16"): stages 0-3 are fp32 CUDA-core kernels (1e-4);
-from stage 4 on every contraction has bf16 operands with fp32 accumulation, the residual stream is fp32.
+Tolerances (stated per SURVEY.md §7 "fp16 vs bf16"): stage 0 is an fp32 CUDA-core kernel with the hardware tanh in its GELU (1e-3); from stage 1 on
+every pointwise contraction has bf16 operands with fp32 accumulation (tcgen05), the residual stream is fp32.
 """
 import numpy as np
 import pytest
@@ -39,7 +39,7 @@ def test_cnn_stage_taps(setup, stage):
     a = torch.tensor(audio).cuda()
     got = tap(model, a, f"stage{stage}", 2 * LENS[stage] * DIMS[stage]).reshape(2, LENS[stage], DIMS[stage])[1]
     ref = taps[f"stage{stage}"]
-    tol = 2e-4 if stage <= 3 else 3e-2
+    tol = 1e-3 if stage == 0 else 3e-2
     assert _rel(got, ref) < tol, f"stage {stage}: rel err {_rel(got, ref)}"
 
 
