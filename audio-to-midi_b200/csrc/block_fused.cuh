@@ -101,7 +101,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     for (int kb = 0; kb < Cfg::KB1; ++kb) tma_load_2d(sW + kb * (H * 128), &tmW1, bar_w1, kb * 64, 0);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < H + C; i += FB_THREADS) sB1[i] = __ldg(params + 10 * C + i);
+  copy_const_to_smem<(H + C) / 4, FB_THREADS>(sB1, params + 10 * C, threadIdx.x);
 
   // ---------------------------------------------------------------- phase 1: dwconv7 + LN -> A1
   {

@@ -70,8 +70,8 @@ block_mid_kernel(const float* Xin, float* Xout, int L, int M, const float* __res
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < Cfg::P_TOTAL; i += BM_TOK) sp[i] = __ldg(params + i);
-  for (int i = threadIdx.x; i < (Cfg::W1_BYTES + Cfg::W2_BYTES) / 16; i += BM_TOK) reinterpret_cast<uint4*>(sW1)[i] = __ldg(wimg + i);
+  copy_const_to_smem<Cfg::P_TOTAL / 4, BM_TOK>(sp, params, threadIdx.x);
+  copy_const_to_smem<(Cfg::W1_BYTES + Cfg::W2_BYTES) / 16, BM_TOK>(sW1, wimg, threadIdx.x);
   pdl_wait();  // parameters are constants; activations of the previous kernel are read below
   // rows tile0-3 .. tile0+BM_TOK+2, zero outside [0, M): every load of a thread is issued before its first store
   {

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
   float* sx = smem_f + ((Lay::TOTAL + 3) & ~3);  // (TILE + 6) rows of input
 
   pdl_launch_dependents();
-  for (int i = threadIdx.x; i < Lay::TOTAL; i += SB_TOK) sp[i] = __ldg(params + i);
+  static_assert(Lay::TOTAL % 4 == 0, "parameter image is copied as 16-byte vectors");
+  copy_const_to_smem<Lay::TOTAL / 4, SB_TOK>(sp, params, threadIdx.x);
   pdl_wait();  // parameters are constants; activations of the previous kernel are read below
   const int tile0 = blockIdx.x * TILE;
   // rows tile0-3 .. tile0+TILE+2, zero outside [0, M): every load of a thread is issued before its first store

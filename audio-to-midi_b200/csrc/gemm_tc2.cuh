@@ -106,10 +106,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if ((g.flags & GF_BIAS) || MODE == G2_GLU)
-    for (int i = threadIdx.x; i < g.N; i += G2_THREADS) sBias[i] = __ldg(g.bias + i);
-  if (g.flags & GF_GAMMA)
-    for (int i = threadIdx.x; i < g.N; i += G2_THREADS) sGamma[i] = __ldg(g.gamma + i);
+  {
+    // bias / layer-scale vectors (constants, N <= 1024, N % 4 == 0): both loads of a thread are issued before its stores
+    const bool want_b = (g.flags & GF_BIAS) || MODE == G2_GLU, want_g = (g.flags & GF_GAMMA) != 0;
+    const int nv = g.N >> 2;
+    float4 vb[2], vg[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * G2_THREADS;
+      if (want_b && i < nv) vb[k] = __ldg(reinterpret_cast<const float4*>(g.bias) + i);
+      if (want_g && i < nv) vg[k] = __ldg(reinterpret_cast<const float4*>(g.gamma) + i);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * G2_THREADS;
+      if (want_b && i < nv) reinterpret_cast<float4*>(sBias)[i] = vb[k];
+      if (want_g && i < nv) reinterpret_cast<float4*>(sGamma)[i] = vg[k];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

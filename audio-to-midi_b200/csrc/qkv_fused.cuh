@@ -69,11 +69,22 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // RoPE rows pos0 .. pos0+127 (constants): 128 x 8 float4 each for cos and sin
-  for (int i = threadIdx.x; i < 2 * FF_ROWS * 8; i += QF_THREADS) {
-    const int which = i >> 10, r = (i >> 3) & 127, q = i & 7;
-    const float4 v = __ldg(reinterpret_cast<const float4*>((which ? rope_sin : rope_cos) + (pos0 + r) * 32) + q);
-    *reinterpret_cast<float4*>((which ? sSin : sCos) + r * 32 + 4 * (q ^ (r & 7))) = v;
+  // RoPE rows pos0 .. pos0+127 (constants): 128 x 8 float4 each for cos and sin; all loads of a thread before its stores
+  {
+    constexpr int NV = 2 * FF_ROWS * 8, PER = (NV + QF_THREADS - 1) / QF_THREADS;
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * QF_THREADS;
+      const int which = i >> 10, r = (i >> 3) & 127, q = i & 7;
+      if (i < NV) v[k] = __ldg(reinterpret_cast<const float4*>((which ? rope_sin : rope_cos) + (pos0 + r) * 32) + q);
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * QF_THREADS;
+      const int which = i >> 10, r = (i >> 3) & 127, q = i & 7;
+      if (i < NV) *reinterpret_cast<float4*>((which ? sSin : sCos) + r * 32 + 4 * (q ^ (r & 7))) = v[k];
+    }
   }
   tc_fence_before();
   __syncthreads();

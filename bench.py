@@ -358,6 +358,15 @@ def run_ours(args):
         achieved = f["bytes"] / (f["ms"] / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm"], "traffic": None}
+    # measured DRAM traffic of that kernel (one ncu --set full capture per round, profiles/*_traffic.json), per launch
+    try:
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+        with open(tf) as fh:
+            roof["traffic"] = json.load(fh).get(name)
+        roof["traffic_source"] = os.path.relpath(tf, ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+    except Exception:
+        pass
     roof.update({"kernel": name, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
                  "share_of_step": f["ms"] / total_ms, "peak_source": peaks["src"] + ", sustained bf16 figure",
                  "intensity_flop_per_byte": f["flops"] / max(f["bytes"], 1.0), "machine_balance": balance,

@@ -1,6 +1,6 @@
 """Stall samples of an ncu report aggregated per CUDA source line (the CSV source page only lists SASS).
 The k-th SASS row of the report is the k-th instruction of the kernel in `nvdisasm -g` of the in-tree library, whose
-'//## File "...", line N' annotations give the line.   usage: python tools/ncu_lines.py rep.ncu-rep kernel_substring [ntop]"""
+'//## File "...", line N' annotations give the line.   usage: python tools/ncu_lines.py rep.ncu-rep kernel_substring [ntop] [mangled_section_substring]"""
 import csv
 import os
 import re
@@ -10,6 +10,7 @@ import tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
 ntop = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+section = sys.argv[4] if len(sys.argv) > 4 else kern   # e.g. block_fused_kernelILi128ELb0 to pick one template instance
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "audio-to-midi_b200", "_build", "libaudio2midi_b200.so")
 tmp = tempfile.mkdtemp()
@@ -20,7 +21,7 @@ sass = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_outp
 lines, cur, inside = [], None, False
 for ln in sass:
     if ln.startswith("\t.section\t.text."):
-        inside = kern in ln
+        inside = section in ln
         continue
     if ln.startswith("\t.section"):
         inside = False
