@@ -26,6 +26,7 @@
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
 #include "postattn_fused.cuh"
+#include "block256_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_wgrad.cuh"
@@ -326,6 +327,7 @@ bool make_tmap_f32(A2mHandle* h, CUtensorMap* m, const void* base, uint64_t rows
 static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
+static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Blocks as dwconv_ln + two GEMM launches
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
@@ -470,6 +472,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block256_fused_kernel, B6_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -912,6 +915,20 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
                             t1, t1, static_cast<__nv_bfloat16*>(nullptr));
           }, label, out, static_cast<size_t>(M) * C);
         cur ^= 1;
+      } else if (C == 256 && g_fuse_b256) {
+        // stage 6: the whole Block in one launch (block256_fused.cuh), weights streamed per hidden chunk
+        const BigBlockW& bw = w.big_block[s][j];
+        const float* in = ws.X[cur];
+        float* out = ws.X[cur ^ 1];
+        const float* prm = dev_ptr<float>(h, bw.fused);
+        CUtensorMap t1, t2;
+        if (!make_tmap(h, &t1, dev_ptr<__nv_bfloat16>(h, bw.w1), 2 * C, C, C, 64, 64)) return false;
+        if (!make_tmap(h, &t2, dev_ptr<__nv_bfloat16>(h, bw.w2g), C, 2 * C, 2 * C, 64, 256)) return false;
+        const int tiles = (M + FF_ROWS - 1) / FF_ROWS;
+        add_step(p, Meta{"block256_fused_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C + 8.0 * C * C}, [=](cudaStream_t st) {
+          return launch_k(PF_FUSED, block256_fused_kernel, dim3(tiles), dim3(B6_THREADS), B6_SMEM, st, t1, t2, in, out, L, M, prm);
+        }, label, out, static_cast<size_t>(M) * C);
+        cur ^= 1;
       } else {
         const BigBlockW& bw = w.big_block[s][j];
         float* X = ws.X[cur];
@@ -1281,6 +1298,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
   return A2M_OK;
 }
 
