@@ -5,7 +5,7 @@
 //     qkv[:, 512:768] =        LN(x) (Wv Wc)^T
 // Replaces ln_rows_kernel + gemm_tc2<128, ROPE>: the normalised activations never leave shared memory.
 //
-//   warp 0      TMA producer: W [768, 256] streamed as 12 stages of [256 rows x 64 k] (32 KB) through a 3-deep ring
+//   warp 0      TMA producer: W [768, 256] streamed as 12 stages of [256 rows x 64 k] (32 KB) through a 2-deep ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer: 3 column chunks of 256, accumulators ping-pong in 2 x 256 columns
 //   warps 2-17  LayerNorm of the tile (one warp per row) -> bf16 A operand; then per chunk, in two halves of 32 columns per
 //               head: TMEM -> RoPE -> bf16 into a 64B-swizzled staging tile -> TMA store (per-thread global stores of one
@@ -20,11 +20,11 @@ namespace a2m {
 constexpr int QF_THREADS = FF_THREADS;          // 2 + 16 warps
 constexpr int QF_N = 768;
 constexpr int QF_NCHUNK = QF_N / 256;            // 3
-constexpr int QF_NST = 3;
+constexpr int QF_NST = 2;                        // the epilogue, not the weight stream, paces this kernel: two stages suffice
 constexpr int QF_ROPE_BYTES = 2 * FF_ROWS * 32 * 4;               // cos then sin, 128 positions x 32 pairs (float4 index XOR row & 7)
 constexpr int QF_OUT_TILE = FF_ROWS * 64;                         // staging tile: 128 rows x 32 bf16, 64B swizzle
-constexpr int QF_OUT_BYTES = 4 * QF_OUT_TILE;                     // one tile per head of the chunk
-constexpr int QF_MAIN_BYTES = FF_A_BYTES + QF_NST * FF_STAGE;     // 160 KB
+constexpr int QF_OUT_BYTES = 2 * 4 * QF_OUT_TILE;                 // one tile per head of the chunk, double buffered
+constexpr int QF_MAIN_BYTES = FF_A_BYTES + QF_NST * FF_STAGE;     // 128 KB
 constexpr size_t QF_SMEM = 1024 + QF_MAIN_BYTES + QF_OUT_BYTES + QF_ROPE_BYTES + 256;
 
 // tmW: Wqkv [768, 256] bf16, box {64, 256}.  tmO: out [M, 768] bf16, box {32, 128}, 64B swizzle.  X: fp32 [M, 256].
@@ -142,7 +142,6 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     mbar_arrive(bar_a);
     if (threadIdx.x == 64) FF_STAMP(82);
 
-    uint8_t* stile = sOut + cq * QF_OUT_TILE;
     const uint32_t rsw = static_cast<uint32_t>(row >> 1) & 3u;   // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
     const bool storer = threadIdx.x == 64;
 #pragma unroll 1
@@ -178,9 +177,10 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             }
           }
         }
-        // the previous half's TMA stores must have finished reading the staging tiles
-        if (storer) bulk_wait_read<0>();
-        named_bar_sync(1, FF_CTHREADS);
+        // staging tiles are double buffered by half: the stores of the previous half (other buffer) are waited for just
+        // before this half's barrier, so the buffer the NEXT half overwrites is known to be drained by then
+        uint8_t* sbuf = sOut + half * (4 * QF_OUT_TILE);
+        uint8_t* stile = sbuf + cq * QF_OUT_TILE;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;
@@ -191,10 +191,11 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           *reinterpret_cast<uint4*>(stile + row * 64 + ((static_cast<uint32_t>(q) ^ rsw) << 4)) = o;
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, FF_CTHREADS);
+        if (storer) bulk_wait_read<0>();
+        named_bar_sync(1, FF_CTHREADS);
         if (storer) {
 #pragma unroll
-          for (int hd = 0; hd < 4; ++hd) tma_store_2d(&tmO, sOut + hd * QF_OUT_TILE, n * 256 + hd * 64 + half * 32, tile0);
+          for (int hd = 0; hd < 4; ++hd) tma_store_2d(&tmO, sbuf + hd * QF_OUT_TILE, n * 256 + hd * 64 + half * 32, tile0);
           bulk_commit();
         }
       }
