@@ -113,7 +113,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     RM::load(params + 9 * C, lane, lb);
     pdl_wait();  // weights / parameters above are constants; x is produced by the previous kernel
     if (threadIdx.x == 0) FB_STAMP(113);
-    constexpr int TPP = 8;                                   // tokens per pass
+    constexpr int TPP = 8;                                   // tokens per pass (warp_sum8_all)
     constexpr int PASSES = FB_TOK / (FB_THREADS / 32) / TPP;  // 2
     const int col = RM::chan(lane, 0);
 #pragma unroll 1
@@ -130,35 +130,56 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           for (int j = 0; j < PER; ++j) rows[i][j] = 0.f;
         }
       }
+      // depthwise conv of the 8 tokens of the pass, then their LayerNorm statistics jointly (warp_sum8_all)
+      float y[TPP][PER];
 #pragma unroll
       for (int i = 0; i < TPP; ++i) {
-        const int r = r0 + i;
-        const int tok = tile0 + r;
-        const int l = tok % L;
-        float y[PER];
+        const int l = (tile0 + r0 + i) % L;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) y[j] = bias[j];
+        for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
 #pragma unroll
         for (int t = 0; t < 7; ++t) {
           const int ll = l + t - 3;
           if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary (warp-uniform)
 #pragma unroll
-            for (int j = 0; j < PER; ++j) y[j] = fmaf(w[t][j], rows[i + t][j], y[j]);
+            for (int j = 0; j < PER; ++j) y[i][j] = fmaf(w[t][j], rows[i + t][j], y[i][j]);
           }
         }
-        RM::layer_norm(y, lw, lb);
-        if (tok >= M) {
+      }
+      float st[TPP];
 #pragma unroll
-          for (int j = 0; j < PER; ++j) y[j] = 0.f;
-        }
+      for (int i = 0; i < TPP; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) a += y[i][j];
+        st[i] = a;
+      }
+      warp_sum8_all(st, lane);
+      float mean[TPP];
+#pragma unroll
+      for (int i = 0; i < TPP; ++i) {
+        mean[i] = st[i] * (1.0f / C);
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) a += (y[i][j] - mean[i]) * (y[i][j] - mean[i]);
+        st[i] = a;
+      }
+      warp_sum8_all(st, lane);
+#pragma unroll
+      for (int i = 0; i < TPP; ++i) {
+        const int r = r0 + i;
+        const float inv = rsqrtf(st[i] * (1.0f / C) + kLnEps);
+        const bool live = tile0 + r < M;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) y[i][j] = live ? (y[i][j] - mean[i]) * inv * lw[j] + lb[j] : 0.f;
         uint8_t* dst = sA + (col >> 6) * (FB_TOK * 128) + sw128_offset(r, col & 63);
         if constexpr (PER == 4) {
           uint2 q;
-          q.x = pack_bf16x2(y[0], y[1]);
-          q.y = pack_bf16x2(y[2], y[3]);
+          q.x = pack_bf16x2(y[i][0], y[i][1]);
+          q.y = pack_bf16x2(y[i][2], y[i][3]);
           *reinterpret_cast<uint2*>(dst) = q;
         } else {
-          *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[0], y[1]);
+          *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[i][0], y[i][1]);
         }
       }
     }
