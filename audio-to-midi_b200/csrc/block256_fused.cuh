@@ -172,33 +172,53 @@ block256_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
             for (int j = 0; j < PER; ++j) rows[i][j] = 0.f;
           }
         }
+        float y[TPP][PER];
 #pragma unroll
         for (int i = 0; i < TPP; ++i) {
-          const int r = r0 + i;
-          const int tok = tile0 + r;
-          const int l = tok % L;
-          float y[PER];
+          const int l = (tile0 + r0 + i) % L;
 #pragma unroll
-          for (int j = 0; j < PER; ++j) y[j] = bias[j];
+          for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
 #pragma unroll
           for (int t = 0; t < 7; ++t) {
             const int ll = l + t - 3;
             if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary (warp-uniform)
 #pragma unroll
-              for (int j = 0; j < PER; ++j) y[j] = fmaf(w[t][j], rows[i + t][j], y[j]);
+              for (int j = 0; j < PER; ++j) y[i][j] = fmaf(w[t][j], rows[i + t][j], y[i][j]);
             }
           }
-          RM::layer_norm(y, lw, lb);
-          if (tok >= M) {
+        }
+        // LayerNorm statistics of the 4 tokens jointly
+        float st[TPP], mean[TPP];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) y[j] = 0.f;
-          }
+        for (int i = 0; i < TPP; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int j = 0; j < PER; ++j) a += y[i][j];
+          st[i] = a;
+        }
+        warp_sum_all<TPP>(st, lane);
+#pragma unroll
+        for (int i = 0; i < TPP; ++i) {
+          mean[i] = st[i] * (1.0f / B6_C);
+          float a = 0.f;
+#pragma unroll
+          for (int j = 0; j < PER; ++j) a += (y[i][j] - mean[i]) * (y[i][j] - mean[i]);
+          st[i] = a;
+        }
+        warp_sum_all<TPP>(st, lane);
+#pragma unroll
+        for (int i = 0; i < TPP; ++i) {
+          const int r = r0 + i;
+          const float inv = rsqrtf(st[i] * (1.0f / B6_C) + kLnEps);
+          const bool live = tile0 + r < M;
+#pragma unroll
+          for (int j = 0; j < PER; ++j) y[i][j] = live ? (y[i][j] - mean[i]) * inv * lw[j] + lb[j] : 0.f;
 #pragma unroll
           for (int g = 0; g < RM::G; ++g) {
             const int col = RM::chan(lane, g);
             uint2 q;
-            q.x = pack_bf16x2(y[4 * g], y[4 * g + 1]);
-            q.y = pack_bf16x2(y[4 * g + 2], y[4 * g + 3]);
+            q.x = pack_bf16x2(y[i][4 * g], y[i][4 * g + 1]);
+            q.y = pack_bf16x2(y[i][4 * g + 2], y[i][4 * g + 3]);
             *reinterpret_cast<uint2*>(sA + (col >> 6) * (FF_ROWS * 128) + sw128_offset(r, col & 63)) = q;
           }
         }

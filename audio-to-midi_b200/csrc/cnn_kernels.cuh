@@ -37,13 +37,15 @@ __device__ __forceinline__ float gelu_tanh_cc(float x) {
   return fmaf(hx, t, hx);
 }
 
-// Sums v[i] over the 32 lanes for 8 values at once and returns every total to every lane (in v): a transposing butterfly
-// (4 + 2 + 1 exchanges that halve the vector, 2 plain butterflies) leaves total i in lanes 4 i .. 4 i + 3, then 8 broadcasts:
-// 17 independent-ish shuffles instead of the 40 dependent ones of eight warp_sum() calls.
-__device__ __forceinline__ void warp_sum8_all(float (&v)[8], int lane) {
+// Sums v[i] over the 32 lanes for N (4 or 8) values at once and returns every total to every lane (in v): a transposing
+// butterfly (N/2 + ... + 1 exchanges that halve the vector, then plain butterflies) leaves total i in lanes (32/N) i ..,
+// then N broadcasts: 17 (N = 8) shuffles instead of the 40 dependent ones of eight warp_sum() calls.
+template <int N>
+__device__ __forceinline__ void warp_sum_all(float (&v)[N], int lane) {
+  static_assert(N == 4 || N == 8, "warp_sum_all: 4 or 8 values");
   int off = 16;
 #pragma unroll
-  for (int n = 8; n > 1; n >>= 1, off >>= 1) {
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
     const bool upper = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < n / 2; ++i) {
@@ -53,11 +55,12 @@ __device__ __forceinline__ void warp_sum8_all(float (&v)[8], int lane) {
     }
   }
   float r = v[0];
-  r += __shfl_xor_sync(0xffffffffu, r, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(0xffffffffu, r, 4 * i);
+  for (int o = (32 / N) / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __shfl_sync(0xffffffffu, r, (32 / N) * i);
 }
+__device__ __forceinline__ void warp_sum8_all(float (&v)[8], int lane) { warp_sum_all<8>(v, lane); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
