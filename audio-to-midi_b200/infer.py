@@ -132,3 +132,112 @@ def compute_testset_loss(model, audio, events, rank: int = 0, world_size: int = 
         pr = probs.cpu().numpy()
         details.extend(detailed_event_loss(pr[k], events[i + k]) for k in range(j - i))
     return lo, hi, (np.concatenate(losses) if losses else np.zeros(0, np.float32)), details
+
+
+# ------------------------------------------------------------------------------------------ MIDI writer
+NUM_VELOCITY_CATEGORIES = 10      # audio_to_midi_dataset.py:33
+_TICKS_PER_BEAT = 480             # mido.MidiFile default
+_TEMPO_US = 500000                # mido.bpm2tempo(120), 4/4  (infer.py:53-57)
+
+
+def _varlen(n: int) -> bytes:
+    out = [n & 0x7F]
+    n >>= 7
+    while n:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    return bytes(reversed(out))
+
+
+def write_midi_file(events, duration_per_frame: float, output_file: str):
+    """infer.py:46-83 without mido (absent from the image): one track, tempo 120, 4/4, note_on / note_off pairs of
+    events (attack_frame, key, duration_frames, velocity) at MIDI key `key + 21`, velocity round(v / 10 * 127), times
+    frame * duration_per_frame converted with mido.second2tick's rounding; messages sorted as the reference sorts its
+    (time, type, key, velocity) tuples ('note_off' < 'note_on' at equal times).  Writes a format-1 standard MIDI file
+    byte-compatible with what mido saves for the same messages (no running status, end_of_track appended)."""
+    def frame_to_tick(frame):
+        seconds = frame * duration_per_frame
+        return int(round(seconds / (_TEMPO_US * 1e-6 / _TICKS_PER_BEAT)))      # mido.second2tick
+
+    msgs = []
+    for attack_frame, key, duration_frame, velocity in events:
+        midi_key = int(key) + 21
+        vel = int(round((velocity / NUM_VELOCITY_CATEGORIES) * 127))
+        msgs.append((frame_to_tick(attack_frame), "note_on", midi_key, vel))
+        msgs.append((frame_to_tick(attack_frame + duration_frame), "note_off", midi_key, vel))
+    track = bytearray()
+    track += _varlen(0) + bytes([0xFF, 0x51, 0x03]) + _TEMPO_US.to_bytes(3, "big")                  # set_tempo
+    track += _varlen(0) + bytes([0xFF, 0x58, 0x04, 4, 2, 24, 8])                                    # time_signature 4/4
+    now = 0
+    for t, kind, key, vel in sorted(msgs):
+        track += _varlen(t - now) + bytes([0x90 if kind == "note_on" else 0x80, key & 0x7F, vel & 0x7F])
+        now = t
+    track += _varlen(0) + bytes([0xFF, 0x2F, 0x00])                                                 # end_of_track
+    with open(output_file, "wb") as f:
+        f.write(b"MThd" + (6).to_bytes(4, "big") + (1).to_bytes(2, "big") + (1).to_bytes(2, "big") + _TICKS_PER_BEAT.to_bytes(2, "big"))
+        f.write(b"MTrk" + len(track).to_bytes(4, "big") + bytes(track))
+
+
+def read_midi_notes(path: str):
+    """Minimal reader of files written by write_midi_file (tests): list of (tick, 'note_on' | 'note_off', key, velocity)."""
+    data = open(path, "rb").read()
+    assert data[:4] == b"MThd" and data[14:18] == b"MTrk"
+    n = int.from_bytes(data[18:22], "big")
+    body, i, tick, out = data[22:22 + n], 0, 0, []
+    while i < len(body):
+        d = 0
+        while True:
+            b = body[i]
+            i += 1
+            d = (d << 7) | (b & 0x7F)
+            if not b & 0x80:
+                break
+        tick += d
+        st = body[i]
+        if st == 0xFF:
+            ln = body[i + 2]
+            i += 3 + ln
+        else:
+            out.append((tick, "note_on" if st & 0xF0 == 0x90 else "note_off", body[i + 1], body[i + 2]))
+            i += 3
+    return out
+
+
+# ------------------------------------------------------------------------------------------ SURVEY §8f-4: checkpoints
+def save_checkpoint(model, directory: str, step: int):
+    """Pytree-path-keyed `.npz` stand-in for the reference's orbax CheckpointManager (train.py:384-394; orbax and
+    tensorstore are absent from the image): `<directory>/<step>/params.npz` holds every array leaf under its key path
+    (exactly the names and shapes an `ocp.args.StandardRestore` of the reference model yields), `metadata.json` the
+    model metadata the reference stores next to a checkpoint (model.py:36-41)."""
+    import json
+    import os
+    from .model import get_model_metadata
+    d = os.path.join(directory, str(int(step)))
+    os.makedirs(d, exist_ok=True)
+    np.savez(os.path.join(d, "params.npz"), **{p: np.asarray(a) for p, a in model.tree_leaves_with_path()})
+    with open(os.path.join(d, "metadata.json"), "w") as f:
+        json.dump(get_model_metadata(), f)
+    return d
+
+
+def load_newest_checkpoint(checkpoint_path: str):
+    """infer.py:172-236 for the `.npz` layout of save_checkpoint: restores the highest step, warns when the stored model
+    metadata differs from the current configuration (as the reference does), returns (model, state)."""
+    import json
+    import os
+    from .model import OutputSequenceGenerator, get_model_metadata, model_config
+    steps = sorted(int(s) for s in os.listdir(checkpoint_path) if s.isdigit())
+    if not steps:
+        raise FileNotFoundError("There is no checkpoint to load! Inference will be useless")
+    d = os.path.join(checkpoint_path, str(steps[-1]))
+    meta_file = os.path.join(d, "metadata.json")
+    if os.path.exists(meta_file):
+        with open(meta_file) as f:
+            stored = json.load(f)
+        if stored != json.loads(json.dumps(get_model_metadata())):
+            print(f"WARNING: The loaded model has metadata {stored}\nCurrent configuration is {get_model_metadata()}")
+    with np.load(os.path.join(d, "params.npz")) as z:
+        leaves = {k: z[k] for k in z.files}
+    model = OutputSequenceGenerator(model_config, key=1234)
+    model.load_leaves(leaves)
+    return model, None

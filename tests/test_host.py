@@ -200,3 +200,41 @@ def test_lr_schedule_and_multipliers():
     m = T.layer_lr_multipliers(paths, 0.7)
     assert m[-1] == 1.0 and m[3] == 1.0 and m[2] == 1.0          # deepest conv layer: decay ** 0
     assert abs(m[0] - 0.7 ** 39) < 1e-9 and abs(m[1] - 0.7 ** 36) < 1e-9
+
+
+def test_midi_writer_round_trip(tmp_path):
+    """write_midi_file (infer.py:46-83): header, tempo / time-signature metas, tick conversion of mido.second2tick,
+    velocity scaling, note_off before note_on at equal ticks, end_of_track."""
+    from audio_to_midi_b200 import infer
+    events = [(0, 39, 25, 7), (25, 39, 10, 7), (10, 60, 5, 10), (100, 0, 1, 1)]
+    f = tmp_path / "out.mid"
+    infer.write_midi_file(events, 0.02, str(f))
+    raw = f.read_bytes()
+    assert raw[:14] == b"MThd" + (6).to_bytes(4, "big") + b"\x00\x01\x00\x01\x01\xe0"
+    assert raw[22:29] == b"\x00\xff\x51\x03\x07\xa1\x20"            # set_tempo 500000 us
+    assert raw[29:37] == b"\x00\xff\x58\x04\x04\x02\x18\x08"        # 4/4, 24 clocks per click, 8 32nds per beat
+    assert raw[-4:] == b"\x00\xff\x2f\x00"
+    notes = infer.read_midi_notes(str(f))
+    tick = lambda frame: int(round(frame * 0.02 / (500000e-6 / 480)))
+    want = sorted([(tick(a), "note_on", k + 21, int(round(v / 10 * 127))) for a, k, d, v in events] +
+                  [(tick(a + d), "note_off", k + 21, int(round(v / 10 * 127))) for a, k, d, v in events])
+    assert notes == want
+    i_off = notes.index((tick(25), "note_off", 60, 89))
+    assert notes[i_off + 1] == (tick(25), "note_on", 60, 89)           # release of the first note precedes the re-attack
+    assert tick(25) == 480                                              # 0.5 s at 120 bpm = one beat
+
+
+def test_checkpoint_npz_round_trip(tmp_path):
+    """save_checkpoint / load_newest_checkpoint: every pytree leaf under its key path, newest step wins."""
+    from audio_to_midi_b200 import infer
+    m0 = A.OutputSequenceGenerator(A.model_config, key=3)
+    m1 = A.OutputSequenceGenerator(A.model_config, key=4)
+    infer.save_checkpoint(m0, str(tmp_path), 100)
+    infer.save_checkpoint(m1, str(tmp_path), 2000)
+    got, state = infer.load_newest_checkpoint(str(tmp_path))
+    assert state is None
+    a, b = dict(m1.tree_leaves_with_path()), dict(got.tree_leaves_with_path())
+    assert list(a) == list(b) and len(a) == 450
+    assert all(np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for k in a)
+    assert not np.array_equal(np.asarray(dict(m0.tree_leaves_with_path())["decoder.decoder_pooling.weight"]),
+                              np.asarray(b["decoder.decoder_pooling.weight"]))
