@@ -145,6 +145,7 @@ struct TLayerW {
 struct Weights {
   StemParams stem;
   size_t small_block[4][3];
+  size_t down_p[5], down_w[5];        // down_mid_kernel (output stages 3, 4): lnw | lnb | bias, pre-swizzled bf16 weight tile
   size_t mid_p[4][3], mid_w[4][3];   // block_mid_kernel (stages 1-3): fp32 parameter image, bf16 pre-swizzled W1 | gamma*W2 tiles
   size_t small_down[5];           // index = output stage 1..4
   BigBlockW big_block[kStages][21];
@@ -482,6 +483,8 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(block_mid_kernel<8>, MidBlockCfg<8>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(down_mid_kernel<16>, MidDownCfg<16>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(down_mid_kernel<32>, MidDownCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -583,6 +586,19 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
         img.insert(img.end(), wk.begin(), wk.end());
         img.insert(img.end(), bb.begin(), bb.end());
         w->small_down[s] = ar->put_f32(img);
+        if (Cin >= 16) {
+          // tensor-core variant (block_mid.cuh, down_mid_kernel): lnw | lnb | bias and the [Cout][64] swizzled weight tile
+          std::vector<float> pimg;
+          pimg.insert(pimg.end(), a.begin(), a.end());
+          pimg.insert(pimg.end(), b.begin(), b.end());
+          pimg.insert(pimg.end(), bb.begin(), bb.end());
+          w->down_p[s] = ar->put_f32(pimg);
+          std::vector<float> wimg(static_cast<size_t>(C) * 64, 0.f);
+          for (int n = 0; n < C; ++n)
+            for (int k = 0; k < 2 * Cin; ++k)
+              wimg[static_cast<size_t>(n) * 64 + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = wk[static_cast<size_t>(n) * 2 * Cin + k];
+          w->down_w[s] = ar->put_bf16(wimg);
+        }
       } else {
         w->big_down[s].lnw = ar->put_f32(vec(lw));
         w->big_down[s].lnb = ar->put_f32(vec(lb));
@@ -842,6 +858,16 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (s <= 4) {
         const float* prm = dev_ptr<float>(h, w.small_down[s]);
         const Meta md{"downsample_small_kernel", 2.0 * M * C * C, 8.0 * M * C};
+        if (s >= 3 && g_mid_tc) {
+          const float* dp = dev_ptr<float>(h, w.down_p[s]);
+          const uint4* dw = dev_ptr<uint4>(h, w.down_w[s]);
+          const Meta mdt{"down_mid_kernel", 2.0 * M * C * C, 8.0 * M * C};
+          const dim3 grid((M + BM_TOK - 1) / BM_TOK);
+          if (s == 3)
+            add_step(p, mdt, [=](cudaStream_t st) { return launch_k(PF_SMALL, down_mid_kernel<16>, grid, dim3(BM_TOK), MidDownCfg<16>::SMEM, st, in, out, M, dp, dw); });
+          else
+            add_step(p, mdt, [=](cudaStream_t st) { return launch_k(PF_SMALL, down_mid_kernel<32>, grid, dim3(BM_TOK), MidDownCfg<32>::SMEM, st, in, out, M, dp, dw); });
+        } else
         switch (s) {
           case 1: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); }); break;
           case 2: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); }); break;

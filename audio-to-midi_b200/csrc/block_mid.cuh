@@ -236,3 +236,148 @@ block_mid_kernel(const float* Xin, float* Xout, int L, int M, const float* __res
 }
 
 }  // namespace a2m
+
+namespace a2m {
+
+// ------------------------------------------------------------------------------------------ Downsample, Cin in {16, 32}
+// Downsample (model.py:102-118): LayerNorm over the input channels of every token, then Conv1d(Cin -> 2 Cin, k = 2, s = 2),
+// i.e. out[t'] = W [ LN(x[2t']) ; LN(x[2t'+1]) ] + b with K = 2 Cin (the two input tokens of an output token are adjacent
+// rows, so the input is simply viewed as [M_out, 2 Cin]).  Same recipe as block_mid_kernel: coalesced padded smem tile,
+// one thread per OUTPUT token for the two LayerNorms -> bf16 A row, one tcgen05 product 128 x 2Cin x 2Cin against the
+// pre-swizzled weight tile, bias + coalesced store through the same smem tile.  downsample_small_kernel read and wrote
+// 256 contiguous bytes per thread (32 LSU wavefronts per instruction) and did the product with broadcast LDS.
+template <int CIN>
+struct MidDownCfg {
+  static constexpr int K = 2 * CIN, N = 2 * CIN;      // 32 / 64
+  static constexpr int RS = K + 4;
+  static constexpr int W_BYTES = ((N * 128 + 1023) / 1024) * 1024;
+  static constexpr int P_LNB = CIN, P_B = 2 * CIN, P_TOTAL = 2 * CIN + N;   // lnw | lnb | bias
+  static constexpr int A_BYTES = BM_TOK * 128;
+  static constexpr int X_BYTES = BM_TOK * RS * 4;
+  static constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
+  static constexpr size_t SMEM = 1024 + A_BYTES + W_BYTES + X_BYTES + P_TOTAL * 4 + 64;
+};
+
+// X: [M_out, 2 Cin] fp32 view of the input; Y: [M_out, 2 Cin] fp32.  wimg: bf16 [N rows][64] pre-swizzled (k = tap * Cin + c).
+template <int CIN>
+__global__ void __launch_bounds__(BM_TOK, 3)
+down_mid_kernel(const float* X, float* Y, int M_out, const float* __restrict__ params, const uint4* __restrict__ wimg) {
+  using Cfg = MidDownCfg<CIN>;
+  constexpr int K = Cfg::K, N = Cfg::N, V = K / 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + Cfg::A_BYTES;
+  float* sx = reinterpret_cast<float*>(sW + Cfg::W_BYTES);
+  float* sp = sx + BM_TOK * Cfg::RS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sp + Cfg::P_TOTAL);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int tile0 = blockIdx.x * BM_TOK;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  copy_const_to_smem<Cfg::P_TOTAL / 4, BM_TOK>(sp, params, threadIdx.x);
+  copy_const_to_smem<N * 128 / 16, BM_TOK>(sW, wimg, threadIdx.x);
+  pdl_wait();  // parameters are constants; activations of the previous kernel are read below (plain loads)
+  {
+    constexpr int NV = BM_TOK * V, PER = NV / BM_TOK;
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * BM_TOK;
+      const int r = i / V, q = i - r * V;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tile0 + r < M_out) v[k] = reinterpret_cast<const float4*>(X + static_cast<size_t>(tile0 + r) * K)[q];
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * BM_TOK;
+      const int r = i / V, q = i - r * V;
+      reinterpret_cast<float4*>(sx + r * Cfg::RS)[q] = v[k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int row = threadIdx.x;
+  const uint32_t t_row = static_cast<uint32_t>(warp * 32) << 16;
+
+  // two LayerNorms (one per input token) -> bf16 A row
+  {
+    float n[K];
+    const float* xr = sx + row * Cfg::RS;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 v = reinterpret_cast<const float4*>(xr)[q];
+      n[4 * q] = v.x; n[4 * q + 1] = v.y; n[4 * q + 2] = v.z; n[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) mean += n[t * CIN + c];
+      mean *= (1.0f / CIN);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) var += (n[t * CIN + c] - mean) * (n[t * CIN + c] - mean);
+      const float inv = rsqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) n[t * CIN + c] = (n[t * CIN + c] - mean) * inv * sp[c] + sp[Cfg::P_LNB + c];
+    }
+#pragma unroll
+    for (int q = 0; q < K / 8; ++q)
+      *reinterpret_cast<uint4*>(sA + sw128_offset(row, 8 * q)) =
+          make_uint4(pack_bf16x2(n[8 * q], n[8 * q + 1]), pack_bf16x2(n[8 * q + 2], n[8 * q + 3]),
+                     pack_bf16x2(n[8 * q + 4], n[8 * q + 5]), pack_bf16x2(n[8 * q + 6], n[8 * q + 7]));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t da = umma_desc_sw128(smem_u32(sA));
+    const uint64_t db = umma_desc_sw128(smem_u32(sW));
+#pragma unroll
+    for (int k = 0; k < K / 16; ++k)
+      umma_bf16(tmem_d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc, k != 0 ? 1u : 0u);
+    umma_commit(bar);
+  }
+  __syncwarp();
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  {
+    float* orow = sx + row * Cfg::RS;   // this thread's input row is dead: its output row takes the same bytes
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(tmem_d + t_row + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(orow + c0)[q] =
+            make_float4(__uint_as_float(r[4 * q]) + sp[Cfg::P_B + c0 + 4 * q], __uint_as_float(r[4 * q + 1]) + sp[Cfg::P_B + c0 + 4 * q + 1],
+                        __uint_as_float(r[4 * q + 2]) + sp[Cfg::P_B + c0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + sp[Cfg::P_B + c0 + 4 * q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int i = threadIdx.x; i < BM_TOK * V; i += BM_TOK) {
+    const int r = i / V, q = i - r * V;
+    if (tile0 + r < M_out) reinterpret_cast<float4*>(Y + static_cast<size_t>(tile0 + r) * N)[q] = reinterpret_cast<const float4*>(sx + r * Cfg::RS)[q];
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(*tmem_slot);
+  }
+}
+
+}  // namespace a2m
