@@ -102,3 +102,53 @@ def test_pipelined_host_path_matches_sync(setup):
         assert lg.shape == (b.shape[0], 250, 90)
         assert np.array_equal(lg, lg_s) and np.array_equal(pr, pr_s)
     assert list(model.predict_pipelined(iter([]), rope)) == []
+
+
+def test_odd_batch_matches_torch_oracle():
+    """5 windows (an odd number of 128-row tiles per CNN stage, 10 transformer tiles): every window against the
+    PyTorch-CPU fp32 restatement, so tile boundaries inside and between windows are exercised in the fused kernels."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model
+    from oracle import model_torch as MT
+    from oracle import synth
+    model, tree = make_model(97, **ACTIVE)
+    audio = synth.make_windows(5, 97)
+    with torch.no_grad():
+        ref_logits, ref_probs = MT.forward(MT.to_torch(tree), torch.tensor(audio))
+    _, pr = model.predict(None, torch.tensor(audio).cuda(), A.precompute_frequencies(64, 300))
+    err = np.abs(pr.cpu().numpy() - ref_probs.numpy()).reshape(5, -1).max(axis=1)
+    assert (err < 3e-2).all(), err
+
+
+def test_fused_and_unfused_paths_agree(tmp_path):
+    """The run-time switches of INTEGRATION.md section 5 select launch-by-launch equivalents of the fused kernels
+    (read once at a2m_create, hence one subprocess per setting): every setting must reproduce the default path's
+    probabilities to bf16 accuracy.  Guards both the switches and the fused kernels against each other."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import audio_to_midi_b200 as A\n"
+        "from gpu_util import make_model\n"
+        "from oracle import synth\n"
+        "model, _ = make_model(4321, gamma_mode='active', decoder_gain=4.0, trained_like=True)\n"
+        "audio = synth.make_windows(3, 4321)\n"
+        "_, pr = model.predict(None, torch.tensor(audio).cuda(), A.precompute_frequencies(64, 300))\n"
+        "np.save(sys.argv[1], pr.cpu().numpy())\n")
+    outs = {}
+    settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_POST": "0", "A2M_FUSE_FFN": "0", "A2M_MID_TC": "0",
+                                           "A2M_FUSE_B256": "0"},
+                "ffn_only": {"A2M_FUSE_POST": "0"}, "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
+    for name, env in settings.items():
+        out = tmp_path / f"{name}.npy"
+        res = subprocess.run([sys.executable, "-c", script, str(out)], env={**os.environ, **env}, capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs[name] = np.load(out)
+    assert np.array_equal(outs["default"], outs["no_graph_no_pdl"])       # same kernels, different launch mechanism
+    for name in ("unfused", "ffn_only"):
+        d = np.abs(outs[name] - outs["default"]).max()
+        assert 0 < d < 2e-2, (name, d)
