@@ -329,6 +329,7 @@ static thread_local bool tl_pdl = false;
 // bit per kernel family (debug): 0 small CNN kernels, 1 ln/dwconv, 2 gemm, 3 fused block, 4 attention
 static unsigned g_pdl_mask = 0xffffffffu;
 static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Blocks as dwconv_ln + two GEMM launches
+static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
@@ -891,6 +892,23 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       }
       cur ^= 1;
     }
+    if (s <= 1 && g_fuse_small && kDepths[s] == 3) {
+      // stages 0-1: the three Blocks in one launch (cnn_kernels.cuh, stage_small_kernel)
+      const float* in = ws.X[cur];
+      float* out = ws.X[cur ^ 1];
+      const float* p0 = dev_ptr<float>(h, w.small_block[s][0]);
+      const float* p1 = dev_ptr<float>(h, w.small_block[s][1]);
+      const float* p2 = dev_ptr<float>(h, w.small_block[s][2]);
+      const Meta ms{"stage_small_kernel", 3 * 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
+      const dim3 grid((M + SS_TOK - 1) / SS_TOK);
+      const std::string label = "stage" + std::to_string(s);
+      const size_t te = static_cast<size_t>(M) * C;
+      if (s == 0)
+        add_step(p, ms, [=](cudaStream_t st) { return launch_k(PF_SMALL, stage_small_kernel<4>, grid, dim3(SS_THREADS), SmallStageCfg<4>::SMEM, st, in, out, L, M, p0, p1, p2); }, label, out, te);
+      else
+        add_step(p, ms, [=](cudaStream_t st) { return launch_k(PF_SMALL, stage_small_kernel<8>, grid, dim3(SS_THREADS), SmallStageCfg<8>::SMEM, st, in, out, L, M, p0, p1, p2); }, label, out, te);
+      cur ^= 1;
+    } else
     for (int j = 0; j < kDepths[s]; ++j) {
       const bool last = (j == kDepths[s] - 1);
       const std::string label = last ? "stage" + std::to_string(s) : "";
@@ -1324,6 +1342,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
   return A2M_OK;
 }

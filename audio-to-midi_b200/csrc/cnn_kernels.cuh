@@ -257,6 +257,156 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
 }
 
 
+// ------------------------------------------------------------------------------------------ three small Blocks fused
+// The three Blocks of a narrow stage (C in {4, 8}: a 128-token tile is 2-4 KB, every launch is a latency-bound chain
+// of load -> barrier -> ~300 instructions per token -> store) in ONE launch: the tile is loaded once with a halo of 9
+// tokens, Block k is evaluated by one thread per token for the rows the next Block still needs (halo shrinking by 3 per
+// Block, ping-pong between two shared-memory buffers), the third Block's 128 rows are stored.  One third of the global
+// traffic and of the launches of three block_small_kernel calls; the arithmetic per token is identical (same device
+// function), so are the results.
+template <int C>
+__device__ __forceinline__ void small_block_token(const float* __restrict__ sp, const float* rows /* row of token-3 */, int RS,
+                                                  int l, int L, float* out /* [C] */) {
+  using Lay = SmallBlockLayout<C>;
+  constexpr int H = Lay::H, V = C / 4;
+  float y[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) y[c] = sp[Lay::DWB + c];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const int ll = l + t - 3;
+    if (ll >= 0 && ll < L) {   // zero "SAME" padding at the WINDOW boundary
+      const float* row = rows + t * RS;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 xv = reinterpret_cast<const float4*>(row)[q];
+        const float4 wv = reinterpret_cast<const float4*>(sp + Lay::DW + t * C)[q];
+        y[4 * q] = fmaf(wv.x, xv.x, y[4 * q]);
+        y[4 * q + 1] = fmaf(wv.y, xv.y, y[4 * q + 1]);
+        y[4 * q + 2] = fmaf(wv.z, xv.z, y[4 * q + 2]);
+        y[4 * q + 3] = fmaf(wv.w, xv.w, y[4 * q + 3]);
+      }
+    }
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) mean += y[c];
+  mean *= (1.0f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) var += (y[c] - mean) * (y[c] - mean);
+  const float inv = rsqrtf(var * (1.0f / C) + kLnEps);
+#pragma unroll
+  for (int c = 0; c < C; ++c) y[c] = (y[c] - mean) * inv * sp[Lay::LNW + c] + sp[Lay::LNB + c];
+  float o[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) o[c] = sp[Lay::B2 + c];
+#pragma unroll 2
+  for (int h = 0; h < H; ++h) {
+    float a = sp[Lay::B1 + h];
+    const float4* w1 = reinterpret_cast<const float4*>(sp + Lay::W1 + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w1[q];
+      a = fmaf(w.x, y[4 * q], a);
+      a = fmaf(w.y, y[4 * q + 1], a);
+      a = fmaf(w.z, y[4 * q + 2], a);
+      a = fmaf(w.w, y[4 * q + 3], a);
+    }
+    const float gl = gelu_tanh_cc(a);
+    const float4* w2 = reinterpret_cast<const float4*>(sp + Lay::W2T + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w2[q];
+      o[4 * q] = fmaf(w.x, gl, o[4 * q]);
+      o[4 * q + 1] = fmaf(w.y, gl, o[4 * q + 1]);
+      o[4 * q + 2] = fmaf(w.z, gl, o[4 * q + 2]);
+      o[4 * q + 3] = fmaf(w.w, gl, o[4 * q + 3]);
+    }
+  }
+  const float* xr = rows + 3 * RS;   // layer scale + residual
+#pragma unroll
+  for (int c = 0; c < C; ++c) out[c] = fmaf(sp[Lay::GAMMA + c], o[c], xr[c]);
+}
+
+constexpr int SS_TOK = 128;              // output tokens per CTA
+constexpr int SS_THREADS = 160;          // >= SS_TOK + 12 (rows evaluated by the first Block)
+template <int C>
+struct SmallStageCfg {
+  static constexpr int RS = (C == 4) ? 4 : C + 4;
+  static constexpr int P = (SmallBlockLayout<C>::TOTAL + 3) & ~3;
+  static constexpr int ROWS = SS_TOK + 18;
+  static constexpr size_t SMEM = (3 * P + 2 * ROWS * RS) * sizeof(float);
+};
+
+// params0/1/2: SmallBlockLayout images of the stage's three Blocks.
+template <int C>
+__global__ void __launch_bounds__(SS_THREADS) stage_small_kernel(const float* Xin, float* Xout, int L, int M, const float* __restrict__ params0,
+                                                                 const float* __restrict__ params1, const float* __restrict__ params2) {
+  using Lay = SmallBlockLayout<C>;
+  using Cfg = SmallStageCfg<C>;
+  constexpr int RS = Cfg::RS, V = C / 4;
+  static_assert(Lay::TOTAL % 4 == 0, "parameter images are copied as 16-byte vectors");
+  extern __shared__ __align__(16) float smem_f[];
+  float* sp = smem_f;                                   // three parameter images
+  float* bufA = smem_f + 3 * Cfg::P;                    // rows tile0-9 .. tile0+SS_TOK+8
+  float* bufB = bufA + Cfg::ROWS * RS;
+
+  pdl_launch_dependents();
+  copy_const_to_smem<Lay::TOTAL / 4, SS_THREADS>(sp, params0, threadIdx.x);
+  copy_const_to_smem<Lay::TOTAL / 4, SS_THREADS>(sp + Cfg::P, params1, threadIdx.x);
+  copy_const_to_smem<Lay::TOTAL / 4, SS_THREADS>(sp + 2 * Cfg::P, params2, threadIdx.x);
+  pdl_wait();  // parameters are constants; activations of the previous kernel are read below (plain loads)
+  const int tile0 = blockIdx.x * SS_TOK;
+  {
+    constexpr int NV = Cfg::ROWS * V, PER = (NV + SS_THREADS - 1) / SS_THREADS;
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * SS_THREADS;
+      const int r = i / V, q = i - r * V;
+      const int g = tile0 - 9 + r;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < NV && g >= 0 && g < M) v[k] = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * SS_THREADS;
+      const int r = i / V, q = i - r * V;
+      if (i < NV) reinterpret_cast<float4*>(bufA + r * RS)[q] = v[k];
+    }
+  }
+  __syncthreads();
+  // Block k (k = 0, 1, 2) produces buffer rows 3(k+1) .. ROWS - 3(k+1) - 1  (buffer row r <-> token tile0 - 9 + r)
+  float* src = bufA;
+  float* dst = bufB;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    const int first = 3 * (k + 1), count = Cfg::ROWS - 6 * (k + 1);
+    if (static_cast<int>(threadIdx.x) < count) {
+      const int r = first + threadIdx.x;
+      const int tok = tile0 - 9 + r;
+      float o[C];
+      if (tok >= 0 && tok < M) {
+        small_block_token<C>(sp + k * Cfg::P, src + (r - 3) * RS, RS, tok % L, L, o);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = 0.f;
+      }
+      if (k < 2) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(dst + r * RS)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      } else if (tok < M) {
+        float* g = Xout + static_cast<size_t>(tok) * C;
+#pragma unroll
+        for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(g)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+    __syncthreads();
+    float* t = src; src = dst; dst = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ small Downsample
 // Packed parameters: lnw[Cin] | lnb[Cin] | w[Cout][2*Cin] (k index = tap * Cin + c) | b[Cout]
 template <int CIN>

@@ -140,7 +140,7 @@ def test_fused_and_unfused_paths_agree(tmp_path):
         "np.save(sys.argv[1], pr.cpu().numpy())\n")
     outs = {}
     settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_POST": "0", "A2M_FUSE_FFN": "0", "A2M_MID_TC": "0",
-                                           "A2M_FUSE_B256": "0"},
+                                           "A2M_FUSE_B256": "0", "A2M_FUSE_SMALL": "0"},
                 "ffn_only": {"A2M_FUSE_POST": "0"}, "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
     for name, env in settings.items():
         out = tmp_path / f"{name}.npy"
