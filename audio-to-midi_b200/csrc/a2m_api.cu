@@ -330,6 +330,7 @@ static thread_local bool tl_pdl = false;
 static unsigned g_pdl_mask = 0xffffffffu;
 static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Blocks as dwconv_ln + two GEMM launches
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
+static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
@@ -484,6 +485,8 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(block_mid_kernel<8>, MidBlockCfg<8>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_mid2_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(block_mid2_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(down_mid_kernel<16>, MidDownCfg<16>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(down_mid_kernel<32>, MidDownCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(dwconv_ln_kernel<256>, (DW_TOK + 6) * 256 * 4)) != cudaSuccess) return e;
@@ -926,8 +929,14 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
           const dim3 grid((M + BM_TOK - 1) / BM_TOK);
           switch (s) {
             case 1: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<8>, grid, dim3(BM_TOK), MidBlockCfg<8>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
-            case 2: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<16>, grid, dim3(BM_TOK), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
-            default: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<32>, grid, dim3(BM_TOK), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
+            case 2:
+              if (g_mid_two) add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<16>, dim3(std::min<unsigned>(grid.x, h->num_sms * bm2_ctas_per_sm<16>())), dim3(BM2_THREADS), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+              else add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<16>, grid, dim3(BM_TOK), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+              break;
+            default:
+              if (g_mid_two) add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<32>, dim3(std::min<unsigned>(grid.x, h->num_sms * bm2_ctas_per_sm<32>())), dim3(BM2_THREADS), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+              else add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<32>, grid, dim3(BM_TOK), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+              break;
           }
         } else
         switch (s) {
@@ -1343,6 +1352,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_MID_TWO")) g_mid_two = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
   return A2M_OK;
 }

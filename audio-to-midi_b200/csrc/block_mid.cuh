@@ -39,7 +39,8 @@ struct MidBlockCfg {
   static constexpr int X_BYTES = (BM_TOK + 6) * RS * 4;
   static constexpr uint32_t TMEM_COLS = N1 < 32 ? 32 : N1;   // D2 re-uses D1's columns (drained by step 4 before step 5 is issued)
   static constexpr int MIN_CTAS = C == 32 ? 4 : 6;
-  static constexpr size_t SMEM = 1024 + A_BYTES + ((W1_BYTES + W2_BYTES + 1023) / 1024) * 1024 + X_BYTES + P_TOTAL * 4 + 64;
+  static constexpr int STAT_BYTES = 2 * BM_TOK * 8;   // block_mid2_kernel: (sum, sum of squares) per row and half
+  static constexpr size_t SMEM = 1024 + A_BYTES + ((W1_BYTES + W2_BYTES + 1023) / 1024) * 1024 + X_BYTES + P_TOTAL * 4 + 64 + STAT_BYTES;
 };
 
 // Xin / Xout carry no __restrict__ / __ldg: read-only loads of activations may be hoisted above griddepcontrol.wait.
@@ -238,6 +239,223 @@ block_mid_kernel(const float* Xin, float* Xout, int L, int M, const float* __res
 }  // namespace a2m
 
 namespace a2m {
+
+// ------------------------------------------------------------------------------------------ two threads per token
+// block_mid_kernel with 256 threads: thread t and thread t + 128 share token t & 127 (TMEM lane = t & 127 for both: warps
+// w and w + 4 address the same TMEM quadrant) and split its channels / hidden units / output columns in halves, so every
+// per-token chain (depthwise taps, LayerNorm, GELU, epilogue) is half as long and twice as many warps are resident for
+// the same shared memory.  LayerNorm statistics: single pass (sum and sum of squares) exchanged once through shared memory.
+constexpr int BM2_THREADS = 256;
+#ifdef A2M_FFN_TIMING
+#define BM_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && C == 32) g_ffn_timing[(i)] = clock64(); } while (0)
+#else
+#define BM_STAMP(i) do { } while (0)
+#endif
+template <int C>
+constexpr int bm2_ctas_per_sm() { return MidBlockCfg<C>::MIN_CTAS == 6 ? 5 : MidBlockCfg<C>::MIN_CTAS; }
+
+template <int C>
+__global__ void __launch_bounds__(BM2_THREADS, MidBlockCfg<C>::MIN_CTAS == 6 ? 5 : MidBlockCfg<C>::MIN_CTAS)
+block_mid2_kernel(const float* Xin, float* Xout, int L, int M, const float* __restrict__ params, const uint4* __restrict__ wimg) {
+  using Cfg = MidBlockCfg<C>;
+  static_assert(C == 16 || C == 32, "two-thread variant: C in {16, 32}");
+  constexpr int V = C / 4, CH = C / 2, VH = CH / 4;     // channels per thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                  // A1, then A2
+  uint8_t* sW1 = sA + Cfg::A_BYTES;
+  uint8_t* sW2 = sW1 + Cfg::W1_BYTES;
+  float* sx = reinterpret_cast<float*>(sA + Cfg::A_BYTES + ((Cfg::W1_BYTES + Cfg::W2_BYTES + 1023) / 1024) * 1024);
+  float* sp = sx + (BM_TOK + 6) * Cfg::RS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp + Cfg::P_TOTAL);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float2* sStat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 64);   // [2 halves][128 rows] (sum, sum of squares)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp >> 2;                          // which half of the channels / columns
+  const int row = (warp & 3) * 32 + lane;              // token inside the tile == TMEM lane
+  const int ntiles = (M + BM_TOK - 1) / BM_TOK;
+
+  pdl_launch_dependents();
+  BM_STAMP(96);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  copy_const_to_smem<Cfg::P_TOTAL / 4, BM2_THREADS>(sp, params, threadIdx.x);
+  copy_const_to_smem<(Cfg::W1_BYTES + Cfg::W2_BYTES) / 16, BM2_THREADS>(sW1, wimg, threadIdx.x);
+  pdl_wait();  // parameters are constants; activations of the previous kernel are read below (plain loads)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;           // D1 columns 0 .. N1-1, then D2 columns 0 .. N2-1
+  const uint32_t t_row = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const int c0 = half * CH;                     // first channel of this thread
+  // persistent over tiles: barriers, TMEM and the parameter / weight images are set up once per CTA
+  uint32_t it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  const int tile0 = tile * BM_TOK;
+  if (it == 0) BM_STAMP(97);
+  {
+    constexpr int NV = (BM_TOK + 6) * V;
+    constexpr int PER = (NV + BM2_THREADS - 1) / BM2_THREADS;
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * BM2_THREADS;
+      const int r = i / V, q = i - r * V;
+      const int g = tile0 - 3 + r;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < NV && g >= 0 && g < M) v[k] = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + k * BM2_THREADS;
+      const int r = i / V, q = i - r * V;
+      if (i < NV) reinterpret_cast<float4*>(sx + r * Cfg::RS)[q] = v[k];
+    }
+  }
+  __syncthreads();
+  if (it == 0) BM_STAMP(98);
+  const int tok = tile0 + row;
+
+  // ---- depthwise k7 on this thread's CH channels, single-pass LayerNorm statistics shared with the partner thread
+  float y[CH];
+  {
+    const int l = tok % L;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) y[c] = sp[Cfg::P_DWB + c0 + c];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int ll = l + t - 3;
+      if (ll >= 0 && ll < L) {
+        const float* xr = sx + (row + t) * Cfg::RS + c0;
+#pragma unroll
+        for (int q = 0; q < VH; ++q) {
+          const float4 xv = reinterpret_cast<const float4*>(xr)[q];
+          const float4 wv = reinterpret_cast<const float4*>(sp + t * C + c0)[q];
+          y[4 * q] = fmaf(wv.x, xv.x, y[4 * q]);
+          y[4 * q + 1] = fmaf(wv.y, xv.y, y[4 * q + 1]);
+          y[4 * q + 2] = fmaf(wv.z, xv.z, y[4 * q + 2]);
+          y[4 * q + 3] = fmaf(wv.w, xv.w, y[4 * q + 3]);
+        }
+      }
+    }
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { sm += y[c]; sq = fmaf(y[c], y[c], sq); }
+    sStat[half * BM_TOK + row] = make_float2(sm, sq);
+  }
+  __syncthreads();
+  {
+    const float2 a = sStat[row], b = sStat[BM_TOK + row];
+    const float mean = (a.x + b.x) * (1.0f / C);
+    const float inv = rsqrtf(fmaxf((a.y + b.y) * (1.0f / C) - mean * mean, 0.f) + kLnEps);
+    const bool live = tok < M;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) y[c] = live ? (y[c] - mean) * inv * sp[Cfg::P_LNW + c0 + c] + sp[Cfg::P_LNB + c0 + c] : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < CH / 8; ++q)
+    *reinterpret_cast<uint4*>(sA + sw128_offset(row, c0 + 8 * q)) =
+        make_uint4(pack_bf16x2(y[8 * q], y[8 * q + 1]), pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
+                   pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (it == 0) BM_STAMP(99);
+  // ---- D1 = A1 . W1^T
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, Cfg::N1);
+    const uint64_t da = umma_desc_sw128(smem_u32(sA));
+    const uint64_t db = umma_desc_sw128(smem_u32(sW1));
+#pragma unroll
+    for (int k = 0; k < Cfg::K1 / 16; ++k)
+      umma_bf16(tmem_d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc1, k != 0 ? 1u : 0u);
+    umma_commit(&bars[0]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[0], it & 1);
+  tc_fence_after();
+  if (it == 0) BM_STAMP(100);
+
+  // ---- bias + GELU of this thread's C hidden units -> A2 row
+#pragma unroll
+  for (int j0 = 0; j0 < C; j0 += 16) {
+    const int h0 = half * C + j0;
+    uint32_t r[16];
+    tmem_ld_x16(tmem_d + t_row + h0, r);
+    tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      pk[j] = pack_bf16x2(gelu_tanh_fast(__uint_as_float(r[2 * j]) + sp[Cfg::P_B1 + h0 + 2 * j]),
+                          gelu_tanh_fast(__uint_as_float(r[2 * j + 1]) + sp[Cfg::P_B1 + h0 + 2 * j + 1]));
+    *reinterpret_cast<uint4*>(sA + sw128_offset(row, h0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(sA + sw128_offset(row, h0 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (it == 0) BM_STAMP(101);
+  // ---- D2 = A2 . (gamma W2)^T   (re-uses D1's columns: every thread has drained them)
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc2 = umma_idesc_bf16(128, Cfg::N2);
+    const uint64_t da = umma_desc_sw128(smem_u32(sA));
+    const uint64_t db = umma_desc_sw128(smem_u32(sW2));
+#pragma unroll
+    for (int k = 0; k < Cfg::K2 / 16; ++k)
+      umma_bf16(tmem_d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc2, k != 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], it & 1);
+  tc_fence_after();
+  if (it == 0) BM_STAMP(102);
+
+  // ---- + gamma b2 + x on this thread's CH output channels, in place in the token tile, then coalesced store
+  {
+    float* xr = sx + (row + 3) * Cfg::RS + c0;
+    uint32_t r[CH];
+    if constexpr (CH == 16) tmem_ld_x16(tmem_d + t_row + c0, r);
+    else tmem_ld_x8(tmem_d + t_row + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < VH; ++q) {
+      float4 v = reinterpret_cast<float4*>(xr)[q];
+      v.x += __uint_as_float(r[4 * q]) + sp[Cfg::P_B2 + c0 + 4 * q];
+      v.y += __uint_as_float(r[4 * q + 1]) + sp[Cfg::P_B2 + c0 + 4 * q + 1];
+      v.z += __uint_as_float(r[4 * q + 2]) + sp[Cfg::P_B2 + c0 + 4 * q + 2];
+      v.w += __uint_as_float(r[4 * q + 3]) + sp[Cfg::P_B2 + c0 + 4 * q + 3];
+      reinterpret_cast<float4*>(xr)[q] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int i = threadIdx.x; i < BM_TOK * V; i += BM2_THREADS) {
+    const int r = i / V, q = i - r * V;
+    const int g = tile0 + r;
+    if (g < M) reinterpret_cast<float4*>(Xout + static_cast<size_t>(g) * C)[q] = reinterpret_cast<const float4*>(sx + (r + 3) * Cfg::RS)[q];
+  }
+  tc_fence_before();
+  __syncthreads();   // the token tile and the accumulator columns are free for the next tile
+  tc_fence_after();
+  if (it == 0) BM_STAMP(103);
+  if (it == 1) BM_STAMP(104);
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(*tmem_slot);
+  }
+}
 
 // ------------------------------------------------------------------------------------------ Downsample, Cin in {16, 32}
 // Downsample (model.py:102-118): LayerNorm over the input channels of every token, then Conv1d(Cin -> 2 Cin, k = 2, s = 2),

@@ -48,3 +48,7 @@ print(f"block_fused<128>: pdl_wait passed {rel(113)}  dwconv+LN done {rel(114)} 
 for name, b in (("attn_global", 64), ("attn_local", 72)):
     t0 = t[b]
     print(f"{name}: pdl_wait passed {t[b+1]-t0}  loaded {t[b+2]-t0}  S ready {t[b+3]-t0}  softmax done {t[b+4]-t0}  O ready {t[b+5]-t0}  stored {t[b+6]-t0}")
+
+t0 = t[96]
+print("block_mid2<32>: tile loop entered %d  x tile in smem %d  dwconv+LN+A1 written %d  D1 ready %d  GELU+A2 written %d  D2 ready %d  tile 0 done %d  tile 1 done %d"
+      % tuple(t[i] - t0 for i in range(97, 105)))
