@@ -36,7 +36,7 @@ class MLMultiArrayWrapper3(C.Structure):
 EXPORTS = [
     "a2m_create", "a2m_destroy", "a2m_last_error", "a2m_load_weights", "a2m_workspace_bytes", "a2m_forward",
     "a2m_forward_host", "a2m_submit_host", "a2m_collect_host", "a2m_host_alloc", "a2m_host_free",
-    "a2m_last_launch_count", "a2m_window_count", "a2m_prepare_windows", "a2m_window_losses", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_read_timing", "a2m_debug_forward_tap", "a2m_debug_gemm",
+    "a2m_last_launch_count", "a2m_window_count", "a2m_prepare_windows", "a2m_window_losses", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_read_timing", "a2m_debug_gemm_pair", "a2m_debug_forward_tap", "a2m_debug_gemm",
     "a2m_train_init", "a2m_set_dropout", "a2m_param_count", "a2m_get_params", "a2m_set_lr_multipliers", "a2m_forward_train", "a2m_backward",
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",

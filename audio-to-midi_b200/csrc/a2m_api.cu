@@ -27,6 +27,7 @@
 #include "qkv_fused.cuh"
 #include "postattn_fused.cuh"
 #include "block256_fused.cuh"
+#include "gemm_pair.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_wgrad.cuh"
@@ -476,6 +477,8 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block256_fused_kernel, B6_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_pair_kernel<128>, gemm_pair_smem_bytes<128>())) != cudaSuccess) return e;
+  if ((e = set_smem(gemm_pair_kernel<256>, gemm_pair_smem_bytes<256>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_local_tc_kernel, AL_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, false>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
@@ -1691,6 +1694,22 @@ int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t 
   } else {
     CUDA_TRY(launch_gemm(block_n, GEMM_GENERIC, ta, tb, g, h->num_sms, static_cast<cudaStream_t>(stream)));
   }
+  return A2M_OK;
+}
+
+// CTA-pair (cta_group::2) GEMM experiment: D[M, N] fp32 = A[M, K] x W[N, K]^T; M % 256 == 0, N in {128, 256}, K % 64 == 0.
+int a2m_debug_gemm_pair(A2mHandle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* W, float* out32, void* stream) {
+  if (!h) return A2M_EINVAL;
+  if (M % 256 != 0 || K % 64 != 0 || (N != 128 && N != 256)) { h->err = "a2m_debug_gemm_pair: M % 256, K % 64, N in {128, 256}"; return A2M_EINVAL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUtensorMap ta, tb;
+  if (!make_tmap(h, &ta, A, M, K, K, 64, 128)) return A2M_ECUDA;
+  if (!make_tmap(h, &tb, W, N, K, K, 64, N / 2)) return A2M_ECUDA;
+  const dim3 grid(2 * (M / 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 128) gemm_pair_kernel<128><<<grid, GP_THREADS, gemm_pair_smem_bytes<128>(), st>>>(ta, tb, out32, N, M, K);
+  else gemm_pair_kernel<256><<<grid, GP_THREADS, gemm_pair_smem_bytes<256>(), st>>>(ta, tb, out32, N, M, K);
+  CUDA_TRY(cudaGetLastError());
   return A2M_OK;
 }
 

@@ -126,6 +126,9 @@ int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t 
 int a2m_set_use_graph(A2mHandle* h, int32_t enable);
 
 /* ---- test hooks (used by tests/ only) ------------------------------------------------------------ */
+/* CTA-pair (tcgen05 cta_group::2, cluster of two CTAs) GEMM used to prove the recipe that the fused transformer kernels
+ * will adopt: out32[M, N] = A[M, K] (bf16) x W[N, K]^T (bf16); M % 256 == 0, N in {128, 256}, K % 64 == 0. */
+int a2m_debug_gemm_pair(A2mHandle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* W, float* out32, void* stream);
 /* Phase timeline (clock64 stamps of CTA 0) of the last ffn_fused_kernel launch; only in builds compiled with
  * -DA2M_FFN_TIMING (tools/ffn_timeline.py), returns -1 in the product build. */
 int a2m_debug_read_timing(long long* out, int32_t n);

@@ -63,3 +63,26 @@ def test_gemm_strided_a(eng):
     o32, _ = debug_gemm(eng, 128, a, w, 16)
     ref = a.double().cpu().numpy() @ w.double().cpu().numpy().T
     assert np.abs(o32.cpu().numpy() - ref).max() < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (512, 128, 256), (1024, 256, 256), (256, 256, 512)])
+def test_cta_pair_gemm(M, N, K):
+    """tcgen05 cta_group::2 (gemm_pair.cuh): a cluster of two CTAs computes 256 rows, each CTA holding half of W."""
+    import ctypes as C
+    from audio_to_midi_b200 import _lib
+    from gpu_util import engine, make_model
+    m, _ = make_model(1)
+    eng = engine(m)
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A_ = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    f = eng.L.a2m_debug_gemm_pair
+    f.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f.restype = C.c_int
+    rc = f(eng.h, M, N, K, A_.data_ptr(), W.data_ptr(), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(eng.h, rc, "a2m_debug_gemm_pair")
+    torch.cuda.synchronize()
+    ref = A_.double() @ W.double().T
+    err = (out.double() - ref).abs().max().item()
+    assert err < 1e-3 * np.sqrt(K), err
