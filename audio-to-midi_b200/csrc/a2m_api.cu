@@ -333,6 +333,8 @@ static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Bloc
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
 static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
+static bool g_qkv_pair = false;  // A2M_QKV_PAIR=1: cta_group::2 qkv_pair_kernel instead of the single-CTA qkv_fused_kernel (correct, but
+                                 // measured 17.2 us against 13.2 us: its chunk period is 6.3-7.5 k cycles against 4.6 k)
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
@@ -475,6 +477,7 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(qkv_pair_kernel, QP_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block256_fused_kernel, B6_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(gemm_pair_kernel<128>, gemm_pair_smem_bytes<128>())) != cudaSuccess) return e;
@@ -1050,6 +1053,14 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         if (!make_tmap_t(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, Mt, 768, 768, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
         const float* lw = dev_ptr<float>(h, t.ln1w);
         const float* lb = dev_ptr<float>(h, t.ln1b);
+        if (g_qkv_pair) {
+          CUtensorMap twp;   // each CTA of a pair loads its 128 of a chunk's 256 rows of W
+          if (!make_tmap(h, &twp, dev_ptr<__nv_bfloat16>(h, t.wqkv), 768, kD, kD, 64, 128)) return false;
+          add_step(p, Meta{"qkv_pair_kernel", 0.0, 4.0 * Mt * kD + 2.0 * Mt * 768 + 2.0 * 768 * kD}, [=](cudaStream_t st) {
+            return launch_k(PF_FUSED, qkv_pair_kernel, dim3(Mt / FF_ROWS), dim3(QF_THREADS), QP_SMEM, st, twp, to,
+                            static_cast<const float*>(xt), Mt, lw, lb, rope_cos, rope_sin, kTP);
+          });
+        } else
         add_step(p, Meta{"qkv_fused_kernel", 0.0, 4.0 * Mt * kD + 2.0 * Mt * 768 + 2.0 * 768 * kD}, [=](cudaStream_t st) {
           return launch_k(PF_FUSED, qkv_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(QF_THREADS), QF_SMEM, st, tw, to,
                           static_cast<const float*>(xt), Mt, lw, lb, rope_cos, rope_sin, kTP);
@@ -1352,6 +1363,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_QKV_PAIR")) g_qkv_pair = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;

@@ -141,7 +141,8 @@ def test_fused_and_unfused_paths_agree(tmp_path):
     outs = {}
     settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_POST": "0", "A2M_FUSE_FFN": "0", "A2M_MID_TC": "0",
                                            "A2M_FUSE_B256": "0", "A2M_FUSE_SMALL": "0"},
-                "ffn_only": {"A2M_FUSE_POST": "0"}, "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
+                "ffn_only": {"A2M_FUSE_POST": "0"}, "qkv_pair": {"A2M_QKV_PAIR": "1"},
+                "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
     for name, env in settings.items():
         out = tmp_path / f"{name}.npy"
         res = subprocess.run([sys.executable, "-c", script, str(out)], env={**os.environ, **env}, capture_output=True, text=True,
@@ -152,3 +153,5 @@ def test_fused_and_unfused_paths_agree(tmp_path):
     for name in ("unfused", "ffn_only"):
         d = np.abs(outs[name] - outs["default"]).max()
         assert 0 < d < 2e-2, (name, d)
+    # the CTA-pair (tcgen05 cta_group::2) q|k|v kernel accumulates the same products in the same order
+    assert np.abs(outs["qkv_pair"] - outs["default"]).max() < 1e-3

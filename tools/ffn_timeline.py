@@ -52,3 +52,7 @@ for name, b in (("attn_global", 64), ("attn_local", 72)):
 t0 = t[96]
 print("block_mid2<32>: tile loop entered %d  x tile in smem %d  dwconv+LN+A1 written %d  D1 ready %d  GELU+A2 written %d  D2 ready %d  tile 0 done %d  tile 1 done %d"
       % tuple(t[i] - t0 for i in range(97, 105)))
+
+t0 = t[80]
+print("qkv (pair or single, whichever ran): setup+cluster sync %d  LN done %d  dfull chunks %s  epilogue done %d  after final cluster sync %d"
+      % (t[81] - t0, t[82] - t0, [t[104 + 2 * n] - t0 for n in range(3)], t[110] - t0, t[111] - t0))
