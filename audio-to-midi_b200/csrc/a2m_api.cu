@@ -332,6 +332,7 @@ static unsigned g_pdl_mask = 0xffffffffu;
 static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Blocks as dwconv_ln + two GEMM launches
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
 static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
+static bool g_local_bwd_tc = true;   // debug switch (A2M_LOCAL_BWD_TC=0): CUDA-core attn_local_bwd_kernel in the training backward
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_qkv_pair = false;  // A2M_QKV_PAIR=1: cta_group::2 qkv_pair_kernel instead of the single-CTA qkv_fused_kernel (correct, but
                                  // measured 17.2 us against 13.2 us: its chunk period is 6.3-7.5 k cycles against 4.6 k)
@@ -1369,6 +1370,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TWO")) g_mid_two = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_LOCAL_BWD_TC")) g_local_bwd_tc = std::atoi(e) != 0;
   return A2M_OK;
 }
 
