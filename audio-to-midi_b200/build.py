@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libaudio2midi_b200.so")
 SOURCES = ["a2m_api.cu", "modelutil.cpp"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "cnn_kernels.cuh", "attention.cuh", "block_fused.cuh", "block_mid.cuh", "ffn_fused.cuh", "qkv_fused.cuh", "postattn_fused.cuh", "block256_fused.cuh", "gemm_pair.cuh", "gemm_tc2.cuh", "gemm_wgrad.cuh", "attention_bwd.cuh", "train_kernels.cuh", "a2m_train.inc", "audio_prep.cuh", os.path.join("..", "..", "include", "a2m.h")]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "cnn_kernels.cuh", "attention.cuh", "block_fused.cuh", "block_mid.cuh", "ffn_fused.cuh", "qkv_fused.cuh", "postattn_fused.cuh", "block256_fused.cuh", "gemm_pair.cuh", "gemm_tc2.cuh", "gemm_wgrad.cuh", "attention_bwd.cuh", "train_kernels.cuh", "block_mid_bwd.cuh", "a2m_train.inc", "audio_prep.cuh", os.path.join("..", "..", "include", "a2m.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -33,6 +33,7 @@
 #include "gemm_wgrad.cuh"
 #include "attention_bwd.cuh"
 #include "train_kernels.cuh"
+#include "block_mid_bwd.cuh"
 
 using namespace a2m;
 
@@ -147,6 +148,7 @@ struct Weights {
   StemParams stem;
   size_t small_block[4][3];
   size_t down_p[5], down_w[5];        // down_mid_kernel (output stages 3, 4): lnw | lnb | bias, pre-swizzled bf16 weight tile
+  size_t mid_bw[4][3] = {};          // block_mid_bwd_kernel (stages 2-3, training): bf16 swizzled W1 | W2^T | W1^T | W2 tiles
   size_t mid_p[4][3], mid_w[4][3];   // block_mid_kernel (stages 1-3): fp32 parameter image, bf16 pre-swizzled W1 | gamma*W2 tiles
   size_t small_down[5];           // index = output stage 1..4
   BigBlockW big_block[kStages][21];
@@ -333,6 +335,7 @@ static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Bloc
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
 static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
 static bool g_local_bwd_tc = true;   // debug switch (A2M_LOCAL_BWD_TC=0): CUDA-core attn_local_bwd_kernel in the training backward
+static bool g_mid_bwd_tc = true;     // debug switch (A2M_MID_BWD_TC=0): CUDA-core block_small_bwd_kernel for stages 2-3
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_qkv_pair = false;  // A2M_QKV_PAIR=1: cta_group::2 qkv_pair_kernel instead of the single-CTA qkv_fused_kernel (correct, but
                                  // measured 17.2 us against 13.2 us: its chunk period is 6.3-7.5 k cycles against 4.6 k)
@@ -662,6 +665,21 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
               wmul[static_cast<size_t>(N1) * 64 + swz(n, k)] = gm.p[n];
             }
           w->mid_w[s][j] = ar->put(wimg, true, wmul);
+          if (train && s >= 2) {
+            // backward operands (block_mid_bwd.cuh): W1 [H][c] | W2^T [H][c] | W1^T [C][h] | W2 [C][h], no layer scale folded
+            std::vector<float> bimg(static_cast<size_t>(6 * C) * 64, 0.f);
+            for (int n = 0; n < H; ++n)
+              for (int k = 0; k < C; ++k) {
+                bimg[swz(n, k)] = w1.p[static_cast<size_t>(n) * C + k];
+                bimg[static_cast<size_t>(H) * 64 + swz(n, k)] = w2.p[static_cast<size_t>(k) * H + n];
+              }
+            for (int n = 0; n < C; ++n)
+              for (int k = 0; k < H; ++k) {
+                bimg[static_cast<size_t>(2 * H) * 64 + swz(n, k)] = w1.p[static_cast<size_t>(k) * C + n];
+                bimg[static_cast<size_t>(2 * H + C) * 64 + swz(n, k)] = w2.p[static_cast<size_t>(n) * H + k];
+              }
+            w->mid_bw[s][j] = ar->put_bf16(bimg);
+          }
         }
       } else {
         BigBlockW& bw = w->big_block[s][j];
@@ -1371,6 +1389,7 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_MID_TWO")) g_mid_two = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_LOCAL_BWD_TC")) g_local_bwd_tc = std::atoi(e) != 0;
+  if (const char* e = std::getenv("A2M_MID_BWD_TC")) g_mid_bwd_tc = std::atoi(e) != 0;
   return A2M_OK;
 }
 
