@@ -41,14 +41,18 @@ struct MidBwdCfg {
   static constexpr int NP = 14 * C;                               // dw 7C | dwb | lnw | lnb | b1 2C | b2 | gamma
   static constexpr int NACC = 12 * C + H;                         // dw 7C | dwb | lnw | lnb | b2 | gamma | b1
   static constexpr int RAW = 1024 + 3 * TILE + ((W_BYTES + 1023) / 1024) * 1024 + X_BYTES + (NP + NACC) * 4 + 64;
-  // at most two CTAs per SM (each allocates 256 TMEM columns)
-  static constexpr size_t SMEM = RAW < 80 * 1024 ? 80 * 1024 : RAW;
-  static constexpr uint32_t TMEM_COLS = 256;
-  static constexpr uint32_t COL_U = 0, COL_DH = 64, COL_DA = 128, COL_O = 160, COL_WG = 192;
+  // DA / O re-use the columns of U / DH (drained by step 4 before step 5 is issued); WG lives across tiles.
+  // C = 16: 128 TMEM columns, three CTAs per SM;  C = 32: 256 columns, two CTAs per SM (shared memory padded so that no
+  // more CTAs than the tensor memory can serve become resident -- a CTA spinning in tcgen05.alloc would never finish).
+  static constexpr int CTAS = C == 16 ? 3 : 2;
+  static constexpr int MIN_SMEM = C == 16 ? 58 * 1024 : 80 * 1024;
+  static constexpr size_t SMEM = RAW < MIN_SMEM ? MIN_SMEM : RAW;
+  static constexpr uint32_t TMEM_COLS = C == 16 ? 128 : 256;
+  static constexpr uint32_t COL_U = 0, COL_DH = H, COL_DA = 0, COL_O = C, COL_WG = 2 * H;
 };
 
 template <int C>
-__global__ void __launch_bounds__(MBB_THREADS, 2)
+__global__ void __launch_bounds__(MBB_THREADS, MidBwdCfg<C>::CTAS)
 block_mid_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int M, const float* __restrict__ params,
                      const uint4* __restrict__ wimg, float* __restrict__ gparams) {
   using Cfg = MidBwdCfg<C>;

@@ -624,6 +624,14 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
   for (int i = 0; i < TH; ++i)
 #pragma unroll
     for (int j = 0; j < TC; ++j) { accW1[i][j] = 0.f; accW2[i][j] = 0.f; }
+  // C = 4: the two 8 x 4 pointwise weight gradients are accumulated per thread in registers over all of its tokens
+  // (64 FMAs per token) and reduced over the CTA once, instead of one warp walking the staged rows of every tile
+  // (~2000 instructions per tile on the critical path of the other three warps).
+  constexpr bool REG_WG = (C == 4);
+  constexpr int RW = REG_WG ? H * C : 1;
+  float regW1[RW], regW2[RW];
+#pragma unroll
+  for (int i = 0; i < RW; ++i) { regW1[i] = 0.f; regW2[i] = 0.f; }
 
   for (int i = threadIdx.x; i < Lay::TOTAL; i += SBB_THREADS) sp[i] = __ldg(params + i);
   const int ntiles = (M + SBB_IN - 1) / SBB_IN;
@@ -681,15 +689,17 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
         da[c] = 0.f;
         o[c] = sp[Lay::B2 + c];
       }
+      if constexpr (!REG_WG) {
 #pragma unroll
-      for (int q = 0; q < V; ++q) {
-        *reinterpret_cast<uint2*>(sa + threadIdx.x * CS + 4 * q) =
-            make_uint2(pack_bf16x2(m * a[4 * q], m * a[4 * q + 1]), pack_bf16x2(m * a[4 * q + 2], m * a[4 * q + 3]));
-        *reinterpret_cast<uint2*>(sdg + threadIdx.x * CS + 4 * q) =
-            make_uint2(pack_bf16x2(m * dg2[4 * q], m * dg2[4 * q + 1]), pack_bf16x2(m * dg2[4 * q + 2], m * dg2[4 * q + 3]));
+        for (int q = 0; q < V; ++q) {
+          *reinterpret_cast<uint2*>(sa + threadIdx.x * CS + 4 * q) =
+              make_uint2(pack_bf16x2(m * a[4 * q], m * a[4 * q + 1]), pack_bf16x2(m * a[4 * q + 2], m * a[4 * q + 3]));
+          *reinterpret_cast<uint2*>(sdg + threadIdx.x * CS + 4 * q) =
+              make_uint2(pack_bf16x2(m * dg2[4 * q], m * dg2[4 * q + 1]), pack_bf16x2(m * dg2[4 * q + 2], m * dg2[4 * q + 3]));
+        }
       }
       float b1part = 0.f;   // this lane's share of the b1 gradient is reduced below, 4 hidden units at a time
-#pragma unroll 1
+#pragma unroll(REG_WG ? 2 : 1)
       for (int h0 = 0; h0 < H; h0 += 4) {
         float du4[4], gl4[4];
 #pragma unroll
@@ -712,8 +722,18 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
           du4[hh] = m * du;
           gl4[hh] = m * gl;
         }
-        *reinterpret_cast<uint2*>(sdu + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(du4[0], du4[1]), pack_bf16x2(du4[2], du4[3]));
-        *reinterpret_cast<uint2*>(sgl + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(gl4[0], gl4[1]), pack_bf16x2(gl4[2], gl4[3]));
+        if constexpr (REG_WG) {
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              regW1[(h0 + hh) * C + c] = fmaf(du4[hh], a[c], regW1[(h0 + hh) * C + c]);
+              regW2[(h0 + hh) * C + c] = fmaf(gl4[hh], dg2[c], regW2[(h0 + hh) * C + c]);
+            }
+        } else {
+          *reinterpret_cast<uint2*>(sdu + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(du4[0], du4[1]), pack_bf16x2(du4[2], du4[3]));
+          *reinterpret_cast<uint2*>(sgl + threadIdx.x * HS + h0) = make_uint2(pack_bf16x2(gl4[0], gl4[1]), pack_bf16x2(gl4[2], gl4[3]));
+        }
         // b1 gradient: sum over the warp's tokens of du for these 4 hidden units
         const float r = warp_vec_reduce<4>(du4, lane);
         if ((lane & 7) == 0) atomicAdd(&sacc[12 * C + h0 + (lane >> 3)], r);
@@ -799,12 +819,19 @@ __global__ void __launch_bounds__(SBB_THREADS) block_small_bwd_kernel(const floa
       for (int q = 0; q < V; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     }
     // weight gradients of the two pointwise convs: token-reduced outer products, 4 x 4 outputs per thread
-    if (threadIdx.x < NTILE) {
-      outer_tile<TH, TC, HS, CS>(sdu, sa, my_r0, my_c0, accW1);    // dW1[h][c]  += du[h] a[c]
-      outer_tile<TH, TC, HS, CS>(sgl, sdg, my_r0, my_c0, accW2);   // dW2t[h][c] += gelu(u)[h] dg2[c]
+    if constexpr (!REG_WG) {
+      if (threadIdx.x < NTILE) {
+        outer_tile<TH, TC, HS, CS>(sdu, sa, my_r0, my_c0, accW1);    // dW1[h][c]  += du[h] a[c]
+        outer_tile<TH, TC, HS, CS>(sgl, sdg, my_r0, my_c0, accW2);   // dW2t[h][c] += gelu(u)[h] dg2[c]
+      }
     }
   }
-  if (threadIdx.x < NTILE) {
+  if constexpr (REG_WG) {
+    static_assert(!REG_WG || RW == 32, "one butterfly per matrix");
+    const float r1 = warp_vec_reduce<RW>(regW1, lane), r2 = warp_vec_reduce<RW>(regW2, lane);
+    atomicAdd(gparams + Lay::W1 + lane, r1);     // flat index h * C + c == lane
+    atomicAdd(gparams + Lay::W2T + lane, r2);
+  } else if (threadIdx.x < NTILE) {
 #pragma unroll
     for (int i = 0; i < TH; ++i)
 #pragma unroll
