@@ -28,6 +28,19 @@
 
 namespace a2m {
 
+// gelu_tanh and its derivative with the hardware tanh (one MUFU instead of ex2 + rcp; the forward's gelu_tanh_fast):
+//   g = 0.5 x (1 + t),  dg = 0.5 (1 + t) + 0.5 x (1 - t^2) k (1 + 3 a x^2),  t = tanh(k (x + a x^3))
+__device__ __forceinline__ void gelu_tanh_grad_fast(float x, float* g, float* dg) {
+  const float k = 0.7978845608028654f, a = 0.044715f;
+  const float x2 = x * x;
+  const float u = k * x * fmaf(a, x2, 1.0f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hp = fmaf(0.5f, t, 0.5f);
+  *g = x * hp;
+  *dg = fmaf(0.5f * x * (k * fmaf(3.0f * a, x2, 1.0f)), fmaf(-t, t, 1.0f), hp);
+}
+
 constexpr int MBB_THREADS = 128;
 constexpr int MBB_IN = MBB_THREADS - 6;
 
@@ -219,7 +232,9 @@ block_mid_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int 
     tc_fence_after();
 
     // ---- 4: gl = gelu(u), du = DH * gelu'(u) -> T0 (du), T1 (gl); b1 gradient (sum over the inner tokens of du)
-#pragma unroll
+    // C = 32: the fully unrolled kernel is > 100 KB of SASS and stalls on instruction fetch (ncu: stall_no_instruction ~ 1.1
+    // warps per issue, profiles/r01f_block_mid_bwd_ncu.txt); the two large loop bodies are kept rolled there.
+#pragma unroll(C == 32 ? 1 : 2)
     for (int c0 = 0; c0 < H; c0 += 32) {
       uint32_t ru[32], rd[32];
       tmem_ld_x32(tmem + t_row + Cfg::COL_U + c0, ru);
@@ -230,8 +245,8 @@ block_mid_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int 
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float g0, g1, d0, d1;
-        gelu_tanh_grad(__uint_as_float(ru[2 * j]) + sp[P_B1 + c0 + 2 * j], &g0, &d0);
-        gelu_tanh_grad(__uint_as_float(ru[2 * j + 1]) + sp[P_B1 + c0 + 2 * j + 1], &g1, &d1);
+        gelu_tanh_grad_fast(__uint_as_float(ru[2 * j]) + sp[P_B1 + c0 + 2 * j], &g0, &d0);
+        gelu_tanh_grad_fast(__uint_as_float(ru[2 * j + 1]) + sp[P_B1 + c0 + 2 * j + 1], &g1, &d1);
         du[2 * j] = __uint_as_float(rd[2 * j]) * d0;
         du[2 * j + 1] = __uint_as_float(rd[2 * j + 1]) * d1;
         pg[j] = pack_bf16x2(g0, g1);
@@ -328,7 +343,7 @@ block_mid_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int 
 #pragma unroll
       for (int c = 0; c < C; ++c) g[c] = live ? inv * (da[c] - s1 - xhat[c] * s2) : 0.f;
       // depthwise-conv gradients: dw[t][c] += g[c] x[tok + t - 3][c], dwb[c] += g[c]
-#pragma unroll
+#pragma unroll(C == 32 ? 1 : 7)
       for (int t = 0; t < 7; ++t) {
         const int ll = l + t - 3;
         const float mt = (ll >= 0 && ll < L) ? m : 0.f;
