@@ -82,3 +82,31 @@ def test_validation_loss_and_hit_rate():
         assert set(d) == set(ref)
         # event metrics are threshold decisions: equal unless a probability sits within tolerance of a threshold
         assert abs(d["hit_rate"] - ref["hit_rate"]) < 0.2
+
+
+def test_config5_full_size_properties():
+    """BASELINE config 5 at full size -- 600 s clip, overlap 0.5 s -> 134 windows -> 30 175 stitched frames --
+    through size-independent properties: the window-partitioned run over 8 "ranks" (17 or 16 windows each) reproduces the single-process probabilities BIT FOR BIT (windows are independent, results do not depend
+    on the batch a window travels in), stitched frame count, and event extraction is idempotent through to_frame_events."""
+    import audio_to_midi_b200 as A
+    from audio_to_midi_b200 import infer as I
+    from gpu_util import make_model
+    from oracle import synth
+    model, _ = make_model(99, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    raw = np.asarray(synth.make_clip(600.0, 5), np.float32)
+    assert raw.shape == (2, 9_600_000)
+    events, stitched, probs = I.transcribe_clip(model, raw, overlap=0.5, max_batch=64)
+    assert probs.shape == (134, 250, 90)
+    assert stitched.shape == (30175, 90)
+    assert np.isfinite(probs).all() and probs.min() >= 0.0 and probs.max() <= 1.0
+    parts = []
+    for rank in range(8):
+        lo, hi = I.shard_windows(134, 8, rank)
+        assert hi - lo == (17 if rank < 6 else 16)
+        _, _, p = I.transcribe_clip(model, raw, overlap=0.5, max_batch=5, rank=rank, world_size=8)
+        assert p.shape[0] == hi - lo
+        parts.append(p)
+    assert np.array_equal(np.concatenate(parts), probs)
+    # extract_events(to_frame_events(e)) == e on the model's own output (oracle self-check, here at full size)
+    frames = A.modelutil.to_frame_events([events], stitched.shape[0])[0]
+    assert A.modelutil.extract_events(frames) == events or len(events) == 0
