@@ -38,6 +38,7 @@ EXPORTS = [
     "a2m_forward_host", "a2m_submit_host", "a2m_collect_host", "a2m_host_alloc", "a2m_host_free",
     "a2m_last_launch_count", "a2m_window_count", "a2m_prepare_windows", "a2m_window_losses", "a2m_profile_steps", "a2m_set_use_graph", "a2m_debug_read_timing", "a2m_debug_gemm_pair", "a2m_debug_forward_tap", "a2m_debug_gemm",
     "a2m_train_init", "a2m_set_dropout", "a2m_param_count", "a2m_get_params", "a2m_set_lr_multipliers", "a2m_forward_train", "a2m_backward",
+    "a2m_grad_bucket_count", "a2m_grad_bucket_range", "a2m_stream_wait_grad_bucket",
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
 ]
@@ -111,6 +112,12 @@ def lib() -> C.CDLL:
     L.a2m_forward_train.restype = C.c_int
     L.a2m_backward.argtypes = [vp, vp, f32, vp, vp, vp]
     L.a2m_backward.restype = C.c_int
+    L.a2m_grad_bucket_count.argtypes = [vp]
+    L.a2m_grad_bucket_count.restype = i32
+    L.a2m_grad_bucket_range.argtypes = [vp, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.a2m_grad_bucket_range.restype = C.c_int
+    L.a2m_stream_wait_grad_bucket.argtypes = [vp, i32, vp]
+    L.a2m_stream_wait_grad_bucket.restype = C.c_int
     L.a2m_adamw_step.argtypes = [vp, vp, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp]
     L.a2m_adamw_step.restype = C.c_int
     L.a2m_train_launch_count.argtypes = [vp]

@@ -216,6 +216,7 @@ struct Step {
   bool side = false;    // launch on the side stream, after everything enqueued on the main stream so far
   int rec_mark = -1;    // side steps: record completion mark k after this step
   int join_mark = -1;   // main steps: wait for completion mark k before this step (buffer re-use)
+  int bucket_event = -1;   // main steps: gradient bucket k of the caller's blob is final after this step (a2m_stream_wait_grad_bucket)
 };
 
 struct Plan {

@@ -1127,6 +1127,21 @@ __global__ void __launch_bounds__(256) grad_unpack_kernel(const float* __restric
   }
 }
 
+// The same for the destinations lo <= src[i] < hi only, with the gradient blob reached through a device pointer slot
+// (rewritten by every a2m_backward, so the captured backward graph does not bake the caller's pointer in).
+__global__ void __launch_bounds__(256) grad_unpack_range_kernel(const float* __restrict__ gpack, const int* __restrict__ src,
+                                                                float* const* __restrict__ grads_slot, size_t n, int lo, int hi) {
+  float* grads = *grads_slot;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    const int s = src[i];
+    if (s >= lo && s < hi) {
+      const float g = gpack[i];
+      if (g != 0.f) atomicAdd(grads + s, g);
+    }
+  }
+}
+__global__ void set_ptr_kernel(float** slot, float* p) { *slot = p; }
+
 // AdamW (optax.adamw as configured in train.py:646-726) followed by optax.clip_by_global_norm on the UPDATES
 // (train.py:726 chains the clip after the optimiser).  Pass 1: moments, raw update u, sum u^2 and a finite flag.
 // Pass 2: p += u * min(1, clip / ||u||).

@@ -170,10 +170,46 @@ class TrainEngine:
         self._keep = (audio, labels)   # the stem backward reads the audio asynchronously
         return logits
 
-    def allreduce_grads(self):
-        """Data-parallel gradient exchange (train.py:238-244 shards the batch over devices): NCCL all-reduce (sum)
-        over NVLink, then the mean over ranks.  No-op without an initialised process group."""
-        allreduce_mean_([self.grads, self.loss])
+    def grad_buckets(self):
+        """[(lo, hi)] element ranges of the gradient blob in the order they become final during a2m_backward: bucket 0 =
+        final norm + transformer + decoder (ready once the transformer backward has run), bucket 1 = the CNN (ready at the end)."""
+        out = []
+        for k in range(int(self.L.a2m_grad_bucket_count(self.h))):
+            lo, hi = C.c_size_t(), C.c_size_t()
+            _lib.check(self.h, self.L.a2m_grad_bucket_range(self.h, k, C.byref(lo), C.byref(hi)), "a2m_grad_bucket_range")
+            out.append((int(lo.value), int(hi.value)))
+        return out
+
+    def allreduce_grads(self, overlap: bool = True):
+        """Data-parallel gradient exchange (train.py:238-244 shards the batch over devices): NCCL all-reduce (sum) over
+        NVLink, then the mean over ranks; no-op without an initialised process group.  Bucketed and overlapped with the
+        backward: call it right after the last forward_backward of the step -- bucket 0 (79 % of the bytes) is
+        reduced on a communication stream as soon as a2m_backward's in-plan scatter has produced it, while the CNN backward
+        still runs on the compute stream; the CNN bucket and the loss follow on the compute stream."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        torch = self.torch
+        w = dist.get_world_size()
+        buckets = self.grad_buckets() if overlap else []
+        if len(buckets) == 2 and buckets[0][1] > buckets[0][0] and buckets[1][1] > buckets[1][0]:
+            main = torch.cuda.current_stream(self.tdev)
+            if getattr(self, "_comm", None) is None:
+                self._comm = torch.cuda.Stream(self.tdev)
+            comm = self._comm
+            _lib.check(self.h, self.L.a2m_stream_wait_grad_bucket(self.h, 0, C.c_void_p(comm.cuda_stream)), "a2m_stream_wait_grad_bucket")
+            tail = self.grads[buckets[0][0]:buckets[0][1]]
+            with torch.cuda.stream(comm):
+                dist.all_reduce(tail)
+                tail.mul_(1.0 / w)
+            head = self.grads[buckets[1][0]:buckets[1][1]]
+            dist.all_reduce(head)
+            head.mul_(1.0 / w)
+            dist.all_reduce(self.loss)
+            self.loss.mul_(1.0 / w)
+            main.wait_stream(comm)
+        else:
+            allreduce_mean_([self.grads, self.loss])
 
     def optimizer_step(self, lr: float, cfg: OptimizerConfig, grad_divisor: float = 1.0):
         self.step_count += 1
@@ -199,6 +235,59 @@ class TrainEngine:
         self.optimizer_step(lr, cfg, grad_divisor=grad_scale * steps)
         scaled_loss = self.loss / steps
         return scaled_loss / grad_scale, self.stats[1] == 0, scaled_loss
+
+    def train_pipelined(self, batches, rope_freqs: RopeFreqs, cfg: OptimizerConfig, lr_fn: Callable[[int], float], first_step: int = 1,
+                        dropout_rate: float = 0.0, key: int = 0, grad_scale: float = 1.0):
+        """Host-fed training loop (the reference's loop over a prefetching loader, train.py:340-380): `batches` is a sequence
+        of (audio, labels) page-locked host tensors.  The H2D copy of batch i+1 runs on a copy stream while step i computes
+        (two device buffers), and every step's loss is read back through a page-locked buffer that the host consumes one
+        step later, so the host never waits on the step it has just enqueued.  Returns the list of per-step losses."""
+        torch = self.torch
+        main = torch.cuda.current_stream(self.tdev)
+        n = len(batches)
+        if n == 0:
+            return []
+        x0, y0 = batches[0]
+        shapes = (tuple(x0.shape), tuple(y0.shape))
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe["shapes"] != shapes:     # copy stream, device buffers, events and the page-locked loss slot live with the engine
+            pipe = {"shapes": shapes, "copy": torch.cuda.Stream(self.tdev),
+                    "bufs": [(torch.empty(shapes[0], dtype=torch.float32, device=self.tdev),
+                              torch.empty(shapes[1], dtype=torch.float32, device=self.tdev)) for _ in range(2)],
+                    "events": [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(3)],
+                    "pin_loss": torch.empty(2, dtype=torch.float32).pin_memory()}
+            self._pipe = pipe
+        copy, bufs, pin_loss = pipe["copy"], pipe["bufs"], pipe["pin_loss"]
+        ready, consumed, loss_ev = pipe["events"]
+        copy.wait_stream(main)                            # buffers may still be read by steps of an earlier call
+
+        def prefetch(i):
+            b = i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(consumed[b])          # step i - 2 has finished reading this buffer
+                bufs[b][0].copy_(batches[i][0], non_blocking=True)
+                bufs[b][1].copy_(batches[i][1], non_blocking=True)
+                ready[b].record(copy)
+
+        losses = []
+        prefetch(0)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                prefetch(i + 1)
+            main.wait_event(ready[b])
+            loss, _valid, _ = self.training_step(bufs[b][0], bufs[b][1], rope_freqs, cfg, lr_fn(first_step + i), grad_scale=grad_scale,
+                                                 dropout_rate=dropout_rate, key=key)
+            consumed[b].record(main)
+            pin_loss[b:b + 1].copy_(loss.reshape(1), non_blocking=True)
+            loss_ev[b].record(main)
+            if i >= 1:
+                loss_ev[b ^ 1].synchronize()
+                losses.append(float(pin_loss[b ^ 1]))
+        loss_ev[(n - 1) & 1].synchronize()
+        losses.append(float(pin_loss[(n - 1) & 1]))
+        return losses
 
     # ---- parameter access
     def params_flat(self):

@@ -167,6 +167,14 @@ int a2m_forward_train(A2mHandle* h, const float* audio_dev, int32_t batch, const
  * loss_dev[0] += that value.  labels_dev [batch, 250, 90] fp32.  Gradient accumulation over minibatches
  * (train.py:283-293) = repeated forward_train / backward calls on the same grads_dev. */
 int a2m_backward(A2mHandle* h, const float* labels_dev, float scale, float* grads_dev, float* loss_dev, void* stream);
+/* Gradient buckets for an all-reduce that overlaps the backward (train.py:238-244 shards the batch; the exchange jit
+ * inserts there is one collective here).  Bucket 0 = final norm + transformer + decoder (the tail of the leaf order),
+ * final once the transformer backward has run; bucket 1 = the CNN, final when a2m_backward's work completes.
+ * a2m_grad_bucket_range: elements [*lo, *hi) of the gradient blob.  a2m_stream_wait_grad_bucket: `stream` waits until
+ * that range is final for the most recent a2m_backward (call after it returned). */
+int32_t a2m_grad_bucket_count(const A2mHandle* h);
+int a2m_grad_bucket_range(const A2mHandle* h, int32_t bucket, size_t* lo, size_t* hi);
+int a2m_stream_wait_grad_bucket(A2mHandle* h, int32_t bucket, void* stream);
 /* optax.adamw then clip_by_global_norm(clip_norm) on the updates, applied to the master parameters; gradients are
  * divided by grad_divisor first (train.py:314).  step counts from 1.  stats_dev (optional, 2 floats): squared norm of
  * the unclipped update, number of non-finite gradient entries (train.py:320-322 grads_valid == 0).  The data-parallel

@@ -184,3 +184,65 @@ def test_tensor_core_backward_kernels_agree_with_cuda_core_ones(tmp_path):
         differ += int(rel > 0)
     assert worst < 0.03, worst
     assert differ > 100, differ
+
+
+def test_train_pipelined_matches_step_by_step():
+    """TrainEngine.train_pipelined (copy stream + double-buffered inputs + lagged loss read-back) runs the same steps as
+    a plain loop of training_step on device-resident inputs: same per-step losses (the loss is summed with atomics, so to
+    rounding), same parameters afterwards."""
+    import train_util as U
+    from oracle import params as P
+    tree, audio, labels = U.setup(2)
+    rope = A.precompute_frequencies(64, 300)
+    cfg = T.OptimizerConfig()
+    lr = lambda i: 1e-3
+    batches = [(audio, labels), (audio[::-1].copy(), labels[::-1].copy()), (audio * np.float32(0.5), labels)]
+    m1 = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
+    e1 = T.TrainEngine(m1, 0)
+    ref = []
+    for i, (x, y) in enumerate(batches):
+        loss, valid, _ = e1.training_step(torch.tensor(x).cuda(), torch.tensor(y).cuda(), rope, cfg, lr(i + 1), dropout_rate=0.1, key=5)
+        ref.append(float(loss.item()))
+    p1 = e1.params_flat().cpu().numpy()
+    del e1
+    m2 = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
+    e2 = T.TrainEngine(m2, 0)
+    pinned = [(torch.tensor(x).pin_memory(), torch.tensor(y).pin_memory()) for x, y in batches]
+    got = e2.train_pipelined(pinned, rope, cfg, lr, first_step=1, dropout_rate=0.1, key=5)
+    p2 = e2.params_flat().cpu().numpy()
+    assert len(got) == 3
+    # gradients are reduced with atomics, and Adam's normalised update amplifies their rounding: a few 1e-4 per step
+    assert np.allclose(got, ref, rtol=2e-3), (got, ref)
+    assert np.abs(p1 - p2).max() < 5e-3 * max(1.0, np.abs(p1).max())
+
+
+def test_gradient_bucket_is_final_when_its_event_fires():
+    """SURVEY 8e (all-reduce bucketed and overlapped with the backward): bucket 0 of the gradient blob -- final norm,
+    transformer, decoder, the tail of the leaf order -- is scattered by a step INSIDE the backward graph and announced by an
+    event-record node.  A second stream that waits on it must see exactly the final values of that range while the CNN
+    backward is still running; the buckets tile the blob."""
+    import train_util as U
+    tree, audio, labels = U.setup(4)
+    m = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(__import__("oracle.params", fromlist=["flatten"]).flatten(tree))
+    eng = T.TrainEngine(m, 0)
+    rope = A.precompute_frequencies(64, 300)
+    buckets = eng.grad_buckets()
+    assert len(buckets) == 2 and buckets[1][0] == 0 and buckets[1][1] == buckets[0][0] and buckets[0][1] == eng.n_params
+    first_tail = min(o for p, o in zip(eng.paths, eng.offsets) if not p.startswith("layers."))
+    assert buckets[0][0] == first_tail
+    assert (buckets[0][1] - buckets[0][0]) > 0.75 * eng.n_params          # most of the bytes can overlap
+    x, y = torch.tensor(audio).cuda(), torch.tensor(labels).cuda()
+    side = torch.cuda.Stream()
+    for _ in range(3):                                                      # first call captures the graph, later ones replay it
+        eng.zero_grad()
+        eng.forward_backward(x, y, rope)
+        _lib.check(eng.h, eng.L.a2m_stream_wait_grad_bucket(eng.h, 0, C.c_void_p(side.cuda_stream)), "wait bucket")
+        with torch.cuda.stream(side):
+            snap = eng.grads[buckets[0][0]:].clone()
+            head_early = eng.grads[:buckets[0][0]].clone()
+        torch.cuda.synchronize()
+        final = eng.grads[buckets[0][0]:]
+        assert torch.equal(snap, final)
+        assert float(final.abs().max()) > 0
+    # the CNN bucket was still being produced when bucket 0 fired (otherwise nothing overlaps)
+    assert not torch.equal(head_early, eng.grads[:buckets[0][0]])
