@@ -16,6 +16,14 @@
 
 namespace a2m {
 
+// d/dx gelu_tanh(x) (the arithmetic of train_kernels.cuh gelu_tanh_grad, derivative only)
+__device__ __forceinline__ float gelu_tanh_deriv(float x) {
+  const float k = 0.7978845608028654f, a = 0.044715f;
+  const float u = k * (x + a * x * x * x);
+  const float s = __fdividef(1.0f, 1.0f + __expf(-2.0f * u));
+  return s + x * s * (1.0f - s) * 2.0f * k * (1.0f + 3.0f * a * x * x);
+}
+
 enum Gemm2Mode : int {
   G2_F32 = 0,   // [+bias] [gelu] [*gamma] [+resid (template)] -> fp32
   G2_BF16 = 1,  // [+bias] [gelu] -> bf16
@@ -39,7 +47,8 @@ template <int BN, int MODE, bool RESID>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
-  static_assert(!RESID || MODE == G2_F32, "residual add is an fp32-output feature");
+  // RESID: G2_F32 -- fp32 residual tile added in place;  G2_BF16 -- bf16 pre-activation tile u, out = acc * gelu'(u)
+  static_assert(!RESID || MODE == G2_F32 || MODE == G2_BF16, "the staged second operand exists for the fp32 and plain bf16 epilogues");
   constexpr int STAGES = g2_stages<BN>();
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -178,11 +187,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t ck = 0;
         int m_blk, n_blk;
         for (int it = 0; tile_coords(it, m_blk, n_blk); ++it) {
-          for (int c = 0; c < BN / 32; ++c, ++ck) {
+          constexpr int CW = (MODE == G2_F32) ? 32 : 64;   // columns per 128-byte staging row
+          for (int c = 0; c < BN / CW; ++c, ++ck) {
             const uint32_t cb = ck % G2_NCH, cph = (ck / G2_NCH) & 1;
             mbar_wait(&bar_cempty[cb], cph ^ 1);
             mbar_arrive_expect_tx(&bar_cfull[cb], G2_CHUNK);
-            tma_load_2d(sStage + cb * G2_CHUNK, &tmR, &bar_cfull[cb], n_blk * BN + c * 32, m_blk * GEMM_BM);
+            tma_load_2d(sStage + cb * G2_CHUNK, &tmR, &bar_cfull[cb], n_blk * BN + c * CW, m_blk * GEMM_BM);
           }
         }
       }
@@ -314,6 +324,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
                 }
+                if constexpr (RESID) {
+                  // the staged tile holds u (bf16) where the result goes: multiply by gelu'(u), then overwrite in place
+                  if (half == 0) mbar_wait(&bar_cfull[cb], (ck / G2_NCH) & 1);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint4 uu = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + q) ^ rsw) << 4));
+                    const uint32_t w4[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                      v[8 * q + 2 * t] *= gelu_tanh_deriv(__uint_as_float(w4[t] << 16));
+                      v[8 * q + 2 * t + 1] *= gelu_tanh_deriv(__uint_as_float(w4[t] & 0xffff0000u));
+                    }
+                  }
+                }
               } else if (col0 < g.rope_cols) {  // rope.py:43-52, pairs (2i, 2i+1), i = (col % 64) / 2
                 constexpr int kPairsPerHalf = 16;  // output chunks start at multiples of 64 columns
 #pragma unroll
@@ -352,6 +376,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_2d(&tmC, sStage + cb * G2_CHUNK, ocol0, row0);
             bulk_commit();
             bulk_wait_read<1>();
+            if constexpr (RESID)
+              if (ck > 0) mbar_arrive(&bar_cempty[(ck - 1) % G2_NCH]);
           }
           ++ck;
         }
