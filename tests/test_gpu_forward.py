@@ -155,3 +155,21 @@ def test_fused_and_unfused_paths_agree(tmp_path):
         assert 0 < d < 2e-2, (name, d)
     # the CTA-pair (tcgen05 cta_group::2) q|k|v kernel accumulates the same products in the same order
     assert np.abs(outs["qkv_pair"] - outs["default"]).max() < 1e-3
+
+
+def test_batch_invariance_bitwise():
+    """Windows are independent (infer.py:40 is a pure vmap): the probabilities of a window must not depend on the batch it
+    travels in -- bit for bit, across batch sizes that change every kernel's grid (97 = one call vs 64 + 33 vs 97 x 1's
+    first and last).  This is the property the window-partitioned multi-GPU paths (configs 3 and 5) rest on."""
+    from oracle import synth
+    model, _ = make_model(4321, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    rope = A.precompute_frequencies(64, 300)
+    audio = torch.tensor(synth.make_windows_fast(97, 77)).cuda()
+    lg, pr = model.predict(None, audio, rope)
+    lg_a, pr_a = model.predict(None, audio[:64], rope)
+    lg_b, pr_b = model.predict(None, audio[64:], rope)
+    assert torch.equal(pr, torch.cat([pr_a, pr_b])) and torch.equal(lg, torch.cat([lg_a, lg_b]))
+    for k in (0, 96):
+        _, p1 = model.predict(None, audio[k], rope)
+        assert torch.equal(p1, pr[k])
+    assert float(pr.std()) > 1e-3
