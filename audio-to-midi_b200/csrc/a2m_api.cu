@@ -148,6 +148,7 @@ struct Weights {
   StemParams stem;
   size_t small_block[4][3];
   size_t down_p[5], down_w[5];        // down_mid_kernel (output stages 3, 4): lnw | lnb | bias, pre-swizzled bf16 weight tile
+  size_t down_bw[5] = {};            // down_mid_bwd_kernel (Cin = 16, 32, training): bf16 swizzled W^T tile
   size_t mid_bw[4][3] = {};          // block_mid_bwd_kernel (stages 2-3, training): bf16 swizzled W1 | W2^T | W1^T | W2 tiles
   size_t mid_p[4][3], mid_w[4][3];   // block_mid_kernel (stages 1-3): fp32 parameter image, bf16 pre-swizzled W1 | gamma*W2 tiles
   size_t small_down[5];           // index = output stage 1..4
@@ -624,6 +625,14 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
             for (int k = 0; k < 2 * Cin; ++k)
               wimg[static_cast<size_t>(n) * 64 + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = wk[static_cast<size_t>(n) * 2 * Cin + k];
           w->down_w[s] = ar->put_bf16(wimg);
+          if (train) {
+            // backward operand (down_mid_bwd_kernel): W^T as 2*Cin rows [k][o] of 64 swizzled elements
+            std::vector<float> timg(static_cast<size_t>(2 * Cin) * 64, 0.f);
+            for (int k = 0; k < 2 * Cin; ++k)
+              for (int o = 0; o < C; ++o)
+                timg[static_cast<size_t>(k) * 64 + (((o >> 3) ^ (k & 7)) << 3) + (o & 7)] = wk[static_cast<size_t>(o) * 2 * Cin + k];
+            w->down_bw[s] = ar->put_bf16(timg);
+          }
         }
       } else {
         w->big_down[s].lnw = ar->put_f32(vec(lw));

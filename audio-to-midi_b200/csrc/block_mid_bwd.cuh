@@ -434,4 +434,216 @@ block_mid_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------ narrow Downsample backward
+// Backward of Downsample (model.py:102-118) for CIN in {16, 32} on tcgen05.  Forward (down_mid_kernel): n = [LN(x_2t) | LN(x_2t+1)]
+// (K2 = 2 CIN values), y = W n + b.  downsample_small_bwd_kernel spends 2 K2 COUT FMAs per output token on the CUDA cores
+// (85 / 155 us per launch).  Here thread t owns output token tile0 + t == TMEM lane t (no halo):
+//   1  x pair and dY row straight from global memory (each thread reads two contiguous 4 K2-byte / 4 COUT-byte runs)
+//   2  xhat, inv of both tokens (kept); n -> bf16 row of TN; dY -> bf16 row of TDY; validity -> column 0 of TONE
+//   3  tcgen05  DN [128 x K2] = dY W                                   (A = TDY K-major, B = W^T rows [k][o])
+//               WG [128 x 80] += dY^T [n | 1]                          (A = TDY MN-major, B = TN | TONE MN-major, N = 64 + 16:
+//               rows 0..COUT-1 x columns 0..K2-1 = dW[o][k], column 64 = db[o]; accumulated in TMEM over the CTA's tiles)
+//   4  thread t: LayerNorm backward of both tokens out of TMEM -> dX rows; dlnw / dlnb accumulated in registers
+// wimg: bf16 W^T as K2 rows of 64 swizzled elements ([k][o], a2m_api.cu pack_weights, train only).
+template <int CIN>
+struct DownMidBwdCfg {
+  static constexpr int COUT = 2 * CIN, K2 = 2 * CIN;
+  static constexpr int TILE = 128 * 128;
+  static constexpr int W_BYTES = K2 * 128;
+  static constexpr int RAW = 1024 + 3 * TILE + W_BYTES + 2 * CIN * 4 + 64;
+  static constexpr size_t SMEM = RAW < 80 * 1024 ? 80 * 1024 : RAW;   // at most two CTAs per SM (256 TMEM columns each)
+  static constexpr uint32_t TMEM_COLS = 256;
+  static constexpr uint32_t COL_DN = 0, COL_WG = 64;    // WG: 80 columns
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(MBB_THREADS, 2)
+down_mid_bwd_kernel(const float* X, const float* dY, float* dX, int M_out, const float* __restrict__ params,
+                    const uint4* __restrict__ wimg, float* __restrict__ gparams) {
+  using Cfg = DownMidBwdCfg<CIN>;
+  using Lay = SmallDownLayout<CIN>;
+  static_assert(CIN == 16 || CIN == 32, "tensor-core narrow Downsample backward: CIN in {16, 32}");
+  constexpr int COUT = Cfg::COUT, K2 = Cfg::K2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sDY = smem;                       // [128 tok][COUT]   A of DN (K-major) and of WG (MN-major)
+  uint8_t* sN = sDY + Cfg::TILE;             // [128 tok][K2]     B of WG, columns 0..63
+  uint8_t* sOne = sN + Cfg::TILE;            // [128 tok][col 0 = valid]   B of WG, columns 64..79
+  uint8_t* sWT = sOne + Cfg::TILE;           // [K2 rows][COUT]   B of DN
+  float* sln = reinterpret_cast<float*>(sWT + Cfg::W_BYTES);   // lnw | lnb
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sln + 2 * CIN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  const uint32_t t_row = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < 2 * CIN; i += MBB_THREADS) sln[i] = __ldg(params + Lay::LNW + i);   // lnw | lnb are contiguous
+  copy_const_to_smem<Cfg::W_BYTES / 16, MBB_THREADS>(sWT, wimg, threadIdx.x);
+  for (int i = threadIdx.x; i < 3 * Cfg::TILE / 16; i += MBB_THREADS) reinterpret_cast<uint4*>(sDY)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  constexpr uint32_t idesc_dn = umma_idesc_bf16(128, K2);
+  constexpr uint32_t idesc_wg = umma_idesc_bf16_abmn(128, 80);
+  float glw[CIN], glb[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) { glw[c] = 0.f; glb[c] = 0.f; }
+
+  const int ntiles = (M_out + MBB_THREADS - 1) / MBB_THREADS;
+  uint32_t it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int tok = tile * MBB_THREADS + row;
+    const bool valid = tok < M_out;
+    const int tokc = min(tok, M_out - 1);
+    // ---- 1, 2
+    float xh[K2], inv[2];
+    {
+      const float4* src = reinterpret_cast<const float4*>(X + static_cast<size_t>(tokc) * K2);
+#pragma unroll
+      for (int q = 0; q < K2 / 4; ++q) {
+        const float4 v = src[q];
+        xh[4 * q] = v.x; xh[4 * q + 1] = v.y; xh[4 * q + 2] = v.z; xh[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) mean += xh[t * CIN + c];
+        mean *= (1.0f / CIN);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) { xh[t * CIN + c] -= mean; var += xh[t * CIN + c] * xh[t * CIN + c]; }
+        inv[t] = rsqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xh[t * CIN + c] *= inv[t];
+      }
+      const float mv = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int q = 0; q < K2 / 8; ++q) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = (8 * q + j) % CIN;
+          a[j] = mv * (xh[8 * q + j] * sln[c] + sln[CIN + c]);
+        }
+        *reinterpret_cast<uint4*>(sN + sw128_offset(row, 8 * q)) =
+            make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+      }
+      const float4* dsrc = reinterpret_cast<const float4*>(dY + static_cast<size_t>(tokc) * COUT);
+#pragma unroll
+      for (int q = 0; q < COUT / 8; ++q) {
+        const float4 d0 = dsrc[2 * q], d1 = dsrc[2 * q + 1];
+        *reinterpret_cast<uint4*>(sDY + sw128_offset(row, 8 * q)) =
+            make_uint4(pack_bf16x2(mv * d0.x, mv * d0.y), pack_bf16x2(mv * d0.z, mv * d0.w), pack_bf16x2(mv * d1.x, mv * d1.y),
+                       pack_bf16x2(mv * d1.z, mv * d1.w));
+      }
+      *reinterpret_cast<uint4*>(sOne + sw128_offset(row, 0)) = make_uint4(valid ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 in column 0
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- 3
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(smem_u32(sDY)), db = umma_desc_sw128(smem_u32(sWT));
+#pragma unroll
+      for (int k = 0; k < COUT / 16; ++k)
+        umma_bf16(tmem + Cfg::COL_DN, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc_dn, k != 0 ? 1u : 0u);
+      // A: one 64-wide MN block (dY; the instruction's second block of 64 M rows reads TN: those accumulator rows are never flushed)
+      const uint64_t wa = umma_desc_sw128_mn(smem_u32(sDY), Cfg::TILE), wb = umma_desc_sw128_mn(smem_u32(sN), Cfg::TILE);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tmem + Cfg::COL_WG, umma_desc_advance_k(wa, k * 2048), umma_desc_advance_k(wb, k * 2048), idesc_wg, (it | k) != 0 ? 1u : 0u);
+      umma_commit(&bars[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], it & 1);
+    tc_fence_after();
+    // ---- 4: LayerNorm backward of the two input tokens
+    {
+      float* dst = dX + static_cast<size_t>(tokc) * K2;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float dn[CIN];
+#pragma unroll
+        for (int c0 = 0; c0 < CIN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tmem + t_row + Cfg::COL_DN + t * CIN + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dn[c0 + j] = __uint_as_float(r[j]);
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float d = dn[c];                 // zero for invalid tokens (their dY row was zeroed)
+          glw[c] += d * xh[t * CIN + c];
+          glb[c] += d;
+          dn[c] = d * sln[c];
+          s1 += dn[c];
+          s2 += dn[c] * xh[t * CIN + c];
+        }
+        s1 *= (1.0f / CIN);
+        s2 *= (1.0f / CIN);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < CIN / 4; ++q) {
+            float4 o;
+            o.x = inv[t] * (dn[4 * q] - s1 - xh[t * CIN + 4 * q] * s2);
+            o.y = inv[t] * (dn[4 * q + 1] - s1 - xh[t * CIN + 4 * q + 1] * s2);
+            o.z = inv[t] * (dn[4 * q + 2] - s1 - xh[t * CIN + 4 * q + 2] * s2);
+            o.w = inv[t] * (dn[4 * q + 3] - s1 - xh[t * CIN + 4 * q + 3] * s2);
+            reinterpret_cast<float4*>(dst + t * CIN)[q] = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // every thread has drained DN and the products have read the tiles: the next tile may overwrite both
+  }
+
+  // ---- flush
+  if (it > 0) {
+    // WG lane o (< COUT): columns 0..K2-1 = dW[o][k], column 64 = db[o]
+    uint32_t r[32];
+#pragma unroll
+    for (int c0 = 0; c0 < K2; c0 += 32) {
+      tmem_ld_x32(tmem + t_row + Cfg::COL_WG + c0, r);
+      tmem_ld_wait();
+      if (row < COUT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(gparams + Lay::W + row * K2 + c0 + j, __uint_as_float(r[j]));
+      }
+    }
+    uint32_t rb[16];
+    tmem_ld_x16(tmem + t_row + Cfg::COL_WG + 64, rb);
+    tmem_ld_wait();
+    if (row < COUT) atomicAdd(gparams + Lay::B + row, __uint_as_float(rb[0]));
+  }
+  {
+    const float r1 = warp_vec_reduce<CIN>(glw, lane), r2 = warp_vec_reduce<CIN>(glb, lane);
+    if ((lane % (32 / CIN)) == 0) {
+      atomicAdd(gparams + Lay::LNW + vec_reduce_channel<CIN>(lane), r1);
+      atomicAdd(gparams + Lay::LNB + vec_reduce_channel<CIN>(lane), r2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  }
+}
+
 }  // namespace a2m
