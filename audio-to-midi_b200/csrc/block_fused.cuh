@@ -132,9 +132,10 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       // depthwise conv of the 8 tokens of the pass, then their LayerNorm statistics jointly (warp_sum8_all)
       float y[TPP][PER];
+      const int l_first = (tile0 + r0) % L;   // one runtime modulo per pass instead of one per token (~22 instructions each)
 #pragma unroll
       for (int i = 0; i < TPP; ++i) {
-        const int l = (tile0 + r0 + i) % L;
+        const int l = l_first + i - ((l_first + i >= L) ? L : 0);
 #pragma unroll
         for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
 #pragma unroll

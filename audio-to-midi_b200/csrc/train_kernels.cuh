@@ -385,13 +385,15 @@ __global__ void __launch_bounds__(DwBwd<C>::THREADS) dwconv_ln_bwd_kernel(const 
       __syncthreads();
     }
     // phase A: g rows tile0-3 .. tile0+TOK+2
-    for (int lr = warp; lr < AR; lr += DWB_THREADS / 32) {
+    // position inside the window of this warp's rows: one runtime modulo per tile and phase, then l += NW (mod L) per row
+    int la = (tile0 - 3 + warp + L) % L;
+    for (int lr = warp; lr < AR; lr += DWB_THREADS / 32, la += DWB_THREADS / 32, la -= (la >= L) ? L : 0) {
       const int tok = tile0 - 3 + lr;
       float g[PER];
 #pragma unroll
       for (int j = 0; j < PER; ++j) g[j] = 0.f;
       if (tok >= 0 && tok < M) {
-        const int l = tok % L;
+        const int l = la;
         float y[PER], xr[7][PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) y[j] = bias[j];
@@ -446,10 +448,11 @@ __global__ void __launch_bounds__(DwBwd<C>::THREADS) dwconv_ln_bwd_kernel(const 
     }
     __syncthreads();
     // phase B: dX[m] = dOut[m] + sum_t w[t] g[m - t + 3]  (conv positions inside the same window only)
-    for (int lr = warp; lr < TOK; lr += DWB_THREADS / 32) {
+    int lb = (tile0 + warp) % L;
+    for (int lr = warp; lr < TOK; lr += DWB_THREADS / 32, lb += DWB_THREADS / 32, lb -= (lb >= L) ? L : 0) {
       const int tok = tile0 + lr;
       if (tok >= M) break;
-      const int l = tok % L;
+      const int l = lb;
       float acc[PER];
       RM::load(sdo + lr * C, lane, acc);
 #pragma unroll

@@ -161,6 +161,8 @@ def test_batch_invariance_bitwise():
     """Windows are independent (infer.py:40 is a pure vmap): the probabilities of a window must not depend on the batch it
     travels in -- bit for bit, across batch sizes that change every kernel's grid (97 = one call vs 64 + 33 vs 97 x 1's
     first and last).  This is the property the window-partitioned multi-GPU paths (configs 3 and 5) rest on."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model
     from oracle import synth
     model, _ = make_model(4321, gamma_mode="active", decoder_gain=4.0, trained_like=True)
     rope = A.precompute_frequencies(64, 300)
