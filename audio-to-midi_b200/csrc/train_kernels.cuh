@@ -1147,6 +1147,31 @@ __global__ void __launch_bounds__(256) grad_unpack_range_kernel(const float* __r
 }
 __global__ void set_ptr_kernel(float** slot, float* p) { *slot = p; }
 
+// Chunked variants: only the packed tensors the backward kernels actually write (about a third of the packed elements --
+// every weight also exists as transposed / folded / re-laid-out copies that never receive gradients) are zeroed before and
+// scattered after the backward.  chunks[i] = (first packed element, count <= 1024).
+__global__ void __launch_bounds__(256) grad_zero_chunks_kernel(float* __restrict__ gpack, const int2* __restrict__ chunks, int n_chunks) {
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int2 ch = chunks[c];
+    for (int i = threadIdx.x; i < ch.y; i += 256) gpack[ch.x + i] = 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) grad_unpack_chunks_kernel(const float* __restrict__ gpack, const int* __restrict__ src,
+                                                                 float* const* __restrict__ grads_slot, const int2* __restrict__ chunks,
+                                                                 int n_chunks, int lo, int hi) {
+  float* grads = *grads_slot;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int2 ch = chunks[c];
+    for (int i = threadIdx.x; i < ch.y; i += 256) {
+      const int s = src[ch.x + i];
+      if (s >= lo && s < hi) {
+        const float g = gpack[ch.x + i];
+        if (g != 0.f) atomicAdd(grads + s, g);
+      }
+    }
+  }
+}
+
 // AdamW (optax.adamw as configured in train.py:646-726) followed by optax.clip_by_global_norm on the UPDATES
 // (train.py:726 chains the clip after the optimiser).  Pass 1: moments, raw update u, sum u^2 and a finite flag.
 // Pass 2: p += u * min(1, clip / ||u||).

@@ -23,3 +23,8 @@ for _ in range(2):
     eng.forward_backward(audio, labels, rope)
 torch.cuda.synchronize()
 print("launches:", eng.launch_count(), "loss", float(eng.loss.item()))
+if len(sys.argv) > 2:   # also one optimizer step (AdamW + clip + re-pack): python tools/ncu_target_train.py 64 opt
+    cfg = T.OptimizerConfig()
+    for _ in range(2):
+        eng.optimizer_step(1e-4, cfg)
+    torch.cuda.synchronize()
