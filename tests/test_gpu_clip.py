@@ -110,3 +110,22 @@ def test_config5_full_size_properties():
     # the event list is the C++ eventizer's: lexicographically sorted (common.rs:142), attacks inside the clip, velocity 7
     assert events == sorted(events)
     assert all(0 <= a < stitched.shape[0] and 0 <= k < 90 and d >= 1 and v == 7 for a, k, d, v in events)
+
+
+def test_predict_and_stitch_host_windows():
+    """infer.py:37-44 (predict_and_stitch) on host windows in several ragged batches (4 + 4 + 2): the pipelined host path
+    returns the same probabilities as one device-resident call, bit for bit, and the stitched track of modelutil."""
+    import audio_to_midi_b200 as A
+    from audio_to_midi_b200 import infer as I
+    from gpu_util import make_model
+    from oracle import synth
+    model, _ = make_model(99, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    wins = synth.make_windows_fast(10, 21)
+    probs, stitched, dpf = I.predict_and_stitch(model, None, wins, 5.0, overlap=0.5, max_batch=4)
+    _, ref = model.predict(None, torch.tensor(wins).cuda(), A.precompute_frequencies(64, 300))
+    assert probs.shape == (10, 250, 90) and abs(dpf - 0.02) < 1e-12
+    assert np.array_equal(probs, ref.cpu().numpy())
+    assert np.array_equal(stitched, A.modelutil.stitch_probs(probs, 0.5, 0.02))
+    # single batch: the plain call path
+    probs1, _, _ = I.predict_and_stitch(model, None, wins[:3], 5.0, overlap=0.5, max_batch=4)
+    assert np.array_equal(probs1, probs[:3])
