@@ -19,6 +19,7 @@
 namespace a2m {
 
 constexpr int AGB_THREADS = 256;
+constexpr int AGBG_THREADS = 512;            // attn_global_bwd_kernel: four warps per TMEM quadrant (32 key columns / 16 accumulator columns each)
 constexpr int AGB_TILE = 128 * 64 * 2;               // 16 KB: one 128-row tile of a [rows][64] bf16 operand
 constexpr int AGB_OPER = 2 * AGB_TILE;               // 32 KB: 256 rows
 constexpr int AGB_PS = 2 * 128 * 64 * 2;             // 32 KB: P or dS tile [128 q][128 keys] as two k-blocks of 64 keys
@@ -31,7 +32,7 @@ constexpr uint32_t AGB_C_S = 0, AGB_C_DP = 128, AGB_C_DK = 256, AGB_C_DV = 320, 
 // tmQ: q||c buffer [B*256, ldq], tmK / tmV: k||v buffer, tmDO: dO [B*256, 256]; all box {64, 256}.
 // lse [B*256, 4] fp32 (natural log of the row's softmax denominator, including the running max);
 // O, dO row-major bf16 with leading dimension ldo.
-__global__ void __launch_bounds__(AGB_THREADS, 1)
+__global__ void __launch_bounds__(AGBG_THREADS, 1)
 attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                        const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, int ldo,
@@ -52,7 +53,7 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant; which 64 of a tile's 128 columns
+  const int quad = warp & 3, qtr = warp >> 2;    // TMEM lane quadrant; which 32 of a tile's 128 key columns (16 of an accumulator's 64)
   const int row = quad * 32 + lane;              // row inside a 128-row tile
   const uint32_t t_row = static_cast<uint32_t>(quad * 32) << 16;
 
@@ -144,20 +145,20 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     Lv[i] = __ldg(lse + grow * ATT_HEADS + h) * 1.4426950408889634f;   // log2 domain
   }
 
-  // inverse RoPE + bf16 store of a 64-column accumulator (this thread: row `r_in_win`, columns half*32 .. +31)
+  // inverse RoPE + bf16 store of a 64-column accumulator (this thread: row `r_in_win`, columns 16 qtr .. + 15)
   auto store_rot = [&](uint32_t tcol, int r_in_win, __nv_bfloat16* dst_base, int ld, int col0, bool rotate) {
-    uint32_t r[32];
-    tmem_ld_x32(tmem + t_row + tcol + half * 32, r);
+    uint32_t r[16];
+    tmem_ld_x16(tmem + t_row + tcol + qtr * 16, r);
     tmem_ld_wait();
-    float v[32];
+    float v[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
     const bool real = r_in_win < ATT_T;
     if (rotate && real) {
-      const float4* cp = reinterpret_cast<const float4*>(rope_cos + r_in_win * 32 + half * 16);
-      const float4* sp = reinterpret_cast<const float4*>(rope_sin + r_in_win * 32 + half * 16);
+      const float4* cp = reinterpret_cast<const float4*>(rope_cos + r_in_win * 32 + qtr * 8);
+      const float4* sp = reinterpret_cast<const float4*>(rope_sin + r_in_win * 32 + qtr * 8);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         const float4 cs = __ldg(cp + j), sn = __ldg(sp + j);
         const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
@@ -168,9 +169,9 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
       }
     }
-    __nv_bfloat16* dst = dst_base + (static_cast<size_t>(b) * ATT_TP + r_in_win) * ld + col0 + h * ATT_HD + half * 32;
+    __nv_bfloat16* dst = dst_base + (static_cast<size_t>(b) * ATT_TP + r_in_win) * ld + col0 + h * ATT_HD + qtr * 16;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       uint4 o;
       o.x = real ? pack_bf16x2_att(v[8 * q], v[8 * q + 1]) : 0u;
       o.y = real ? pack_bf16x2_att(v[8 * q + 2], v[8 * q + 3]) : 0u;
@@ -196,9 +197,8 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     const bool qreal = i * 128 + row < ATT_T;
     const float Dr = Dv[i], Lr = Lv[i];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = half * 64 + c * 32;     // key column inside the tile
+    {
+      const int col0 = qtr * 32;               // key column inside the tile
       uint32_t rs[32], rp[32];
       tmem_ld_x32(tmem + t_row + AGB_C_S + col0, rs);
       tmem_ld_x32(tmem + t_row + AGB_C_DP + col0, rp);
@@ -221,13 +221,13 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         pp[t] = pack_bf16x2_att(p2[0], p2[1]);
         ps[t] = pack_bf16x2_att(d2[0], d2[1]);
       }
-      // [128 q][64 keys] k-block `half`, 128B-swizzled rows; this thread's 32 columns = chunks 4c .. 4c+3
-      uint8_t* bp = sP + half * (128 * 128);
-      uint8_t* bs = sDS + half * (128 * 128);
+      // [128 q][64 keys] k-block qtr / 2, 128B-swizzled rows; this thread's 32 columns = chunks 4 (qtr & 1) .. + 3
+      uint8_t* bp = sP + (qtr >> 1) * (128 * 128);
+      uint8_t* bs = sDS + (qtr >> 1) * (128 * 128);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        *reinterpret_cast<uint4*>(bp + sw128_offset(row, c * 32 + 8 * q)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
-        *reinterpret_cast<uint4*>(bs + sw128_offset(row, c * 32 + 8 * q)) = make_uint4(ps[4 * q], ps[4 * q + 1], ps[4 * q + 2], ps[4 * q + 3]);
+        *reinterpret_cast<uint4*>(bp + sw128_offset(row, (qtr & 1) * 32 + 8 * q)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+        *reinterpret_cast<uint4*>(bs + sw128_offset(row, (qtr & 1) * 32 + 8 * q)) = make_uint4(ps[4 * q], ps[4 * q + 1], ps[4 * q + 2], ps[4 * q + 3]);
       }
     }
     fence_proxy_async_smem();
