@@ -72,6 +72,17 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // RoPE rows of this thread's two output rows (row, 128 + row), its 8 pairs: constants, fetched before the dependency wait
+  float4 pre_c[2][2], pre_s[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int pos = min(i * 128 + row, ATT_T - 1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      pre_c[i][j] = __ldg(reinterpret_cast<const float4*>(rope_cos + pos * 32 + qtr * 8) + j);
+      pre_s[i][j] = __ldg(reinterpret_cast<const float4*>(rope_sin + pos * 32 + qtr * 8) + j);
+    }
+  }
   pdl_wait();
 
   constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128);        // S, dP: both K-major
@@ -155,11 +166,10 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
     const bool real = r_in_win < ATT_T;
     if (rotate && real) {
-      const float4* cp = reinterpret_cast<const float4*>(rope_cos + r_in_win * 32 + qtr * 8);
-      const float4* sp = reinterpret_cast<const float4*>(rope_sin + r_in_win * 32 + qtr * 8);
+      const int which = r_in_win >> 7;   // r_in_win is row or 128 + row
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float4 cs = __ldg(cp + j), sn = __ldg(sp + j);
+        const float4 cs = which ? pre_c[1][j] : pre_c[0][j], sn = which ? pre_s[1][j] : pre_s[0][j];
         const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
