@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU per step")
     ap.add_argument("--train-batch", type=int, default=64, help="training windows per GPU per step")
-    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
