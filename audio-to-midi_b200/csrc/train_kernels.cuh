@@ -601,10 +601,11 @@ __device__ __forceinline__ void outer_tile(const __nv_bfloat16* sA, const __nv_b
   }
 }
 
-// C = 4: capped at 128 registers for four CTAs per SM (104 -> 83 us; five CTAs at C = 8 and a larger grid for the narrow
-// Downsample backward were measured neutral / slower)
+// C <= 8: capped at 128 registers for four CTAs per SM (C = 4: 104 -> 83 us; C = 8 needs 105 and must not be given more --
+// with a minimum of one CTA the compiler took more registers and the kernel went from 102 to 143 us; five CTAs at C = 8 and
+// a larger grid for the narrow Downsample backward were measured neutral / slower)
 template <int C>
-__global__ void __launch_bounds__(SBB_THREADS, C == 4 ? 4 : 1) block_small_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int M,
+__global__ void __launch_bounds__(SBB_THREADS, C <= 8 ? 4 : 0) block_small_bwd_kernel(const float* Xin, const float* dOut, float* dX, int L, int M,
                                                                       const float* __restrict__ params, float* __restrict__ gparams) {
   using Lay = SmallBlockLayout<C>;
   using SM = SmallBwdSmem<C>;
