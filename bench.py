@@ -101,6 +101,44 @@ def cpu_forward_rate(n_windows: int, iters: int, threads: int):
     return n_windows * WINDOW_S / best, best
 
 
+def cpu_train_rate(n_windows: int, iters: int, threads: int):
+    """Forward + backward (torch autograd) of the oracle's loss_fn (train.py:39-62) on the host cores: the training-step
+    counterpart of cpu_forward_rate, on a bounded sample.  Optimizer time is not included (it is < 1 % on the CPU).
+    Returns (samples per second, seconds per iteration)."""
+    import torch
+    from oracle import model_torch as T
+    from oracle import params as P
+    from oracle import synth
+    torch.set_num_threads(threads)
+    tree = T.to_torch(P.init_params(SEED), requires_grad=False)
+    leaves = []
+
+    def mark(t):
+        if isinstance(t, dict):
+            return {k: mark(v) for k, v in t.items()}
+        if isinstance(t, list):
+            return [mark(v) for v in t]
+        if t.dtype.is_floating_point:
+            t = t.clone().requires_grad_(True)
+            leaves.append(t)
+        return t
+
+    tree = mark(tree)
+    audio, labels = synth.make_windows(n_windows, SEED, with_labels=True)
+    audio, labels = torch.tensor(audio), torch.tensor(labels)
+    times = []
+    for it in range(iters + 1):
+        for t in leaves:
+            t.grad = None
+        t0 = time.perf_counter()
+        loss, _ = T.loss_fn(tree, audio, labels)
+        loss.backward()
+        if it > 0:   # the first pass warms the thread pool and the allocator
+            times.append(time.perf_counter() - t0)
+    best = statistics.median(times)
+    return n_windows / best, best
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The JAX reference cannot be imported
     (no jax/equinox in the image, /root/reference absent on the GPU box), so this times the oracle port."""
@@ -220,7 +258,15 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
     dt = float(t.item())
     value = world * B * K / (ms / 1e3)
     peaks = _peaks()
+    cpu_train = None
+    if rank == 0:
+        cores = len(os.sched_getaffinity(0))
+        rate, sec = cpu_train_rate(4, 2, cores)
+        cpu_train = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                     "sample": f"forward + backward of 4 windows x 2 iterations ({sec:.2f} s each), torch autograd of the oracle's loss_fn "
+                               f"(oracle/model_torch.py); JAX reference not installable (SURVEY F1)"}
     return {
+        "cpu_baseline": cpu_train,
         "metric": "train samples/sec", "value": value, "unit": "samples/s", "ms_per_step": ms / K, "steps": K, "warmup": W,
         "batch_per_gpu": B, "global_batch": B * world, "scaling": "weak",
         "step": "forward with tape + backward + gradient all-reduce (NCCL) + AdamW/clip + weight re-pack (train.py:259-332)",
