@@ -41,7 +41,19 @@ EXPORTS = [
     "a2m_grad_bucket_count", "a2m_grad_bucket_range", "a2m_stream_wait_grad_bucket",
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
+    "a2m_create_ex", "a2m_submit_host_ex", "a2m_event_metrics", "a2m_set_params", "a2m_get_opt_state", "a2m_set_opt_state",
+    "a2m_backward_dlogits", "a2m_allreduce_grads", "a2m_comm_unique_id", "a2m_comm_init", "a2m_comm_get", "a2m_comm_destroy",
 ]
+
+
+class A2mConfig(C.Structure):   # include/a2m.h
+    _fields_ = [("device", C.c_int32), ("num_stages", C.c_int32), ("dims", C.c_int32 * 8), ("depths", C.c_int32 * 8),
+                ("cnn_hidden_expansion_x2", C.c_int32), ("num_transformer_layers", C.c_int32), ("num_transformer_heads", C.c_int32),
+                ("attention_size", C.c_int32), ("compressed_attention_kv_size", C.c_int32), ("transformer_intermediate", C.c_int32),
+                ("use_graph", C.c_int32), ("use_pdl", C.c_int32)]
+
+
+F32, F16 = 0, 1
 
 
 def lib() -> C.CDLL:
@@ -136,6 +148,30 @@ def lib() -> C.CDLL:
     L.free_midi_events.restype = None
     L.a2m_to_frame_events.argtypes = [C.POINTER(MidiEvent), C.c_int64, C.c_int64, vp]
     L.a2m_to_frame_events.restype = C.c_int
+    L.a2m_create_ex.argtypes = [C.POINTER(A2mConfig), C.POINTER(vp)]
+    L.a2m_create_ex.restype = C.c_int
+    L.a2m_submit_host_ex.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32]
+    L.a2m_submit_host_ex.restype = C.c_int
+    L.a2m_event_metrics.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.a2m_event_metrics.restype = C.c_int
+    L.a2m_set_params.argtypes = [vp, vp, vp]
+    L.a2m_set_params.restype = C.c_int
+    L.a2m_get_opt_state.argtypes = [vp, vp, vp, vp]
+    L.a2m_get_opt_state.restype = C.c_int
+    L.a2m_set_opt_state.argtypes = [vp, vp, vp, vp]
+    L.a2m_set_opt_state.restype = C.c_int
+    L.a2m_backward_dlogits.argtypes = [vp, vp, vp, vp]
+    L.a2m_backward_dlogits.restype = C.c_int
+    L.a2m_allreduce_grads.argtypes = [vp, vp, vp]
+    L.a2m_allreduce_grads.restype = C.c_int
+    L.a2m_comm_unique_id.argtypes = [vp]
+    L.a2m_comm_unique_id.restype = C.c_int
+    L.a2m_comm_init.argtypes = [vp, vp, i32, i32]
+    L.a2m_comm_init.restype = C.c_int
+    L.a2m_comm_get.argtypes = [vp]
+    L.a2m_comm_get.restype = vp
+    L.a2m_comm_destroy.argtypes = [vp]
+    L.a2m_comm_destroy.restype = C.c_int
     _lib = L
     return L
 

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libaudio2midi_b200.so")
 SOURCES = ["a2m_api.cu", "modelutil.cpp"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "cnn_kernels.cuh", "attention.cuh", "block_fused.cuh", "block_mid.cuh", "ffn_fused.cuh", "qkv_fused.cuh", "postattn_fused.cuh", "block256_fused.cuh", "gemm_pair.cuh", "gemm_tc2.cuh", "gemm_wgrad.cuh", "attention_bwd.cuh", "train_kernels.cuh", "block_mid_bwd.cuh", "a2m_train.inc", "audio_prep.cuh", os.path.join("..", "..", "include", "a2m.h")]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "cnn_kernels.cuh", "attention.cuh", "block_fused.cuh", "block_mid.cuh", "ffn_fused.cuh", "qkv_fused.cuh", "postattn_fused.cuh", "block256_fused.cuh", "gemm_pair.cuh", "gemm_tc2.cuh", "gemm_wgrad.cuh", "attention_bwd.cuh", "train_kernels.cuh", "block_mid_bwd.cuh", "a2m_train.inc", "audio_prep.cuh", "event_metrics.cuh", os.path.join("..", "..", "include", "a2m.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -24,23 +24,37 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if missing or older than its sources; returns its path."""
+    """Compile the CUDA library if missing or older than its sources; returns its path.  Serialised by a file lock and
+    written through a temporary name, so that the ranks of a torchrun launch never compile into (or load) a half-written
+    library: the first rank builds, the others wait and find it up to date."""
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libaudio2midi_b200.so (there is no fallback path)")
     os.makedirs(OUT_DIR, exist_ok=True)
-    extra = os.environ.get("A2M_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DA2M_FFN_TIMING for the in-kernel timeline
-    cmd = [nvcc, *NVCC_FLAGS, *extra, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while this one waited
+                return LIB
+            extra = os.environ.get("A2M_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DA2M_FFN_TIMING for the in-kernel timeline
+            tmp = LIB + f".tmp{os.getpid()}"
+            cmd = [nvcc, *NVCC_FLAGS, *extra, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl", "-o", tmp]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

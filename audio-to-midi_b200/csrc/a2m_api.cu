@@ -4,6 +4,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time (nccl_api below), never linked
 
 #include <algorithm>
 #include <cmath>
@@ -15,6 +17,7 @@
 #include <map>
 #include <set>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,6 +38,7 @@
 #include "attention_bwd.cuh"
 #include "train_kernels.cuh"
 #include "block_mid_bwd.cuh"
+#include "event_metrics.cuh"
 
 using namespace a2m;
 
@@ -146,7 +150,6 @@ struct TLayerW {
 };
 
 struct Weights {
-  StemParams stem;
   size_t small_block[4][3];
   size_t down_p[5], down_w[5];        // down_mid_kernel (output stages 3, 4): lnw | lnb | bias, pre-swizzled bf16 weight tile
   size_t down_bw[5] = {};            // down_mid_bwd_kernel (Cin = 16, 32, training): bf16 swizzled W^T tile
@@ -159,7 +162,7 @@ struct Weights {
   TLayerW tl[2 * kNumTL];         // 2*i local, 2*i+1 global
   size_t dlnw, dlnb, dw, db;      // decoder: bf16 [128, 256] zero padded, fp32 [128]
   size_t dwt;                     // training: bf16 [256, 128]
-  size_t stem_img;                // training: fp32 w[4][2][5] | b[4] | lnw[4] | lnb[4]  (stem_train_kernel)
+  size_t stem_img;                // fp32 w[4][2][5] | b[4] | lnw[4] | lnb[4]  (stem_kernel, stem_bwd_kernel)
   bool folded_kv = false;         // tl[i].wqkv is valid (plain inference load)
 };
 
@@ -253,17 +256,18 @@ struct A2mHandle {
   int last_launches = 0;
   // host path: two slots so that the copies of one batch overlap the compute of the other
   struct Slot {
-    float* dev_audio = nullptr;
-    float* dev_out = nullptr;     // logits then probs
-    float* pin_audio = nullptr;   // staging, used only when the caller's buffers are pageable
-    float* pin_out = nullptr;
-    int cap = 0;
+    uint8_t* dev_audio = nullptr; // fp32 or f16 windows
+    uint8_t* dev_out = nullptr;   // logits (fp32, optional) then probs (fp32 or f16)
+    uint8_t* pin_audio = nullptr; // staging, used only when the caller's buffers are pageable
+    uint8_t* pin_out = nullptr;
+    int cap = 0;                  // windows the buffers were sized for (at 4 bytes per element)
     cudaStream_t copy = nullptr;
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
     bool pending = false;
     int B = 0;
-    float* user_logits = nullptr;
-    float* user_probs = nullptr;
+    void* user_logits = nullptr;
+    void* user_probs = nullptr;
+    size_t logits_bytes = 0, probs_bytes = 0;
     bool out_direct = false;
   } slots[2];
   float* pin_rope = nullptr;
@@ -271,7 +275,11 @@ struct A2mHandle {
   std::vector<float> rope_host_cache;
   cudaStream_t own_stream = nullptr;
   TrainState* train = nullptr;   // training path (a2m_train.inc)
+  bool train_configured = false; // dynamic-smem opt-in of the training kernels done on this handle's device
   void* clip_stats = nullptr;    // device ClipStats of a2m_prepare_windows
+  float* em_pred = nullptr;      // a2m_event_metrics: rasterised predictions when the caller does not want them
+  size_t em_pred_elems = 0;
+  ncclComm_t comm = nullptr;     // a2m_comm_init (data-parallel training); owned by the handle
 };
 
 namespace {
@@ -581,16 +589,10 @@ void pack_weights(const LeafMap& m, Weights* w, Arena* ar, bool train) {
     const auto& cb = leaf(m, p + "conv.bias", {4, 1});
     const auto& lw = leaf(m, p + "norm.weight", {4});
     const auto& lb = leaf(m, p + "norm.bias", {4});
-    std::memcpy(w->stem.w, cw.p, sizeof(float) * 40);
-    std::memcpy(w->stem.b, cb.p, sizeof(float) * 4);
-    std::memcpy(w->stem.ln_w, lw.p, sizeof(float) * 4);
-    std::memcpy(w->stem.ln_b, lb.p, sizeof(float) * 4);
-    if (train) {
-      std::vector<float> img = vec(cw);
-      auto app = [&](const std::vector<float>& v) { img.insert(img.end(), v.begin(), v.end()); };
-      app(vec(cb)); app(vec(lw)); app(vec(lb));
-      w->stem_img = ar->put_f32(img);
-    }
+    std::vector<float> img = vec(cw);
+    auto app = [&](const std::vector<float>& v) { img.insert(img.end(), v.begin(), v.end()); };
+    app(vec(cb)); app(vec(lw)); app(vec(lb));
+    w->stem_img = ar->put_f32(img);
   }
   for (int s = 0; s < kStages; ++s) {
     const int C = kDims[s], H = 2 * C;
@@ -1275,8 +1277,9 @@ int ensure_own_ws(A2mHandle* h, int B) {
   return A2M_OK;
 }
 
-int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, const float* sin_in, int max_pos,
-                float* logits, float* probs, void* workspace, size_t ws_bytes, cudaStream_t stream,
+// audio: fp32, or IEEE binary16 when audio_f16; outputs: any of logits / probs (fp32) / probs16 (binary16) may be null
+int run_forward(A2mHandle* h, const void* audio, bool audio_f16, int B, const float* cos_in, const float* sin_in, int max_pos,
+                float* logits, float* probs, __half* probs16, void* workspace, size_t ws_bytes, cudaStream_t stream,
                 const char* tap_label, float* tap_out, size_t tap_elems) {
   if (!h->loaded) { h->err = "a2m_forward before a2m_load_weights"; return A2M_ESTATE; }
   if (B <= 0 || !audio || !cos_in || !sin_in) { h->err = "bad forward arguments"; return A2M_EINVAL; }
@@ -1305,7 +1308,11 @@ int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, co
                            cudaMemcpyDeviceToDevice, stream));
   {
     const int total = B * kLens[0];
-    stem_kernel<<<(total + 255) / 256, 256, 0, stream>>>(audio, p->ws.X[0], A2M_WINDOW_SAMPLES, kLens[0], total, h->w.stem);
+    const float* sprm = dev_ptr<float>(h, h->w.stem_img);
+    if (audio_f16)
+      stem_kernel<__half><<<(total + 255) / 256, 256, 0, stream>>>(static_cast<const __half*>(audio), p->ws.X[0], A2M_WINDOW_SAMPLES, kLens[0], total, sprm);
+    else
+      stem_kernel<float><<<(total + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(audio), p->ws.X[0], A2M_WINDOW_SAMPLES, kLens[0], total, sprm);
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
@@ -1360,7 +1367,7 @@ int run_forward(A2mHandle* h, const float* audio, int B, const float* cos_in, co
     GemmArgs g = gemm_args(B * kTP, 128, kD);
     g.bias = dev_ptr<float>(h, h->w.db);
     g.rows_per_window = kTP; g.valid_rows = kT; g.valid_cols = A2M_VOCAB;
-    g.logits = logits; g.probs = probs;
+    g.logits = logits; g.probs = probs; g.probs16 = probs16;
     CUDA_TRY(launch_gemm(128, GEMM_DECODER, p->dec_tmA, p->dec_tmB, g, h->num_sms, stream));
     ++launches;
   }
@@ -1416,6 +1423,25 @@ int a2m_create(int device, A2mHandle** out) {
   return A2M_OK;
 }
 
+// OutputSequenceGenerator(conf, key) (model.py:680-738) as a C call: the kernels are specialised for the reference's default
+// model_config (model.py:20-34); any other architecture is refused with A2M_EINVAL rather than run wrongly.
+int a2m_create_ex(const A2mConfig* cfg, A2mHandle** out) {
+  if (!out) return A2M_EINVAL;
+  *out = nullptr;
+  if (!cfg) return A2M_EINVAL;
+  bool ok = cfg->num_stages == kStages && cfg->num_transformer_layers == kNumTL && cfg->num_transformer_heads == ATT_HEADS &&
+            cfg->attention_size == 64 && cfg->compressed_attention_kv_size == 64 && cfg->transformer_intermediate == kFF &&
+            cfg->cnn_hidden_expansion_x2 == 4;
+  for (int s = 0; ok && s < kStages; ++s) ok = cfg->dims[s] == kDims[s] && cfg->depths[s] == kDepths[s];
+  if (!ok) return A2M_EINVAL;
+  int rc = a2m_create(cfg->device, out);
+  if (rc == A2M_OK && *out) {
+    if (cfg->use_graph >= 0) (*out)->use_graph = cfg->use_graph != 0;
+    if (cfg->use_pdl >= 0) (*out)->use_pdl = cfg->use_pdl != 0;
+  }
+  return rc;
+}
+
 void a2m_destroy(A2mHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -1439,7 +1465,9 @@ void a2m_destroy(A2mHandle* h) {
   if (h->dev_rope_in) cudaFree(h->dev_rope_in);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->clip_stats) cudaFree(h->clip_stats);
+  if (h->em_pred) cudaFree(h->em_pred);
   train_free(h);
+  comm_free(h);
   delete h;
 }
 
@@ -1493,7 +1521,7 @@ int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float
                 void* stream) {
   if (!h) return A2M_EINVAL;
   if (!logits_dev || !probs_dev) { h->err = "null output"; return A2M_EINVAL; }
-  return run_forward(h, audio_dev, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, logits_dev, probs_dev, workspace_dev,
+  return run_forward(h, audio_dev, false, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, logits_dev, probs_dev, nullptr, workspace_dev,
                      workspace_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0);
 }
 
@@ -1502,7 +1530,7 @@ int a2m_debug_forward_tap(A2mHandle* h, const float* audio_dev, int32_t batch, c
                           size_t out_elems, void* stream) {
   if (!h) return A2M_EINVAL;
   if (!label || !out_dev) { h->err = "null tap argument"; return A2M_EINVAL; }
-  return run_forward(h, audio_dev, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, nullptr, nullptr, nullptr, 0,
+  return run_forward(h, audio_dev, false, batch, rope_cos_dev, rope_sin_dev, rope_max_pos, nullptr, nullptr, nullptr, nullptr, 0,
                      static_cast<cudaStream_t>(stream), label, out_dev, out_elems);
 }
 
@@ -1515,19 +1543,23 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,
-                    const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
+// audio_dtype / out_dtype: A2M_F32 or A2M_F16.  logits_host may be NULL (infer.py:41 keeps only the probabilities).
+int a2m_submit_host_ex(A2mHandle* h, int32_t slot, const void* audio_host, int32_t audio_dtype, int32_t batch, const float* rope_cos_host,
+                       const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, void* probs_host, int32_t out_dtype) {
   if (!h) return A2M_EINVAL;
-  if (slot < 0 || slot > 1 || batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !logits_host || !probs_host ||
-      rope_max_pos < kT) {
+  if (slot < 0 || slot > 1 || batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !probs_host || rope_max_pos < kT ||
+      (audio_dtype != A2M_F32 && audio_dtype != A2M_F16) || (out_dtype != A2M_F32 && out_dtype != A2M_F16)) {
     h->err = "bad submit_host arguments";
     return A2M_EINVAL;
   }
   A2mHandle::Slot& sl = h->slots[slot];
   if (sl.pending) { h->err = "slot still in flight: call a2m_collect_host first"; return A2M_ESTATE; }
   CUDA_TRY(cudaSetDevice(h->device));
+  const bool in16 = audio_dtype == A2M_F16, out16 = out_dtype == A2M_F16;
   const size_t a_elems = static_cast<size_t>(batch) * 2 * A2M_WINDOW_SAMPLES;
   const size_t o_elems = static_cast<size_t>(batch) * A2M_FRAMES * A2M_VOCAB;
+  const size_t a_bytes = a_elems * (in16 ? 2 : 4);
+  const size_t l_bytes = logits_host ? o_elems * 4 : 0, p_bytes = o_elems * (out16 ? 2 : 4);
   if (!sl.copy) {
     CUDA_TRY(cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
@@ -1565,34 +1597,46 @@ int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t
     CUDA_TRY(cudaMemcpyAsync(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice, cs));
   }
   // input: straight from the caller's buffer when it is page-locked, else through the slot's staging buffer
-  const float* src = audio_host;
+  const void* src = audio_host;
   if (!is_pinned(audio_host)) {
     if (!sl.pin_audio) CUDA_TRY(cudaMallocHost(&sl.pin_audio, static_cast<size_t>(sl.cap) * 2 * A2M_WINDOW_SAMPLES * 4));
-    std::memcpy(sl.pin_audio, audio_host, a_elems * 4);
+    std::memcpy(sl.pin_audio, audio_host, a_bytes);
     src = sl.pin_audio;
   }
-  CUDA_TRY(cudaMemcpyAsync(sl.dev_audio, src, a_elems * 4, cudaMemcpyHostToDevice, sl.copy));
+  CUDA_TRY(cudaMemcpyAsync(sl.dev_audio, src, a_bytes, cudaMemcpyHostToDevice, sl.copy));
   CUDA_TRY(cudaEventRecord(sl.ev_in, sl.copy));
   CUDA_TRY(cudaStreamWaitEvent(cs, sl.ev_in, 0));
-  int rc = run_forward(h, sl.dev_audio, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, sl.dev_out,
-                       sl.dev_out + o_elems, nullptr, 0, cs, nullptr, nullptr, 0);
+  float* d_logits = logits_host ? reinterpret_cast<float*>(sl.dev_out) : nullptr;
+  uint8_t* d_probs = sl.dev_out + o_elems * 4;
+  int rc = run_forward(h, sl.dev_audio, in16, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, d_logits,
+                       out16 ? nullptr : reinterpret_cast<float*>(d_probs), out16 ? reinterpret_cast<__half*>(d_probs) : nullptr,
+                       nullptr, 0, cs, nullptr, nullptr, 0);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(sl.ev_done, cs));
   CUDA_TRY(cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
-  sl.out_direct = is_pinned(logits_host) && is_pinned(probs_host);
+  sl.out_direct = (!logits_host || is_pinned(logits_host)) && is_pinned(probs_host);
   if (sl.out_direct) {
-    CUDA_TRY(cudaMemcpyAsync(logits_host, sl.dev_out, o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
-    CUDA_TRY(cudaMemcpyAsync(probs_host, sl.dev_out + o_elems, o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
+    if (logits_host) CUDA_TRY(cudaMemcpyAsync(logits_host, d_logits, l_bytes, cudaMemcpyDeviceToHost, sl.copy));
+    CUDA_TRY(cudaMemcpyAsync(probs_host, d_probs, p_bytes, cudaMemcpyDeviceToHost, sl.copy));
   } else {
     if (!sl.pin_out) CUDA_TRY(cudaMallocHost(&sl.pin_out, static_cast<size_t>(sl.cap) * 2 * A2M_FRAMES * A2M_VOCAB * 4));
-    CUDA_TRY(cudaMemcpyAsync(sl.pin_out, sl.dev_out, 2 * o_elems * 4, cudaMemcpyDeviceToHost, sl.copy));
+    if (logits_host) CUDA_TRY(cudaMemcpyAsync(sl.pin_out, d_logits, l_bytes, cudaMemcpyDeviceToHost, sl.copy));
+    CUDA_TRY(cudaMemcpyAsync(sl.pin_out + o_elems * 4, d_probs, p_bytes, cudaMemcpyDeviceToHost, sl.copy));
   }
   CUDA_TRY(cudaEventRecord(sl.ev_out, sl.copy));
   sl.pending = true;
   sl.B = batch;
   sl.user_logits = logits_host;
   sl.user_probs = probs_host;
+  sl.logits_bytes = l_bytes;
+  sl.probs_bytes = p_bytes;
   return A2M_OK;
+}
+
+int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,
+                    const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host) {
+  if (h && !logits_host) { h->err = "bad submit_host arguments"; return A2M_EINVAL; }
+  return a2m_submit_host_ex(h, slot, audio_host, A2M_F32, batch, rope_cos_host, rope_sin_host, rope_max_pos, logits_host, probs_host, A2M_F32);
 }
 
 int a2m_collect_host(A2mHandle* h, int32_t slot) {
@@ -1605,8 +1649,8 @@ int a2m_collect_host(A2mHandle* h, int32_t slot) {
   CUDA_TRY(cudaEventSynchronize(sl.ev_out));
   if (!sl.out_direct) {
     const size_t o_elems = static_cast<size_t>(sl.B) * A2M_FRAMES * A2M_VOCAB;
-    std::memcpy(sl.user_logits, sl.pin_out, o_elems * 4);
-    std::memcpy(sl.user_probs, sl.pin_out + o_elems, o_elems * 4);
+    if (sl.user_logits) std::memcpy(sl.user_logits, sl.pin_out, sl.logits_bytes);
+    std::memcpy(sl.user_probs, sl.pin_out + o_elems * 4, sl.probs_bytes);
   }
   return A2M_OK;
 }
@@ -1640,6 +1684,34 @@ int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels
   if (!logits_dev || !labels_dev || !losses_dev || batch <= 0) { h->err = "bad window_losses arguments"; return A2M_EINVAL; }
   CUDA_TRY(cudaSetDevice(h->device));
   bce_window_loss_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, labels_dev, losses_dev, A2M_FRAMES * A2M_VOCAB);
+  CUDA_TRY(cudaGetLastError());
+  return A2M_OK;
+}
+
+int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expected_dev, int32_t batch, int32_t frames, float* metrics_dev,
+                      float* pred_frames_dev, int32_t* n_events_dev, void* stream) {
+  if (!h) return A2M_EINVAL;
+  if (!probs_dev || !expected_dev || !metrics_dev || batch <= 0 || frames <= 0) { h->err = "bad event_metrics arguments"; return A2M_EINVAL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t elems = static_cast<size_t>(batch) * frames * A2M_VOCAB;
+  float* pred = pred_frames_dev;
+  if (!pred) {
+    if (h->em_pred_elems < elems) {
+      if (h->em_pred) cudaFree(h->em_pred);
+      h->em_pred = nullptr;
+      h->em_pred_elems = 0;
+      CUDA_TRY(cudaMalloc(&h->em_pred, elems * 4));
+      h->em_pred_elems = elems;
+    }
+    pred = h->em_pred;
+  }
+  EventDecay d;
+  for (int t = 0; t < EM_DECAY; ++t) {
+    const float x = -0.05f * static_cast<float>(t);                       // f32 product, as python.rs:441 forms it
+    d.v[t] = static_cast<float>(std::exp(static_cast<double>(x)));        // correctly rounded f32 exp
+  }
+  event_metrics_kernel<<<batch, EM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(probs_dev, expected_dev, frames, A2M_VOCAB, pred, metrics_dev,
+                                                                                     n_events_dev, d);
   CUDA_TRY(cudaGetLastError());
   return A2M_OK;
 }

@@ -17,6 +17,7 @@
 // read-only (ld.global.nc) loads above griddepcontrol.wait (seen in SASS: LDG.E.CONSTANT before ACQBULK).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,34 +70,34 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------ Stem
-struct StemParams {
-  float w[4][2][5];  // conv weight (out, in, k)
-  float b[4];
-  float ln_w[4], ln_b[4];
-};
-
-// audio [B, 2, n_samples] fp32 -> X [B * L0, 4] fp32, L0 = n_samples / 5.  One thread per output token.
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ audio, float* __restrict__ out,
-                                                   int n_samples, int L0, int total_tokens, const StemParams p) {
+// Packed fp32 parameter image in the weights arena: w[4][2][5] (40) | b[4] | lnw[4] | lnb[4].  Read from device memory so
+// that a handle whose weights are re-packed after every optimizer step (training) never runs the stem on stale values.
+constexpr int STEM_P = 52;
+// audio [B, 2, n_samples] fp32 or IEEE binary16 -> X [B * L0, 4] fp32, L0 = n_samples / 5.  One thread per output token.
+// The f16 input is lossless for audio that went through load_full_audio: it rounds every sample to f16 (python.rs:235-264),
+// so a host caller can ship half the bytes (a2m_submit_host_ex).
+__device__ __forceinline__ float stem_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float stem_ld(const __half* p) { return __half2float(__ldg(p)); }
+template <class T>
+__global__ void __launch_bounds__(256) stem_kernel(const T* __restrict__ audio, float* __restrict__ out, int n_samples,
+                                                   int L0, int total_tokens, const float* __restrict__ params) {
+  __shared__ float sp[STEM_P];
+  if (threadIdx.x < STEM_P) sp[threadIdx.x] = params[threadIdx.x];
+  __syncthreads();
   const int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= total_tokens) return;
   const int b = tok / L0, l = tok - b * L0;
-  const float* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
-  const float* a1 = a0 + n_samples;
-  float x[2][5];
+  const T* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
+  const T* a1 = a0 + n_samples;
+  float x[10];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    x[0][k] = __ldg(a0 + k);
-    x[1][k] = __ldg(a1 + k);
-  }
+  for (int k = 0; k < 5; ++k) { x[k] = stem_ld(a0 + k); x[5 + k] = stem_ld(a1 + k); }
   float y[4];
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    float acc = p.b[o];
+    float acc = sp[40 + o];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-      for (int k = 0; k < 5; ++k) acc = fmaf(p.w[o][c][k], x[c][k], acc);
+    for (int k = 0; k < 10; ++k) acc = fmaf(sp[o * 10 + k], x[k], acc);
     y[o] = acc;
   }
   const float mean = 0.25f * (y[0] + y[1] + y[2] + y[3]);
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ aud
   for (int o = 0; o < 4; ++o) var += (y[o] - mean) * (y[o] - mean);
   const float inv = rsqrtf(0.25f * var + kLnEps);
   float4 r;
-  r.x = (y[0] - mean) * inv * p.ln_w[0] + p.ln_b[0];
-  r.y = (y[1] - mean) * inv * p.ln_w[1] + p.ln_b[1];
-  r.z = (y[2] - mean) * inv * p.ln_w[2] + p.ln_b[2];
-  r.w = (y[3] - mean) * inv * p.ln_w[3] + p.ln_b[3];
+  r.x = (y[0] - mean) * inv * sp[44] + sp[48];
+  r.y = (y[1] - mean) * inv * sp[45] + sp[49];
+  r.z = (y[2] - mean) * inv * sp[46] + sp[50];
+  r.w = (y[3] - mean) * inv * sp[47] + sp[51];
   reinterpret_cast<float4*>(out)[tok] = r;
 }
 

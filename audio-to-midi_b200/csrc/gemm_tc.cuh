@@ -48,8 +48,9 @@ struct GemmArgs {
   __nv_bfloat16* vt_out;  // [B, heads, 64, rows_per_window] when non-null
   int vt_col0;
   // GEMM_DECODER
-  float* logits;
+  float* logits;      // any of the three may be null
   float* probs;
+  __half* probs16;    // probabilities as IEEE binary16 (the host path's compact output, a2m_submit_host_ex)
   int valid_rows;  // 250
   int valid_cols;  // 90
   // training: dropout of (acc + bias) before the residual add (FeedForwardBlock, model.py:237); gemm_tc2 G2_F32 only
@@ -326,8 +327,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int col = col0 + j;
               if (col < g.valid_cols) {
                 const float z = __uint_as_float(r[j]) + __ldg(g.bias + col);
-                g.logits[obase + col] = z;
-                g.probs[obase + col] = sigmoid_f(z);
+                const float pr = sigmoid_f(z);
+                if (g.logits) g.logits[obase + col] = z;
+                if (g.probs) g.probs[obase + col] = pr;
+                if (g.probs16) g.probs16[obase + col] = __float2half_rn(pr);
               }
             }
           }

@@ -53,6 +53,17 @@ __global__ void __launch_bounds__(256) bce_grad_kernel(const float* __restrict__
   }
 }
 
+// Arbitrary cotangent of the logits (the custom_vjp backward of a JAX caller): dlogits [B, 250, 90] fp32 -> dz [B*256, 128]
+// bf16, zero in the padding.
+__global__ void __launch_bounds__(256) dlogits_pack_kernel(const float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dz, int B) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;   // over B*256*128
+  if (idx >= B * 256 * 128) return;
+  const int col = idx & 127, row = (idx >> 7) & 255, b = idx >> 15;
+  float d = 0.f;
+  if (col < 90 && row < 250) d = dlogits[(static_cast<size_t>(b) * 250 + row) * 90 + col];
+  dz[idx] = __float2bfloat16_rn(d);
+}
+
 // Per-window validation loss (train.py:99-102 testset_loss_function): out[b] = sum_{t,c} BCEWithLogits(z, y), one CTA per window.
 __global__ void __launch_bounds__(256) bce_window_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                                                               float* __restrict__ out, int per_window) {
@@ -1017,42 +1028,7 @@ __global__ void __launch_bounds__(SDB_THREADS) downsample_small_bwd_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------ Stem (training variant + backward)
-// Packed fp32 image: w[4][2][5] (40) | b[4] | lnw[4] | lnb[4]
-constexpr int STEM_P = 52;
-__global__ void __launch_bounds__(256) stem_train_kernel(const float* __restrict__ audio, float* __restrict__ out, int n_samples,
-                                                         int L0, int total_tokens, const float* __restrict__ params) {
-  __shared__ float sp[STEM_P];
-  if (threadIdx.x < STEM_P) sp[threadIdx.x] = params[threadIdx.x];
-  __syncthreads();
-  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= total_tokens) return;
-  const int b = tok / L0, l = tok - b * L0;
-  const float* a0 = audio + static_cast<size_t>(b) * 2 * n_samples + static_cast<size_t>(l) * 5;
-  const float* a1 = a0 + n_samples;
-  float x[10];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { x[k] = __ldg(a0 + k); x[5 + k] = __ldg(a1 + k); }
-  float y[4];
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    float acc = sp[40 + o];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc = fmaf(sp[o * 10 + k], x[k], acc);
-    y[o] = acc;
-  }
-  const float mean = 0.25f * (y[0] + y[1] + y[2] + y[3]);
-  float var = 0.f;
-#pragma unroll
-  for (int o = 0; o < 4; ++o) var += (y[o] - mean) * (y[o] - mean);
-  const float inv = rsqrtf(0.25f * var + kLnEps);
-  float4 r;
-  r.x = (y[0] - mean) * inv * sp[44] + sp[48];
-  r.y = (y[1] - mean) * inv * sp[45] + sp[49];
-  r.z = (y[2] - mean) * inv * sp[46] + sp[50];
-  r.w = (y[3] - mean) * inv * sp[47] + sp[51];
-  reinterpret_cast<float4*>(out)[tok] = r;
-}
-
+// (forward: stem_kernel in cnn_kernels.cuh, same parameter image)
 __global__ void __launch_bounds__(256) stem_bwd_kernel(const float* __restrict__ audio, const float* __restrict__ dOut, int n_samples,
                                                        int L0, int total_tokens, const float* __restrict__ params,
                                                        float* __restrict__ gparams) {
@@ -1197,13 +1173,38 @@ __global__ void __launch_bounds__(256) grad_unpack_chunks_kernel(const float* __
 struct AdamArgs {
   float lr, b1, b2, eps, wd, bc1, bc2, inv_div;   // bc = 1 - beta^t ; grads are multiplied by inv_div first
 };
+// Pass 0: stats[1] = number of non-finite gradient entries (train.py:320-322, grads_valid).  It runs BEFORE anything is
+// written: with a non-finite gradient both passes below are no-ops, so the master weights and the moments are never
+// poisoned (the reference restores a snapshot and halves the loss scale instead, train.py:369-377).
+__global__ void __launch_bounds__(256) grad_finite_kernel(const float* __restrict__ g, size_t n, float* __restrict__ stats) {
+  float bad = 0.f;
+  if (reinterpret_cast<uintptr_t>(g) & 15) {   // unaligned blob (a caller's slice): scalar loads
+    for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull)
+      if (!isfinite(g[i])) bad += 1.f;
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0 && bad != 0.f) atomicAdd(stats + 1, bad);
+    return;
+  }
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n4; i += gridDim.x * 256ull) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    // x * 0 is 0 for every finite x and NaN for inf / NaN
+    const float t = (v.x * 0.f + v.y * 0.f) + (v.z * 0.f + v.w * 0.f);
+    if (t != 0.f) bad += 1.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    if (!isfinite(g[n4 * 4 + threadIdx.x])) bad += 1.f;
+  }
+  bad = warp_sum(bad);
+  if ((threadIdx.x & 31) == 0 && bad != 0.f) atomicAdd(stats + 1, bad);
+}
 __global__ void __launch_bounds__(256) adamw_pass1_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                           float* __restrict__ v, float* __restrict__ u, const float* __restrict__ lr_mult,
                                                           size_t n, AdamArgs a, float* __restrict__ stats /* [0] sum u^2, [1] non-finite count */) {
-  float ss = 0.f, bad = 0.f;
+  if (stats[1] != 0.f) return;   // written by grad_finite_kernel, earlier in the stream
+  float ss = 0.f;
   for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
     const float gi = g[i] * a.inv_div;
-    if (!isfinite(gi)) bad += 1.f;
     const float mi = a.b1 * m[i] + (1.f - a.b1) * gi;
     const float vi = a.b2 * v[i] + (1.f - a.b2) * gi * gi;
     m[i] = mi;
@@ -1215,19 +1216,18 @@ __global__ void __launch_bounds__(256) adamw_pass1_kernel(const float* __restric
     ss += ui * ui;
   }
   ss = warp_sum(ss);
-  bad = warp_sum(bad);
-  __shared__ float s0[8], s1[8];
-  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = ss; s1[threadIdx.x >> 5] = bad; }
+  __shared__ float s0[8];
+  if ((threadIdx.x & 31) == 0) s0[threadIdx.x >> 5] = ss;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int i = 0; i < 8; ++i) { t0 += s0[i]; t1 += s1[i]; }
+    float t0 = 0.f;
+    for (int i = 0; i < 8; ++i) t0 += s0[i];
     atomicAdd(stats, t0);
-    if (t1 != 0.f) atomicAdd(stats + 1, t1);
   }
 }
 __global__ void __launch_bounds__(256) adamw_pass2_kernel(float* __restrict__ p, const float* __restrict__ u, size_t n, float clip,
                                                           const float* __restrict__ stats) {
+  if (stats[1] != 0.f) return;
   const float norm = sqrtf(stats[0]);
   const float f = (norm > clip) ? clip / norm : 1.f;
   for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) p[i] += u[i] * f;

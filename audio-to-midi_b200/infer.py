@@ -78,28 +78,75 @@ def prepare_windows_device(model, audio_samples, overlap: float = 0.25, device=N
     return out
 
 
-def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 64, rank: int = 0, world_size: int = 1):
-    """Long-audio transcription (BASELINE config 5; infer.py:339 / audio_to_midi.py:38-53): normalise + slice on the
-    device, batched forward of this rank's block of windows, then (rank 0 / single process) stitch and eventize.
-    Returns (events, stitched_probs, probs_of_this_rank)."""
+def gather_window_blocks(local, n_total: int, world_size: int, rank: int):
+    """Rank-ordered concatenation of the per-rank blocks of shard_windows on EVERY rank (contiguous blocks, so the result is
+    in window order).  `local` is a torch tensor [n_local, ...] (CUDA -> NCCL, CPU -> gloo).  Blocks differ in size by at most
+    one window, so each rank pads its block to the largest one and a single equal-size all_gather moves everything
+    (windows x 90 KB: 12 MB for the 10-minute clip of config 5).  Used only AFTER the forward: the path itself has no collective."""
     import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        return local
+    per = [shard_windows(n_total, world_size, r) for r in range(world_size)]
+    cap = max(hi - lo for lo, hi in per)
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad)
+    return torch.cat([parts[r][: per[r][1] - per[r][0]] for r in range(world_size)])
+
+
+def _dist_world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 64, rank: int = None, world_size: int = None,
+                    gather: bool = True):
+    """Long-audio transcription (BASELINE config 5; infer.py:339 / audio_to_midi.py:38-53): normalise + slice on the
+    device, batched forward of this rank's block of windows, rank-ordered gather of the probabilities, then stitch and
+    eventize.  rank / world_size default to the torch.distributed process group (1 process: no collective at all).
+    Returns (events, stitched_probs, probs): with several ranks, rank 0 gets the whole clip's events / stitched track and
+    every rank the gathered probabilities; with gather=False (or explicit rank / world_size without a process group, as the
+    single-process partition tests use) a rank returns (None, None, probabilities of its own block)."""
+    import torch
+    drank, dworld = _dist_world()
+    explicit = rank is not None or world_size is not None
+    rank = drank if rank is None else rank
+    world_size = dworld if world_size is None else world_size
     windows = prepare_windows_device(model, audio_samples, overlap)
-    lo, hi = shard_windows(windows.shape[0], world_size, rank)
+    n_total = int(windows.shape[0])
+    lo, hi = shard_windows(n_total, world_size, rank)
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
     chunks = []
     for i in range(lo, hi, max_batch):
         _lg, p = model.predict(None, windows[i:min(i + max_batch, hi)], rope_freqs)
         chunks.append(p)
-    probs = torch.cat(chunks).cpu().numpy().astype(np.float32) if chunks else np.zeros((0, 250, 90), np.float32)
+    local = torch.cat(chunks) if chunks else torch.zeros((0, 250, 90), dtype=torch.float32, device=windows.device)
     if world_size > 1:
-        return None, None, probs          # the caller gathers the per-rank blocks in rank order, then stitches
+        if not gather or (explicit and dworld != world_size):
+            return None, None, local.cpu().numpy().astype(np.float32)
+        probs = gather_window_blocks(local, n_total, world_size, rank).cpu().numpy().astype(np.float32)
+        if rank != 0:
+            return None, None, probs
+    else:
+        probs = local.cpu().numpy().astype(np.float32)
     stitched = modelutil.stitch_probs(probs, overlap, MODEL_AUDIO_LENGTH / probs.shape[1])
     return modelutil.extract_events(stitched), stitched, probs
 
 
+_METRIC_KEYS = ("full_diff", "phantom_notes_diff", "missed_notes_diff", "notes_hit", "hit_rate")
+
+
 def detailed_event_loss(output_probs: np.ndarray, expected: np.ndarray) -> dict:
     """infer.py:94-158 without the plot: eventize the probabilities, rasterise them back to frames and compare with the
-    annotation: full_diff, phantom / missed note mass, notes hit, hit_rate = hit / (hit + phantom + missed)."""
+    annotation: full_diff, phantom / missed note mass, notes hit, hit_rate = hit / (hit + phantom + missed).  Host version
+    (C++ eventizer), one window at a time as the reference runs it; detailed_event_loss_device is the batched one."""
     output_probs = np.ascontiguousarray(output_probs, np.float32)
     predicted = modelutil.to_frame_events([modelutil.extract_events(output_probs)], output_probs.shape[0])[0]
     expected = np.asarray(expected)[: predicted.shape[0]]
@@ -112,21 +159,56 @@ def detailed_event_loss(output_probs: np.ndarray, expected: np.ndarray) -> dict:
             "missed_notes_diff": missed, "notes_hit": hit, "hit_rate": hit / denom if denom > 0 else 1.0}
 
 
-def compute_testset_loss(model, audio, events, rank: int = 0, world_size: int = 1, max_batch: int = 64):
+def detailed_event_loss_device(model, probs, expected, want_frames: bool = False):
+    """detailed_event_loss for a whole batch in ONE launch on the device (a2m_event_metrics): probs / expected
+    torch CUDA tensors [B, F, 90].  Returns the [B, 5] metrics tensor (columns = _METRIC_KEYS) still on the device, and with
+    want_frames also the rasterised predictions [B, F, 90]."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    dev = probs.device.index if probs.device.index is not None else torch.cuda.current_device()
+    eng = model._engine(dev)
+    probs = probs.to(torch.float32).contiguous()
+    expected = expected.to(probs.device, torch.float32).contiguous()
+    B, F, K = probs.shape
+    if K != 90 or tuple(expected.shape) != (B, F, K):
+        raise ValueError(f"probs / expected must both be (B, F, 90), got {tuple(probs.shape)} / {tuple(expected.shape)}")
+    out = torch.empty((B, 5), dtype=torch.float32, device=probs.device)
+    frames = torch.empty_like(probs) if want_frames else None
+    stream = C.c_void_p(torch.cuda.current_stream(probs.device).cuda_stream)
+    rc = eng.L.a2m_event_metrics(eng.h, probs.data_ptr(), expected.data_ptr(), B, F, out.data_ptr(),
+                                 frames.data_ptr() if want_frames else None, None, stream)
+    _lib.check(eng.h, rc, "a2m_event_metrics")
+    return (out, frames) if want_frames else out
+
+
+def metrics_to_dicts(metrics: np.ndarray):
+    return [dict(zip(_METRIC_KEYS, (float(v) for v in row))) for row in np.asarray(metrics)]
+
+
+def compute_testset_loss(model, audio, events, rank: int = None, world_size: int = None, max_batch: int = 64, gather: bool = True,
+                         device_metrics: bool = True):
     """Validation pass of config 3 (compute_testset_loss_individual, train.py:86-209; infer.py:94-158): the annotated
-    windows are batch-partitioned over ranks (contiguous blocks, no collective); each rank runs the batched forward on
-    its block, the per-window BCE sum on the device (a2m_window_losses) and the event metrics on the host.
-    audio (N, 2, 80000), events (N, 250, 90), numpy.  Returns (lo, hi, losses[hi-lo], [detailed_event_loss dict])."""
+    windows are batch-partitioned over ranks (contiguous blocks; the forward has no collective); each rank runs the batched
+    forward on its block, the per-window BCE sum (a2m_window_losses) and the event metrics (a2m_event_metrics) on the device --
+    nothing but [n, 6] floats ever returns to the host.  With a process group the per-rank results are gathered in rank order.
+    audio (N, 2, 80000), events (N, 250, 90), numpy.  Returns (lo, hi, losses, [detailed_event_loss dict]): the block bounds
+    of this rank, and losses / dicts of ALL windows when gathered (else of the block)."""
     import ctypes as C
     import torch
     from . import _lib
     from .model import _default_device
-    lo, hi = shard_windows(audio.shape[0], world_size, rank)
+    drank, dworld = _dist_world()
+    explicit = rank is not None or world_size is not None
+    rank = drank if rank is None else rank
+    world_size = dworld if world_size is None else world_size
+    n_total = int(audio.shape[0])
+    lo, hi = shard_windows(n_total, world_size, rank)
     dev = _default_device()
     eng = model._engine(dev)
     tdev = torch.device(f"cuda:{dev}")
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
-    losses, details = [], []
+    rows = []
     for i in range(lo, hi, max_batch):
         j = min(i + max_batch, hi)
         x = torch.as_tensor(np.ascontiguousarray(audio[i:j], np.float32)).to(tdev)
@@ -135,10 +217,18 @@ def compute_testset_loss(model, audio, events, rank: int = 0, world_size: int = 
         out = torch.empty(j - i, dtype=torch.float32, device=tdev)
         stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
         _lib.check(eng.h, eng.L.a2m_window_losses(eng.h, logits.data_ptr(), y.data_ptr(), j - i, out.data_ptr(), stream), "a2m_window_losses")
-        losses.append(out.cpu().numpy())
-        pr = probs.cpu().numpy()
-        details.extend(detailed_event_loss(pr[k], events[i + k]) for k in range(j - i))
-    return lo, hi, (np.concatenate(losses) if losses else np.zeros(0, np.float32)), details
+        if device_metrics:
+            m = detailed_event_loss_device(model, probs, y)
+        else:
+            pr = probs.cpu().numpy()
+            m = torch.tensor([[detailed_event_loss(pr[k], events[i + k])[q] for q in _METRIC_KEYS] for k in range(j - i)],
+                             dtype=torch.float32, device=tdev)
+        rows.append(torch.cat([out[:, None], m], dim=1))
+    local = torch.cat(rows) if rows else torch.zeros((0, 6), dtype=torch.float32, device=tdev)
+    if world_size > 1 and gather and not (explicit and dworld != world_size):
+        local = gather_window_blocks(local, n_total, world_size, rank)
+    table = local.cpu().numpy()
+    return lo, hi, table[:, 0].copy(), metrics_to_dicts(table[:, 1:])
 
 
 # ------------------------------------------------------------------------------------------ MIDI writer
@@ -211,25 +301,51 @@ def read_midi_notes(path: str):
 
 
 # ------------------------------------------------------------------------------------------ checkpoints
-def save_checkpoint(model, directory: str, step: int):
+def save_checkpoint(model, directory: str, step: int, ensemble_axis: bool = True):
     """Pytree-path-keyed `.npz` stand-in for the reference's orbax CheckpointManager (train.py:384-394; orbax and
-    tensorstore are absent from the image): `<directory>/<step>/params.npz` holds every array leaf under its key path
-    (exactly the names and shapes an `ocp.args.StandardRestore` of the reference model yields), `metadata.json` the
-    model metadata the reference stores next to a checkpoint (model.py:36-41)."""
+    tensorstore are absent from the image): `<directory>/<step>/params.npz` holds every array leaf under its key path,
+    `metadata.json` the model metadata the reference stores next to a checkpoint (model.py:36-41).
+
+    ensemble_axis (default): every array carries the reference's leading ENSEMBLE axis of size 1 -- the reference trains a
+    `filter_vmap`-ed ensemble (train.py:788-795) and saves `eqx.filter(model_ensemble, is_inexact_array)`, so a checkpointed
+    leaf is (1, ...) and a transformer leaf (1, 8, ...).  These are exactly the names and shapes an
+    `ocp.args.StandardRestore` of the reference model yields, which is what tools/convert_orbax.py moves in and out of orbax."""
     import json
     import os
     from .model import get_model_metadata
     d = os.path.join(directory, str(int(step)))
     os.makedirs(d, exist_ok=True)
-    np.savez(os.path.join(d, "params.npz"), **{p: np.asarray(a) for p, a in model.tree_leaves_with_path()})
+    leaves = {p: np.asarray(a) for p, a in model.tree_leaves_with_path()}
+    if ensemble_axis:
+        leaves = {p: a[None, ...] for p, a in leaves.items()}
+    np.savez(os.path.join(d, "params.npz"), **leaves)
     with open(os.path.join(d, "metadata.json"), "w") as f:
-        json.dump(get_model_metadata(), f)
+        json.dump({**get_model_metadata(), "ensemble_axis": bool(ensemble_axis)}, f)
     return d
 
 
-def load_newest_checkpoint(checkpoint_path: str):
+def select_ensemble_member(leaves: dict, reference_shapes: dict, ensemble_select: int = 0) -> dict:
+    """infer.py:213-221 (ensemble_selector): checkpointed arrays carry a leading ensemble axis; pick member
+    `ensemble_select`.  Arrays that already have the model's shape (a checkpoint written without the axis) pass through."""
+    out = {}
+    for p, a in leaves.items():
+        a = np.asarray(a)
+        want = tuple(reference_shapes[p]) if p in reference_shapes else None
+        if want is not None and a.shape == want:
+            out[p] = a
+        elif want is not None and a.ndim == len(want) + 1 and a.shape[1:] == want:
+            if not 0 <= ensemble_select < a.shape[0]:
+                raise IndexError(f"leaf {p}: ensemble member {ensemble_select} of {a.shape[0]}")
+            out[p] = a[ensemble_select]
+        else:
+            out[p] = a          # load_leaves reports the shape mismatch with the leaf's name
+    return out
+
+
+def load_newest_checkpoint(checkpoint_path: str, ensemble_size: int = 1, ensemble_select: int = 0):
     """infer.py:172-236 for the `.npz` layout of save_checkpoint: restores the highest step, warns when the stored model
-    metadata differs from the current configuration (as the reference does), returns (model, state)."""
+    metadata differs from the current configuration (as the reference does), selects ensemble member `ensemble_select`
+    (infer.py:213-221), returns (model, state)."""
     import json
     import os
     from .model import OutputSequenceGenerator, get_model_metadata, model_config
@@ -241,10 +357,12 @@ def load_newest_checkpoint(checkpoint_path: str):
     if os.path.exists(meta_file):
         with open(meta_file) as f:
             stored = json.load(f)
+        stored.pop("ensemble_axis", None)
         if stored != json.loads(json.dumps(get_model_metadata())):
             print(f"WARNING: The loaded model has metadata {stored}\nCurrent configuration is {get_model_metadata()}")
     with np.load(os.path.join(d, "params.npz")) as z:
         leaves = {k: z[k] for k in z.files}
     model = OutputSequenceGenerator(model_config, key=1234)
-    model.load_leaves(leaves)
+    shapes = {p: np.shape(a) for p, a in model.tree_leaves_with_path()}
+    model.load_leaves(select_ensemble_member(leaves, shapes, ensemble_select))
     return model, None

@@ -237,35 +237,61 @@ class TransformerStack(Module):    # model.py:615-670: `layers` is ONE module wh
 
 
 # ----------------------------------------------------------------------------------------------- engine
+def default_config_struct(device: int) -> "_lib.A2mConfig":
+    """model_config (model.py:20-34) as the A2mConfig of include/a2m.h."""
+    c = _lib.A2mConfig()
+    c.device = device
+    c.num_stages = len(model_config["dims"])
+    for i, (d, n) in enumerate(zip(model_config["dims"], model_config["depths"])):
+        c.dims[i], c.depths[i] = d, n
+    c.cnn_hidden_expansion_x2 = int(round(model_config["cnn_hidden_expansion"] * 2))
+    c.num_transformer_layers = model_config["num_transformer_layers"]
+    c.num_transformer_heads = model_config["num_transformer_heads"]
+    c.attention_size = model_config["attention_size"]
+    c.compressed_attention_kv_size = model_config["compressed_attention_kv_size"]
+    c.transformer_intermediate = int(model_config["dims"][-1] * model_config["transformer_hidden_expansion"])
+    c.use_graph = c.use_pdl = -1
+    return c
+
+
 class _Engine:
-    """One C handle per CUDA device; owns the uploaded weights."""
-    _by_device: Dict[int, "_Engine"] = {}
+    """One C handle (a2m_create_ex): the weights arena, workspace and launch plans of ONE model on ONE device.  A model owns
+    its engines (`OutputSequenceGenerator._engines`), a TrainEngine owns its own: handles are never shared or stolen, so a
+    model and a trainer -- or two models -- can be resident on the same GPU at the same time."""
 
     def __init__(self, device: int):
         self.L = _lib.lib()
         h = C.c_void_p()
-        rc = self.L.a2m_create(device, C.byref(h))
+        cfg = default_config_struct(device)
+        rc = self.L.a2m_create_ex(C.byref(cfg), C.byref(h))
         self.h = h
         if rc != 0:
             msg = self.L.a2m_last_error(h).decode() if h else ""
             if h:
                 self.L.a2m_destroy(h)
-            raise _lib.A2mError(f"a2m_create(device={device}) failed with code {rc} {msg}: an sm_100 (B200) GPU and "
+                self.h = None
+            raise _lib.A2mError(f"a2m_create_ex(device={device}) failed with code {rc} {msg}: an sm_100 (B200) GPU and "
                                 "the CUDA library are required; there is no CPU fallback")
         self.device = device
         self.weights_token = None
 
-    @classmethod
-    def get(cls, device: int) -> "_Engine":
-        if device not in cls._by_device:
-            cls._by_device[device] = cls(device)
-        return cls._by_device[device]
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.a2m_destroy(self.h)
+            self.h = None
 
-    def load(self, model: "OutputSequenceGenerator"):
-        leaves = model.tree_leaves_with_path()
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def blob_and_table(leaves):
+        """[(path, array)] -> (contiguous fp32 blob, A2mLeafDesc table, element offsets)."""
         n = len(leaves)
         table = (_lib.LeafDesc * n)()
-        chunks, off = [], 0
+        chunks, off, offsets = [], 0, []
         for i, (path, arr) in enumerate(leaves):
             a = np.ascontiguousarray(arr, dtype=np.float32)
             table[i].path = path.encode()
@@ -274,9 +300,13 @@ class _Engine:
             for d in range(a.ndim):
                 table[i].shape[d] = a.shape[d]
             chunks.append(a.reshape(-1))
+            offsets.append(off // 4)
             off += a.size * 4
-        blob = np.concatenate(chunks)
-        _lib.check(self.h, self.L.a2m_load_weights(self.h, blob.ctypes.data, blob.nbytes, table, n), "a2m_load_weights")
+        return np.concatenate(chunks), table, offsets
+
+    def load(self, model: "OutputSequenceGenerator"):
+        blob, table, _ = self.blob_and_table(model.tree_leaves_with_path())
+        _lib.check(self.h, self.L.a2m_load_weights(self.h, blob.ctypes.data, blob.nbytes, table, len(table)), "a2m_load_weights")
         self.weights_token = model._version
 
 
@@ -307,6 +337,8 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         self._version = 0
         self._rope_cache = {}
         self._out_ring = {}
+        self._engines = {}        # device -> _Engine owned by this model
+        self._trainers = {}       # device -> weakref to the live TrainEngine built from this model (train.py)
 
     # -- pytree helpers (what eqx.tree_at / tree_deserialise_leaves would be used for)
     def load_leaves(self, leaves: Dict[str, np.ndarray]):
@@ -325,18 +357,52 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         self._version += 1
 
     # -- forward
+    def _live_trainer(self, device: int):
+        ref = self._trainers.get(device)
+        t = ref() if ref is not None else None
+        if t is None or t.closed or t.model_version != self._version:
+            return None       # no trainer, or the model's leaves were replaced after the trainer was built
+        return t
+
     def _engine(self, device: int) -> _Engine:
-        eng = _Engine.get(device)
-        if eng.weights_token != self._version or getattr(eng, "owner", None) is not self:
+        """The handle inference runs on.  While a TrainEngine built from this model is alive on `device`, that is the
+        TRAINER's handle: a2m_forward reads the arena the optimizer re-packs after every step, so validation inside a training
+        loop (train.py:396-437) sees the current weights and never disturbs the training session."""
+        t = self._live_trainer(device)
+        if t is not None:
+            return t.eng
+        eng = self._engines.get(device)
+        if eng is None:
+            eng = self._engines[device] = _Engine(device)
+        if eng.weights_token != self._version:
             eng.load(self)
-            eng.owner = self
         return eng
 
     def __call__(self, samples, state, rope_freqs: RopeFreqs, key=None, enable_dropout: bool = False):
         if enable_dropout:
-            raise NotImplementedError("training-mode forward (dropout) is not built yet; see DESIGN.md scope table")
-        logits, probs = self._forward(samples, rope_freqs)
+            logits, probs = self._forward_train(samples, rope_freqs, key)
+        else:
+            logits, probs = self._forward(samples, rope_freqs)
         return (logits, probs), state
+
+    def _forward_train(self, samples, rope_freqs, key):
+        """Training-mode forward, the call shape of train.py:56-58 (`model(audio, state, rope_freqs, key, True)` under vmap):
+        dropout at transformer_dropout_rate on the attention weights and the FFN output, masks seeded by `key` (an int, or
+        an array of per-sample keys that is folded into one seed: the masks are a counter-based hash of (seed, site, element),
+        not jax's threefry).  Runs a2m_forward_train on this model's TrainEngine, so a following
+        `TrainEngine.backward(labels)` differentiates exactly this forward."""
+        from .train import TrainEngine
+        if not type(samples).__module__.startswith("torch") or not samples.is_cuda:
+            raise _lib.A2mError("the training-mode forward takes CUDA tensors (no CPU path)")
+        import torch
+        single = samples.ndim == 2
+        x = samples.reshape((-1, 2, 80000)).to(torch.float32).contiguous()
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        t = self._live_trainer(dev) or TrainEngine(self, dev)
+        seed = fold_key(key)
+        t.set_dropout(model_config["transformer_dropout_rate"], seed)
+        logits, probs = t.forward_train(x, rope_freqs, want_probs=True)
+        return (logits[0], probs[0]) if single else (logits, probs)
 
     def predict(self, state, samples, rope_freqs: RopeFreqs):
         (logits, probs), _ = self(samples, state, rope_freqs, None)
@@ -356,12 +422,12 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
             dev = samples.device.index if samples.device.index is not None else torch.cuda.current_device()
             eng = self._engine(dev)
             x = samples.to(torch.float32).contiguous()
-            ck = (dev, id(rope_freqs))
-            if ck not in self._rope_cache:
+            hit = self._rope_cache.get(dev)
+            if hit is None or hit[2] is not rope_freqs:     # identity of the live object, never a recycled id()
                 cos = torch.as_tensor(np.ascontiguousarray(rope_freqs.cos_freq, np.float32)).to(samples.device)
                 sin = torch.as_tensor(np.ascontiguousarray(rope_freqs.sin_freq, np.float32)).to(samples.device)
-                self._rope_cache = {ck: (cos, sin, rope_freqs)}
-            cos, sin, _ = self._rope_cache[ck]
+                hit = self._rope_cache[dev] = (cos, sin, rope_freqs)
+            cos, sin, _ = hit
             logits = torch.empty((B, 250, 90), dtype=torch.float32, device=samples.device)
             probs = torch.empty_like(logits)
             stream = torch.cuda.current_stream(samples.device).cuda_stream
@@ -380,42 +446,54 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         _lib.check(eng.h, rc, "a2m_forward_host")
         return (logits[0], probs[0]) if single else (logits, probs)
 
-    def predict_pipelined(self, batches, rope_freqs: RopeFreqs, state=None, copy: bool = False):
+    def predict_pipelined(self, batches, rope_freqs: RopeFreqs, state=None, copy: bool = False, want_logits: bool = True,
+                          probs_dtype=np.float32):
         """Generator over an iterable of host batches (B, 2, 80000): yields (logits, probs) per batch, in order,
         keeping two batches in flight so the H2D / D2H copies of one overlap the kernels of the other
-        (a2m_submit_host / a2m_collect_host).  Use ``pinned_empty`` arrays for the inputs to make the copies
+        (a2m_submit_host_ex / a2m_collect_host).  Use ``pinned_empty`` arrays for the inputs to make the copies
         truly asynchronous.  Outputs live in a ring of three page-locked buffers (page-locking is expensive, so
         they are allocated once per batch size): a yielded pair stays valid until two more pairs have been
-        yielded; pass copy=True to get private copies instead."""
+        yielded; pass copy=True to get private copies instead.
+
+        Bytes over PCIe: float16 batches are uploaded as they are (lossless for audio normalised by load_full_audio, which
+        rounds to f16, python.rs:235-264) and widened on the device; want_logits=False skips the logits read-back (infer.py:41
+        keeps only the probabilities; None is yielded in their place); probs_dtype=np.float16 halves the other half."""
         eng = self._engine(_default_device())
         cos = np.ascontiguousarray(rope_freqs.cos_freq, np.float32)
         sin = np.ascontiguousarray(rope_freqs.sin_freq, np.float32)
+        probs_dtype = np.dtype(probs_dtype)
+        if probs_dtype not in (np.dtype(np.float32), np.dtype(np.float16)):
+            raise ValueError("probs_dtype must be float32 or float16")
+        out_code = _lib.F16 if probs_dtype == np.dtype(np.float16) else _lib.F32
         inflight = []
         slot = 0
 
         def finish(item):
             s0, _keep, lg, pr = item
             _lib.check(eng.h, eng.L.a2m_collect_host(eng.h, s0), "a2m_collect_host")
-            return (lg.copy(), pr.copy()) if copy else (lg, pr)
+            if copy:
+                return (None if lg is None else lg.copy()), pr.copy()
+            return lg, pr
 
         for x in batches:
-            if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous):
+            if not (isinstance(x, np.ndarray) and x.dtype in (np.float32, np.float16) and x.flags.c_contiguous):
                 x = np.ascontiguousarray(x, dtype=np.float32)
             if x.ndim != 3 or x.shape[1:] != (2, 80000):
                 raise ValueError(f"batches must be (B, 2, 80000), got {x.shape}")
             if len(inflight) == 2:
                 yield finish(inflight.pop(0))
             B = x.shape[0]
-            ring = self._out_ring.setdefault(B, {"bufs": [], "n": 0})
+            ring = self._out_ring.setdefault((B, want_logits, probs_dtype.str), {"bufs": [], "n": 0})
             if len(ring["bufs"]) < 3:
-                ring["bufs"].append((pinned_empty((B, 250, 90)), pinned_empty((B, 250, 90))))
+                ring["bufs"].append((pinned_empty((B, 250, 90)) if want_logits else None, pinned_empty((B, 250, 90), probs_dtype)))
                 lg, pr = ring["bufs"][-1]
             else:
                 lg, pr = ring["bufs"][ring["n"] % 3]
             ring["n"] += 1
-            rc = eng.L.a2m_submit_host(eng.h, slot, x.ctypes.data, B, cos.ctypes.data, sin.ctypes.data, cos.shape[0],
-                                       lg.ctypes.data, pr.ctypes.data)
-            _lib.check(eng.h, rc, "a2m_submit_host")
+            rc = eng.L.a2m_submit_host_ex(eng.h, slot, x.ctypes.data, _lib.F16 if x.dtype == np.float16 else _lib.F32, B,
+                                          cos.ctypes.data, sin.ctypes.data, cos.shape[0],
+                                          None if lg is None else lg.ctypes.data, pr.ctypes.data, out_code)
+            _lib.check(eng.h, rc, "a2m_submit_host_ex")
             inflight.append((slot, x, lg, pr))
             slot ^= 1
         for item in inflight:
@@ -434,8 +512,18 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         return [(buf[i].kernel.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)) for i in range(m)]
 
     def last_launch_count(self, device: Optional[int] = None) -> int:
-        eng = _Engine.get(_default_device() if device is None else device)
+        eng = self._engine(_default_device() if device is None else device)
         return int(eng.L.a2m_last_launch_count(eng.h))
+
+
+def fold_key(key) -> int:
+    """PRNG key(s) -> one 64-bit dropout seed: an int, a jax-style uint32[2] key, or an array of per-sample keys (train.py:53)."""
+    if key is None:
+        return 0
+    seed = 0
+    for v in np.asarray(key).ravel().tolist():
+        seed = ((seed ^ (int(v) & 0xFFFFFFFFFFFFFFFF)) * 0x9E3779B97F4A7C15 + 0x7F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    return seed
 
 
 def _default_device() -> int:
@@ -474,12 +562,17 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
 _PINNED: dict = {}
 
 
-def vmap(fn, in_axes=(None, 0, None)):
-    """Adapter for the reference call shape jax.vmap(model.predict, in_axes=(None, 0, None)) (infer.py:40):
-    the kernels are natively batched, so the mapped axis is simply passed through."""
-    if tuple(in_axes) != (None, 0, None):
-        raise NotImplementedError("only in_axes=(None, 0, None) (state, samples, rope_freqs) is supported")
-
-    def mapped(state, samples, rope_freqs):
-        return fn(state, samples, rope_freqs)
-    return mapped
+def vmap(fn, in_axes=(None, 0, None), out_axes=0, axis_name=None):
+    """Adapter for the reference's two call shapes: jax.vmap(model.predict, in_axes=(None, 0, None)) (infer.py:40) and
+    jax.vmap(model, in_axes=(0, None, None, 0, None), out_axes=(0, None), axis_name="batch") (train.py:56-58).  The kernels
+    are natively batched, so the mapped axis is simply passed through."""
+    axes = tuple(in_axes)
+    if axes == (None, 0, None):
+        def mapped(state, samples, rope_freqs):
+            return fn(state, samples, rope_freqs)
+        return mapped
+    if axes == (0, None, None, 0, None):
+        def mapped_train(samples, state, rope_freqs, keys, enable_dropout):
+            return fn(samples, state, rope_freqs, keys, enable_dropout)
+        return mapped_train
+    raise NotImplementedError("supported: in_axes=(None, 0, None) for model.predict, (0, None, None, 0, None) for model.__call__")

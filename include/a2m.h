@@ -30,6 +30,10 @@ extern "C" {
 #define A2M_ECUDA (-2)     /* CUDA runtime or driver error */
 #define A2M_ENODEVICE (-3) /* no sm_100 device */
 #define A2M_ESTATE (-4)    /* call order (e.g. forward before load_weights) */
+#define A2M_ENCCL (-5)     /* NCCL not loadable / a collective failed */
+
+#define A2M_F32 0          /* element types of the host-path buffers (a2m_submit_host_ex) */
+#define A2M_F16 1          /* IEEE binary16 */
 
 #define A2M_WINDOW_SAMPLES 80000 /* audio_to_midi_dataset.py:28,111: 5.0 s x 16 kHz */
 #define A2M_FRAMES 250           /* model output frames per window */
@@ -53,6 +57,24 @@ typedef struct {
 /* Creates a handle on CUDA device `device`.  Replaces OutputSequenceGenerator.__init__ (model.py:680-738)
  * for the default model_config (model.py:20-34); weights arrive through a2m_load_weights. */
 int a2m_create(int device, A2mHandle** out);
+/* The same with the architecture spelled out, i.e. OutputSequenceGenerator(conf, key) (model.py:680-738, model_config
+ * model.py:20-34).  The kernels are specialised for the reference's default model_config: any other value of the
+ * architecture fields is refused with A2M_EINVAL.  use_graph / use_pdl: 0 / 1, or -1 for the default. */
+typedef struct {
+  int32_t device;
+  int32_t num_stages;                    /* len(dims) = 7 */
+  int32_t dims[8];                       /* 4, 8, 16, 32, 64, 128, 256 */
+  int32_t depths[8];                     /* 3, 3, 3, 3, 3, 21, 3 */
+  int32_t cnn_hidden_expansion_x2;       /* cnn_hidden_expansion * 2 = 4 */
+  int32_t num_transformer_layers;        /* 8 (each = local + global) */
+  int32_t num_transformer_heads;         /* 4 */
+  int32_t attention_size;                /* 64 */
+  int32_t compressed_attention_kv_size;  /* 64 */
+  int32_t transformer_intermediate;      /* dims[-1] * transformer_hidden_expansion = 512 */
+  int32_t use_graph;
+  int32_t use_pdl;
+} A2mConfig;
+int a2m_create_ex(const A2mConfig* config, A2mHandle** out);
 void a2m_destroy(A2mHandle* h);
 const char* a2m_last_error(const A2mHandle* h);
 
@@ -89,6 +111,13 @@ int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const
 int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,
                     const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host);
 int a2m_collect_host(A2mHandle* h, int32_t slot);
+/* The same with typed buffers.  audio_dtype A2M_F16: the windows arrive as IEEE binary16 -- lossless for audio that went
+ * through load_full_audio, which rounds every sample to f16 (python.rs:235-264) -- and are widened by the stem kernel.
+ * logits_host may be NULL (infer.py:41 keeps only the probabilities); out_dtype A2M_F16 returns the probabilities as
+ * binary16.  f16 in, probabilities only, f16 out moves 22.9 MB per 64 windows instead of 52.5 MB. */
+int a2m_submit_host_ex(A2mHandle* h, int32_t slot, const void* audio_host, int32_t audio_dtype, int32_t batch,
+                       const float* rope_cos_host, const float* rope_sin_host, int32_t rope_max_pos, float* logits_host,
+                       void* probs_host, int32_t out_dtype);
 /* Page-locked host memory for the calls above (cudaMallocHost / cudaFreeHost). */
 void* a2m_host_alloc(size_t bytes);
 void a2m_host_free(void* p);
@@ -107,6 +136,14 @@ int a2m_prepare_windows(A2mHandle* h, const float* clip_dev, int64_t n_samples, 
 /* Per-window validation loss (testset_loss_function, train.py:99-102): losses_dev[b] = sum_{t,c} BCEWithLogits(logits, labels)
  * over the [250, 90] frame grid of window b.  logits_dev / labels_dev [batch, 250, 90] fp32. */
 int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels_dev, int32_t batch, float* losses_dev, void* stream);
+
+/* detailed_event_loss (infer.py:94-158) for a batch of windows in one launch: per window, eventize the
+ * probabilities (extract_events, common.rs:47-144), rasterise the events (to_frame_events, python.rs:423-447) and compare with
+ * the annotation.  probs_dev / expected_dev [batch, frames, 90] fp32; metrics_dev [batch, 5] = full_diff, phantom_notes_diff,
+ * missed_notes_diff, notes_hit, hit_rate.  pred_frames_dev (optional) [batch, frames, 90] receives the rasterised prediction,
+ * n_events_dev (optional) [batch, 90] the number of events per key.  One thread per (window, key). */
+int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expected_dev, int32_t batch, int32_t frames,
+                      float* metrics_dev, float* pred_frames_dev, int32_t* n_events_dev, void* stream);
 
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
@@ -151,6 +188,12 @@ int a2m_debug_gemm(A2mHandle* h, int32_t block_n, int32_t M, int32_t N, int32_t 
 int a2m_train_init(A2mHandle* h, const void* blob_host, size_t blob_bytes, const A2mLeafDesc* table, int32_t n_leaves);
 int64_t a2m_param_count(const A2mHandle* h);                          /* floats in the blob */
 int a2m_get_params(A2mHandle* h, float* out_dev, void* stream);       /* current master parameters, blob layout */
+/* Overwrites the master parameters and re-derives the kernels' packed images: together with a2m_get/set_opt_state this is
+ * the snapshot / roll-back of the reference's non-finite recovery (train.py:334-382). */
+int a2m_set_params(A2mHandle* h, const float* params_dev, void* stream);
+/* AdamW first / second moments (optax ScaleByAdamState mu, nu), blob layout; either pointer may be NULL. */
+int a2m_get_opt_state(A2mHandle* h, float* m_dev, float* v_dev, void* stream);
+int a2m_set_opt_state(A2mHandle* h, const float* m_dev, const float* v_dev, void* stream);
 /* One learning-rate multiplier per leaf (layer-wise decay of train.py:646-726); NULL resets to 1. */
 int a2m_set_lr_multipliers(A2mHandle* h, const float* per_leaf_host, int32_t n_leaves);
 /* Dropout of the following a2m_forward_train / a2m_backward pairs: `rate` = transformer_dropout_rate (model.py:30) applied
@@ -167,6 +210,9 @@ int a2m_forward_train(A2mHandle* h, const float* audio_dev, int32_t batch, const
  * loss_dev[0] += that value.  labels_dev [batch, 250, 90] fp32.  Gradient accumulation over minibatches
  * (train.py:283-293) = repeated forward_train / backward calls on the same grads_dev. */
 int a2m_backward(A2mHandle* h, const float* labels_dev, float scale, float* grads_dev, float* loss_dev, void* stream);
+/* The same backward for an ARBITRARY cotangent of the logits (dlogits_dev [batch, 250, 90] fp32): grads_dev += J^T dlogits.
+ * This is the `bwd` of a jax.custom_vjp around a2m_forward_train: the loss stays the caller's. */
+int a2m_backward_dlogits(A2mHandle* h, const float* dlogits_dev, float* grads_dev, void* stream);
 /* Gradient buckets for an all-reduce that overlaps the backward (train.py:238-244 shards the batch; the exchange jit
  * inserts there is one collective here).  Bucket 0 = final norm + transformer + decoder (the tail of the leaf order),
  * final once the transformer backward has run; bucket 1 = the CNN, final when a2m_backward's work completes.
@@ -175,10 +221,25 @@ int a2m_backward(A2mHandle* h, const float* labels_dev, float scale, float* grad
 int32_t a2m_grad_bucket_count(const A2mHandle* h);
 int a2m_grad_bucket_range(const A2mHandle* h, int32_t bucket, size_t* lo, size_t* hi);
 int a2m_stream_wait_grad_bucket(A2mHandle* h, int32_t bucket, void* stream);
+/* Data-parallel gradient exchange (train.py:238-244 shards the batch over devices): mean over the ranks of
+ * `nccl_comm` (an ncclComm_t; NULL = the handle's own, a2m_comm_init) of the gradient blob and loss of the most recent
+ * a2m_backward.  Two buckets: bucket 0 is reduced on a communication stream owned by the handle as soon as the backward has
+ * produced it, under the CNN backward still running on `stream`; bucket 1 and the loss follow on `stream`, which then waits
+ * for the communication stream.  Collective: every rank calls it after the same a2m_backward.  libnccl is bound at run time
+ * (dlopen of libnccl.so.2 -- the copy already in the process if there is one), it is not a link-time dependency. */
+int a2m_allreduce_grads(A2mHandle* h, void* nccl_comm, void* stream);
+/* Rendezvous helpers for callers that have no communicator of their own: rank 0 calls a2m_comm_unique_id (ncclGetUniqueId,
+ * 128 bytes), ships the id to the other ranks by any side channel, every rank calls a2m_comm_init (ncclCommInitRank). */
+int a2m_comm_unique_id(void* id128_out);
+int a2m_comm_init(A2mHandle* h, const void* id128, int32_t nranks, int32_t rank);
+void* a2m_comm_get(const A2mHandle* h);   /* the ncclComm_t, or NULL */
+int a2m_comm_destroy(A2mHandle* h);
 /* optax.adamw then clip_by_global_norm(clip_norm) on the updates, applied to the master parameters; gradients are
  * divided by grad_divisor first (train.py:314).  step counts from 1.  stats_dev (optional, 2 floats): squared norm of
- * the unclipped update, number of non-finite gradient entries (train.py:320-322 grads_valid == 0).  The data-parallel
- * gradient all-reduce happens between a2m_backward and this call, on grads_dev, by the caller (NCCL). */
+ * the unclipped update, number of non-finite gradient entries (train.py:320-322 grads_valid == 0).  When that number is
+ * not zero the step is a NO-OP on the device: neither the parameters nor the moments are touched (the reference rolls back
+ * to a snapshot instead, train.py:369-377).  The data-parallel gradient all-reduce happens between a2m_backward and this
+ * call (a2m_allreduce_grads, or the caller's own collective on grads_dev). */
 int a2m_adamw_step(A2mHandle* h, const float* grads_dev, float lr, float b1, float b2, float eps, float weight_decay,
                    float grad_divisor, float clip_norm, int32_t step, float* stats_dev, void* stream);
 /* Per-launch profile of the training plans (which = 0 forward-with-tape, 1 backward); contract of a2m_profile_steps. */

@@ -37,6 +37,11 @@ def _ln_channels(x, p):
     return F.layer_norm(x.transpose(1, 2), (c,), p["weight"], p["bias"], 1e-5).transpose(1, 2)
 
 
+def _at_least_f32(x):
+    """The reference's `.astype(jnp.float32)` upcasts (from fp16); never a DOWNcast when the twin runs in fp64."""
+    return x.to(torch.promote_types(x.dtype, torch.float32))
+
+
 def _gelu(x):
     return F.gelu(x, approximate="tanh")
 
@@ -111,7 +116,7 @@ def _self_attention(x, p, rope, heads, dropout_p=0.0, wmask=None):
     v = F.linear(c, p["value_up_proj"]["weight"]).reshape(*lead, s, heads, -1)
     q, k, v = (t.transpose(-3, -2) for t in (q, k, v))              # (..., H, S, hd)
     logits = (q / math.sqrt(q.shape[-1])) @ k.transpose(-1, -2)
-    w = torch.softmax(logits.float(), dim=-1).to(logits.dtype)
+    w = torch.softmax(_at_least_f32(logits), dim=-1).to(logits.dtype)     # model.py:252 upcasts to fp32
     if wmask is not None:
         w = w * wmask
     elif dropout_p > 0.0:
@@ -218,5 +223,5 @@ def loss_fn(params, samples, targets, scale=1.0, rope=None, conf=None, masks=Non
     """train.py:39-62: per-sample sum of BCE-with-logits x scale, mean over batch.  Dropout is off unless `masks`
     (dropout_masks) replays the CUDA path's masks."""
     logits, _ = forward(params, samples, rope, conf, masks=masks)
-    per = F.binary_cross_entropy_with_logits(logits.float(), targets, reduction="none").sum(dim=(1, 2)) * scale
+    per = F.binary_cross_entropy_with_logits(_at_least_f32(logits), targets, reduction="none").sum(dim=(1, 2)) * scale
     return per.mean(), logits

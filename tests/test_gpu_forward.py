@@ -175,3 +175,22 @@ def test_batch_invariance_bitwise():
         _, p1 = model.predict(None, audio[k], rope)
         assert torch.equal(p1, pr[k])
     assert float(pr.std()) > 1e-3
+
+
+def test_host_path_f16_in_probs_only_f16_out(setup):
+    """a2m_submit_host_ex: audio shipped as IEEE binary16 (lossless: load_full_audio rounds to f16, python.rs:235-264), logits not
+    returned (infer.py:41 keeps only probs), probabilities returned as f32 or f16.  Same kernels, so the f32 probabilities are
+    bit-identical to the all-f32 call and the f16 ones are their correctly rounded values."""
+    import audio_to_midi_b200 as A
+    model, _tree, audio = setup[0], setup[1], setup[2]
+    rope = A.precompute_frequencies(64, 300)
+    a32 = np.ascontiguousarray(audio[:4])
+    a16 = a32.astype(np.float16)
+    assert np.array_equal(a16.astype(np.float32), a32)             # synthetic windows are f16-exact by construction
+    (lg, pr), = list(model.predict_pipelined([a32], rope, copy=True))
+    (lg2, pr2), = list(model.predict_pipelined([a16], rope, copy=True, want_logits=False))
+    assert lg2 is None and np.array_equal(pr2, pr)
+    (lg3, pr3), = list(model.predict_pipelined([a16], rope, copy=True, want_logits=False, probs_dtype=np.float16))
+    assert pr3.dtype == np.float16 and np.array_equal(pr3, pr.astype(np.float16))
+    (lg4, pr4), = list(model.predict_pipelined([a32], rope, copy=True, want_logits=True, probs_dtype=np.float16))
+    assert np.array_equal(lg4, lg) and np.array_equal(pr4, pr3)

@@ -250,3 +250,122 @@ def test_gradient_bucket_is_final_when_its_event_fires():
         assert float(final.abs().max()) > 0
     # the CNN bucket was still being produced when bucket 0 fired (otherwise nothing overlaps)
     assert not torch.equal(head_early, eng.grads[:buckets[0][0]])
+
+
+def test_train_then_predict_then_train_and_sync():
+    """the reference loop validates every N steps (train.py:396-437).  Inference through the model while a
+    TrainEngine is alive must (a) run on the weights being trained, (b) leave the training session intact, and
+    sync_to_model / save_checkpoint must store the TRAINED weights."""
+    import train_util as U
+    from oracle import params as P
+    tree, audio, labels = U.setup(2)
+    rope = A.precompute_frequencies(64, 300)
+    cfg = T.OptimizerConfig()
+    model = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
+    x, y = torch.tensor(audio).cuda(), torch.tensor(labels).cuda()
+    _, p_before = model.predict(None, x, rope)                       # the model's own inference handle
+    p_before = p_before.clone()
+    eng = T.TrainEngine(model, 0)
+    _, p_live0 = model.predict(None, x, rope)                        # now the trainer's handle, same weights (un-folded kv path)
+    assert (p_live0 - p_before).abs().max().item() < 2e-2
+    for i in range(3):
+        loss, valid, _ = eng.training_step(x, y, rope, cfg, 1e-2, key=1)
+        assert bool(valid.item())
+    _, p_live = model.predict(None, x, rope)                         # validation inside the loop: sees the trained weights
+    assert (p_live - p_before).abs().max().item() > 1e-3
+    loss2, valid2, _ = eng.training_step(x, y, rope, cfg, 1e-2, key=1)    # ... and the session survives it
+    assert bool(valid2.item()) and np.isfinite(float(loss2.item())) and float(loss2.item()) < float(loss.item()) * 1.5
+    # a second model can be resident next to the trainer without disturbing either
+    other, _ = make_model(3)
+    _, p_other = other.predict(None, x, rope)
+    assert torch.isfinite(p_other).all()
+    loss3, valid3, _ = eng.training_step(x, y, rope, cfg, 1e-2, key=1)
+    assert bool(valid3.item())
+    trained = eng.params_tree()
+    eng.sync_to_model()
+    leaves = dict(model.tree_leaves_with_path())
+    assert all(np.array_equal(np.asarray(leaves[k]), trained[k]) for k in trained)
+    assert not np.array_equal(np.asarray(leaves["decoder.decoder_pooling.weight"]), P.flatten(tree)["decoder.decoder_pooling.weight"])
+    _, p_sync = model.predict(None, x, rope)                         # still the trainer's handle
+    eng.close()
+    _, p_closed = model.predict(None, x, rope)                       # the model's own handle, re-loaded with the trained leaves
+    assert (p_closed - p_sync).abs().max().item() < 2e-2
+
+
+def test_non_finite_gradients_leave_state_untouched():
+    """ADVICE r1 / train.py:369-377: with an inf or NaN in the gradients the optimizer step is a device-side no-op -- master
+    weights and both moments are bit-identical afterwards, stats[1] counts the bad entries; snapshot()/restore() roll a
+    session back; train_pipelined reports the invalid step, halves the loss scale and takes the update count back."""
+    import train_util as U
+    from oracle import params as P
+    tree, audio, labels = U.setup(2)
+    rope = A.precompute_frequencies(64, 300)
+    cfg = T.OptimizerConfig()
+    model = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
+    eng = T.TrainEngine(model, 0)
+    x, y = torch.tensor(audio).cuda(), torch.tensor(labels).cuda()
+    eng.training_step(x, y, rope, cfg, 1e-3, key=1)
+    snap = eng.snapshot()
+    p0, m0, v0, step0 = snap
+    eng.zero_grad()
+    eng.forward_backward(x, y, rope)
+    eng.grads[12345] = float("inf")
+    eng.grads[-7] = float("nan")
+    eng.optimizer_step(1e-3, cfg)
+    torch.cuda.synchronize()
+    assert float(eng.stats[1].item()) == 2.0
+    p1, m1, v1, _ = eng.snapshot()
+    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+    eng.step_count -= 1
+    loss, valid, _ = eng.training_step(x, y, rope, cfg, 1e-3, key=1)          # a clean step moves everything again
+    assert bool(valid.item())
+    p2, m2, v2, _ = eng.snapshot()
+    assert not torch.equal(p0, p2) and not torch.equal(m0, m2)
+    eng.restore(snap)
+    p3, m3, v3, step3 = eng.snapshot()
+    assert torch.equal(p0, p3) and torch.equal(m0, m3) and torch.equal(v0, v3) and step3 == step0
+    # host-fed loop: the second batch carries an inf sample -> its step is reported invalid and skipped, the scale halves
+    bad = audio.copy()
+    bad[0, 0, 100] = np.inf
+    batches = [(torch.tensor(a_).pin_memory(), torch.tensor(labels).pin_memory()) for a_ in (audio, bad, audio)]
+    before = eng.step_count
+    losses, valids, scale = eng.train_pipelined(batches, rope, cfg, lambda i: 1e-3, first_step=before, grad_scale=4.0, return_valid=True)
+    assert valids == [True, False, True] and scale == 2.0 and eng.step_count == before + 2
+    assert np.isfinite(losses[0]) and np.isfinite(losses[2])
+    assert torch.isfinite(eng.params_flat()).all()
+
+
+def test_model_call_with_dropout_and_arbitrary_cotangent():
+    """b1: the reference's training call shape `vmap(model, (0, None, None, 0, None))(audio, state, rope, keys, True)`
+    (train.py:56-58) runs a2m_forward_train with dropout masks seeded by the keys; a2m_backward_dlogits with the BCE cotangent
+    reproduces a2m_backward (the custom_vjp pair a JAX host binds)."""
+    import train_util as U
+    from audio_to_midi_b200.model import fold_key
+    from oracle import model_torch as MT
+    from oracle import params as P
+    tree, audio, labels = U.setup(2)
+    rope = A.precompute_frequencies(64, 300)
+    model = A.OutputSequenceGenerator(A.model_config, key=0).load_leaves(P.flatten(tree))
+    x, y = torch.tensor(audio).cuda(), torch.tensor(labels).cuda()
+    keys = np.array([[0, 11], [0, 12]], np.uint32)
+    call = A.vmap(model, in_axes=(0, None, None, 0, None), out_axes=(0, None), axis_name="batch")
+    (logits, probs), state = call(x, None, rope, keys, True)
+    assert state is None and tuple(logits.shape) == (2, 250, 90)
+    masks = MT.dropout_masks(fold_key(keys), 0.1, 2)
+    with torch.no_grad():
+        zref, pref = MT.forward(MT.to_torch(tree), torch.tensor(audio), masks=masks)
+    assert (logits.cpu() - zref).abs().max().item() < 0.15 and (probs.cpu() - pref).abs().max().item() < 3e-2
+    (z_eval, _), _ = model(x, None, rope)                              # inference call: no dropout, different logits
+    assert (z_eval - logits).abs().max().item() > 1e-3
+    eng = model._live_trainer(0)
+    assert eng is not None
+    eng.zero_grad()
+    eng.backward(y, scale=2.0)
+    g_bce = eng.grads.clone()
+    (logits2, _), _ = call(x, None, rope, keys, True)                  # same keys -> same masks -> same forward
+    assert torch.equal(logits2, logits)
+    dz = (torch.sigmoid(logits2) - y) * (2.0 / 2)                      # d/dz of mean_b(sum BCE * scale), train.py:43-47,61-62
+    eng.zero_grad()
+    eng.backward_dlogits(dz)
+    rel = ((eng.grads - g_bce).norm() / g_bce.norm()).item()
+    assert rel < 2e-2, rel

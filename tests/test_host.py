@@ -123,7 +123,7 @@ def test_no_cpu_fallback():
     m = A.OutputSequenceGenerator(A.model_config, key=1)
     with pytest.raises(_lib.A2mError):
         m.predict(None, np.zeros((1, 2, 80000), np.float32), A.precompute_frequencies(64, 300))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.A2mError):     # the training-mode call shape (train.py:56-58) exists and is GPU-only as well
         m(np.zeros((2, 80000), np.float32), None, A.precompute_frequencies(64, 300), key=1, enable_dropout=True)
     with pytest.raises(ValueError):
         m.predict(None, np.zeros((2, 1000), np.float32), A.precompute_frequencies(64, 300))
@@ -238,3 +238,58 @@ def test_checkpoint_npz_round_trip(tmp_path):
     assert all(np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for k in a)
     assert not np.array_equal(np.asarray(dict(m0.tree_leaves_with_path())["decoder.decoder_pooling.weight"]),
                               np.asarray(b["decoder.decoder_pooling.weight"]))
+
+
+def test_checkpoint_ensemble_axis_and_converter_helpers(tmp_path):
+    """Checkpointed arrays carry the reference's leading ensemble axis (train.py:788-795: leaves are (1, ...), transformer
+    leaves (1, 8, ...)); load_newest_checkpoint selects a member (infer.py:213-221) and also accepts axis-free files.  The
+    orbax converter's npz-side helpers (nested dict <-> dotted key paths) round-trip the pytree."""
+    import importlib.util
+    from audio_to_midi_b200 import infer
+    m = A.OutputSequenceGenerator(A.model_config, key=5)
+    d = infer.save_checkpoint(m, str(tmp_path / "a"), 7)
+    with np.load(os.path.join(d, "params.npz")) as z:
+        assert z["norm.weight"].shape == (1, 256)
+        assert z["transformer.layers.local_attention.attention_block.self_attention.kv_down_proj.weight"].shape == (1, 8, 64, 256)
+        stacked = {k: np.concatenate([z[k], z[k] + 1.0]) for k in z.files}          # a two-member ensemble
+    got, _ = infer.load_newest_checkpoint(str(tmp_path / "a"))
+    a, b = dict(m.tree_leaves_with_path()), dict(got.tree_leaves_with_path())
+    assert all(np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for k in a)
+    os.makedirs(tmp_path / "b" / "9")
+    np.savez(tmp_path / "b" / "9" / "params.npz", **stacked)
+    got1, _ = infer.load_newest_checkpoint(str(tmp_path / "b"), ensemble_size=2, ensemble_select=1)
+    b1 = dict(got1.tree_leaves_with_path())
+    assert all(np.array_equal(np.asarray(a[k]) + 1.0, np.asarray(b1[k])) for k in a)
+    with pytest.raises(IndexError):
+        infer.load_newest_checkpoint(str(tmp_path / "b"), ensemble_select=2)
+    infer.save_checkpoint(m, str(tmp_path / "c"), 3, ensemble_axis=False)           # round-1 layout still loads
+    got2, _ = infer.load_newest_checkpoint(str(tmp_path / "c"))
+    assert all(np.array_equal(np.asarray(a[k]), np.asarray(v)) for k, v in got2.tree_leaves_with_path())
+    spec = importlib.util.spec_from_file_location("convert_orbax", os.path.join(ROOT, "tools", "convert_orbax.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    nested = conv.unflatten_tree({k: np.asarray(v) for k, v in a.items()})
+    assert set(nested) == {"layers", "norm", "transformer", "decoder"}                 # model.py:673-678 (transformer_projection is None)
+    assert set(nested["layers"]["5"]["layers"]) == {str(i) for i in range(22)}
+    flat = conv.flatten_tree(nested)
+    assert set(flat) == set(a) and all(np.array_equal(flat[k], np.asarray(a[k])) for k in a)
+
+
+def test_config_struct_and_key_folding():
+    """A2mConfig mirrors model_config (model.py:20-34); PRNG keys fold into one dropout seed deterministically."""
+    from audio_to_midi_b200 import model as Mo
+    c = Mo.default_config_struct(3)
+    assert c.device == 3 and list(c.dims)[:7] == [4, 8, 16, 32, 64, 128, 256] and list(c.depths)[:7] == [3, 3, 3, 3, 3, 21, 3]
+    assert (c.num_transformer_layers, c.num_transformer_heads, c.attention_size, c.compressed_attention_kv_size,
+            c.transformer_intermediate, c.cnn_hidden_expansion_x2) == (8, 4, 64, 64, 512, 4)
+    assert Mo.fold_key(None) == 0 and Mo.fold_key(5) == Mo.fold_key(np.array([5])) != Mo.fold_key(6)
+    assert Mo.fold_key(np.array([[0, 1], [0, 2]], np.uint32)) != Mo.fold_key(np.array([[0, 2], [0, 1]], np.uint32))
+    assert 0 <= Mo.fold_key(-3) < 2 ** 64
+
+
+def test_lr_schedule_is_zero_based():
+    """optax.scale_by_schedule evaluates schedule(count) BEFORE incrementing: the first update of the warm-up has lr 0."""
+    from audio_to_midi_b200 import train as T
+    s = T.create_learning_rate_schedule(1e-4, 1000, 200_000)
+    assert s(0) == 0.0 and abs(s(1) - 1e-7) < 1e-15 and abs(s(1000) - 1e-4) < 1e-12
+    assert s(1001) < 1e-4 and abs(s(1000 + 200_000)) < 1e-12

@@ -157,3 +157,102 @@ def test_bce_matches_torch():
     y = rng.uniform(size=(2, 250, 90))
     ref = torch.nn.functional.binary_cross_entropy_with_logits(torch.tensor(z), torch.tensor(y), reduction="none").sum(dim=(1, 2))
     np.testing.assert_allclose(M.bce_with_logits_sum(z, y), ref.numpy(), rtol=1e-12)
+
+
+def _piano_roll_probs(rng, frames=400, keys=90, notes=40):
+    """Probability track with clear notes (well away from every threshold) plus a low noise floor."""
+    p = rng.uniform(0.01, 0.04, size=(frames, keys)).astype(np.float32)
+    for _ in range(notes):
+        k, a, n = rng.integers(0, keys), rng.integers(0, frames - 30), rng.integers(8, 30)
+        t = np.arange(n)
+        p[a:a + n, k] = np.maximum(p[a:a + n, k], (0.95 * np.exp(-0.02 * t)).astype(np.float32))
+    return p
+
+
+def test_event_parity_instrument_can_fail():
+    """The eventized-parity checker (tests/event_parity.py) used by the GPU tests: (1) its replay of the state machine is the
+    oracle's extractor; (2) tracks within the tolerance pass and leave most keys DECIDED; (3) one probability moved across 0.5
+    by 2 x TOL fails; (4) a wrong event on a decided key fails; (5) a sub-tolerance nudge across a threshold is excused for
+    that key only."""
+    import pytest
+    from event_parity import check_event_parity, decision_margins
+    TOL = 3e-2
+    rng = np.random.Generator(np.random.PCG64(11))
+    ref = _piano_roll_probs(rng)
+    ev, m1, m2 = decision_margins(ref)
+    assert ev == E.extract_events(ref) and len(ev) >= 20
+    noisy = np.clip(ref + rng.uniform(-TOL / 4, TOL / 4, size=ref.shape).astype(np.float32), 0.0, 1.0)
+    n_dec, n_same = check_event_parity(ref, noisy, E.extract_events(noisy), TOL)
+    assert n_dec >= 60 and n_same >= n_dec
+    a, k = ev[0][0], ev[0][1]                       # the attack frame of a real note: p well above 0.5
+    bad = ref.copy()
+    bad[a, k] = 0.5 - 2 * TOL                       # (3) across the activation threshold by 2 x TOL
+    with pytest.raises(AssertionError, match="tolerance"):
+        check_event_parity(ref, bad, E.extract_events(bad), TOL)
+    wrong = [e for e in ev if e != ev[0]] + [(ev[0][0] + 1, k, ev[0][2], 7)]      # (4) same probabilities, event shifted a frame
+    with pytest.raises(AssertionError, match="event lists differ"):
+        check_event_parity(ref, ref, sorted(wrong), TOL)
+    near = ref.copy()
+    near[:, 3] = 0.02
+    near[100:110, 3] = 0.505                        # (5) a plateau 0.005 above the activation threshold ...
+    nudged = near.copy()
+    nudged[100:110, 3] = 0.495                      # ... pushed just below it: different events, legitimately undecided
+    ev_n = E.extract_events(nudged)
+    assert [e for e in ev_n if e[1] == 3] != [e for e in E.extract_events(near) if e[1] == 3]
+    n_dec2, _ = check_event_parity(near, nudged, ev_n, TOL)
+    assert n_dec2 >= 60
+
+
+def test_autograd_of_twin_matches_fp64_finite_differences():
+    """the gradient oracle of the training tests is torch autograd of oracle/model_torch.loss_fn.  Cross-check it
+    against central finite differences in fp64 on a shrunken configuration that still has every structure of the path: stem,
+    two downsamples, Blocks with active layer scale, one local (16-frame windows over 40 frames, padded to 48) and one global
+    transformer layer with RoPE, compressed kv and the GLU feed-forward, decoder, sum-BCE x scale, mean over the batch."""
+    conf = {"dims": [4, 8, 16], "depths": [1, 2, 1], "cnn_hidden_expansion": 2.0, "num_transformer_layers": 1,
+            "num_transformer_heads": 2, "attention_size": 8, "compressed_attention_q_size": 8, "compressed_attention_kv_size": 4,
+            "transformer_dropout_rate": 0.1, "transformer_hidden_expansion": 2.0, "sdd_rate": 0.1}
+    tree = P.init_params(3, conf=conf, gamma_mode="active", decoder_gain=2.0, trained_like=True)
+    rng = np.random.Generator(np.random.PCG64(5))
+    audio = torch.tensor(rng.normal(0, 0.5, size=(2, 2, 800)), dtype=torch.float64)           # 800 / 5 / 2 / 2 = 40 frames
+    labels = torch.tensor(np.clip((rng.random((2, 40, 90)) < 0.05).astype(np.float64), 0.005, 0.995))
+    cos, sin = T.precompute_frequencies(conf["attention_size"], 64)
+    rope = (cos.double(), sin.double())
+    tp = T.to_torch(tree, dtype=torch.float64)
+    leaves = {}
+
+    def mark(t, prefix=""):
+        if isinstance(t, dict):
+            return {k: mark(v, f"{prefix}{k}.") for k, v in t.items()}
+        if isinstance(t, list):
+            return [mark(v, f"{prefix}{i}.") for i, v in enumerate(t)]
+        t = t.clone().requires_grad_(True)
+        leaves[prefix[:-1]] = t
+        return t
+
+    tp = mark(tp)
+    loss, logits = T.loss_fn(tp, audio, labels, scale=3.0, rope=rope, conf=conf)
+    assert logits.shape == (2, 40, 90)
+    loss.backward()
+    checked = 0
+    worst = 0.0
+    with torch.no_grad():
+        for path, t in leaves.items():
+            if path.endswith("stochastic_depth_dropout.p"):
+                assert t.grad is None or float(t.grad.abs().max()) == 0.0     # never reaches the forward (model.py:160,167)
+                continue
+            flat, g = t.view(-1), t.grad.view(-1)
+            for idx in rng.choice(flat.numel(), size=min(2, flat.numel()), replace=False):
+                old = float(flat[idx])
+                h = 1e-5 * max(1.0, abs(old))
+                flat[idx] = old + h
+                lp, _ = T.loss_fn(tp, audio, labels, scale=3.0, rope=rope, conf=conf)
+                flat[idx] = old - h
+                lm, _ = T.loss_fn(tp, audio, labels, scale=3.0, rope=rope, conf=conf)
+                flat[idx] = old
+                fd = float(lp - lm) / (2 * h)
+                err = abs(fd - float(g[idx])) / max(abs(fd), abs(float(g[idx])), 1e-6)
+                worst = max(worst, err)
+                assert err < 1e-5, (path, int(idx), fd, float(g[idx]))
+                checked += 1
+    assert checked >= 80
+    print(f"finite differences: {checked} entries, worst relative error {worst:.2e}")
