@@ -58,5 +58,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+XLA_LIB = os.path.join(OUT_DIR, "liba2m_xla_ffi.so")
+
+
+def build_xla_ffi() -> str:
+    """Compiles csrc/a2m_xla_ffi.cc (the XLA typed-FFI handlers) against jaxlib's headers.  Only possible where jax is
+    installed -- not in this image: raises RuntimeError otherwise.  Host-only C++ (it forwards device pointers
+    to the C ABI), linked against the in-tree libaudio2midi_b200.so."""
+    try:
+        import jax.ffi
+        inc = jax.ffi.include_dir()
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError(f"jax.ffi is not importable here ({e}): the XLA-FFI handlers cannot be built") from e
+    build()
+    src = os.path.join(CSRC, "a2m_xla_ffi.cc")
+    if os.path.exists(XLA_LIB) and os.path.getmtime(XLA_LIB) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return XLA_LIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{inc}", f"-I{cuda_inc}", src, "-o", XLA_LIB,
+           f"-L{OUT_DIR}", "-laudio2midi_b200", f"-Wl,-rpath,{OUT_DIR}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed on a2m_xla_ffi.cc:\n" + res.stdout + res.stderr)
+    return XLA_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -1,22 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: batched model forward on synthetic windows (BASELINE.json configs[1]).
+"""Benchmark of the hot path: batched model forward on synthetic windows (BASELINE.json configs[1]), plus the other
+configurations north_star names (train step weak / strong scaling, long-clip transcription, validation pass).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
-One process per GPU (the driver launches N>1 through torch.distributed.run).  A "step" is one batched
-forward of B = 64 windows of 5 s per GPU (weak scaling: windows are independent, no collective).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+One process per GPU (the driver launches N>1 through torch.distributed.run).  A "step" is one batched forward of B = 64
+windows of 5 s per GPU (weak scaling: windows are independent, no collective).  Prints ONE JSON line (rank 0).
+See DESIGN.md "Measurement" for how each field is obtained.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import statistics
-import subprocess
-import sys
-import threading
-import time
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  The CPU arms of this file (--impl reference; cpu_baseline at N = 1) are
+# supposed to use all host cores, and the thread count must be in the environment BEFORE numpy / torch load their OpenMP and
+# MKL runtimes (round 1 printed a 100x too slow CPU baseline under torchrun for exactly this reason).
+_CORES = len(os.sched_getaffinity(0))
+if int(os.environ.get("RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_CORES)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -24,8 +34,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WINDOW_S = 5.0
-FLOPS_PER_WINDOW = 2 * 3_618_361_856  # SURVEY.md §8d: de-duplicated forward MACs x 2
+FLOPS_PER_WINDOW = 2 * 3_618_361_856  # SURVEY.md 8d: de-duplicated forward MACs x 2
+TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_WINDOW   # fwd + dgrad + wgrad, no recompute counted
 SEED = 1234
+DROPOUT = 0.1   # transformer_dropout_rate (model.py:30), applied as in train.py:56-58 (enable_dropout=True)
+PORT_NOTE = "PyTorch-CPU fp32 restatement (oracle/model_torch.py); the JAX reference is not installable (SURVEY F1)"
 
 
 def _peaks():
@@ -80,9 +93,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_forward_rate(n_windows: int, iters: int, threads: int):
-    """Times the oracle's PyTorch-CPU fp32 restatement (the reference cannot run: JAX absent).
-    Returns (audio-seconds per second, seconds per iteration)."""
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
+def cpu_forward_rate(n_windows: int, iters: int, threads: int, warmup: int = 1):
+    """Times the oracle's PyTorch-CPU fp32 restatement.  Returns (audio-seconds per second, seconds per iteration)."""
     import torch
     from oracle import model_torch as T
     from oracle import params as P
@@ -91,7 +104,8 @@ def cpu_forward_rate(n_windows: int, iters: int, threads: int):
     params = T.to_torch(P.init_params(SEED))
     audio = torch.tensor(synth.make_windows_fast(n_windows, SEED))
     with torch.no_grad():
-        T.forward(params, audio[:1])  # warm-up (thread pool, allocator)
+        for _ in range(max(warmup, 1)):
+            T.forward(params, audio)
         times = []
         for _ in range(iters):
             t0 = time.perf_counter()
@@ -102,9 +116,8 @@ def cpu_forward_rate(n_windows: int, iters: int, threads: int):
 
 
 def cpu_train_rate(n_windows: int, iters: int, threads: int):
-    """Forward + backward (torch autograd) of the oracle's loss_fn (train.py:39-62) on the host cores: the training-step
-    counterpart of cpu_forward_rate, on a bounded sample.  Optimizer time is not included (it is < 1 % on the CPU).
-    Returns (samples per second, seconds per iteration)."""
+    """Forward + backward (torch autograd) of the oracle's loss_fn (train.py:39-62) on the host cores, on a bounded sample.
+    Optimizer time is not included (< 1 % on the CPU).  Returns (samples per second, seconds per iteration)."""
     import torch
     from oracle import model_torch as T
     from oracle import params as P
@@ -140,89 +153,106 @@ def cpu_train_rate(n_windows: int, iters: int, threads: int):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The JAX reference cannot be imported
-    (no jax/equinox in the image, /root/reference absent on the GPU box), so this times the oracle port."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores.  The JAX reference cannot be
+    imported (no jax / equinox in the image; /root/reference does not exist on the GPU box), so this times the oracle port --
+    on the SAME step as our arm (args.batch windows per GPU per step, same warm-up and step counts), bounded to 128 windows per
+    step so that an N = 8 launch still ends within a few minutes (the metric, audio-seconds per second, does not depend on it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    sample = 4
-    # warm-up + K steps, each a bounded sample of the B-window workload
     import torch
     from oracle import model_torch as T
     from oracle import params as P
     from oracle import synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = _CORES
     torch.set_num_threads(cores)
+    sample = min(args.batch * world, 128)
+    W = max(args.warmup, 3)
     params = T.to_torch(P.init_params(SEED))
     audio = torch.tensor(synth.make_windows_fast(sample, SEED))
     with torch.no_grad():
-        for _ in range(min(args.warmup, 2)):
+        for _ in range(W):
             T.forward(params, audio)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             T.forward(params, audio)
         dt = time.perf_counter() - t0
+        # config 1 (BASELINE.json configs[0]): one clip window, batch 1
+        one = audio[:1]
+        T.forward(params, one)
+        t1 = time.perf_counter()
+        for _ in range(5):
+            T.forward(params, one)
+        dt1 = (time.perf_counter() - t1) / 5
     value = sample * WINDOW_S * args.steps / dt
     line = {
         "impl": "reference", "metric": "audio-seconds/sec transcribed (fwd)", "value": value, "unit": "audio-s/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / args.steps * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"batched forward of the default model, {args.batch} synthetic 5 s windows per GPU "
-                               f"(configs[1]); CPU arm runs a bounded sample of {sample} windows per step"},
+                               f"(BASELINE.json configs[1]), random-init weights, windows batch-partitioned across GPUs",
+                   "batch_per_gpu": args.batch, "cpu_windows_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} windows per step x {args.steps} steps, PyTorch-CPU fp32 restatement "
-                                   f"(oracle/model_torch.py); JAX reference not installable here"},
+                         "sample": f"{sample} windows per step x {args.steps} steps after {W} warm-ups; {PORT_NOTE}",
+                         "config1_batch1": {"value": WINDOW_S / dt1, "unit": "audio-s/s", "ms_per_window": dt1 * 1e3,
+                                            "what": "BASELINE.json configs[0]: one 5 s window, batch 1, CPU"}},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-DROPOUT = 0.1   # transformer_dropout_rate (model.py:30), applied as in train.py:56-58 (enable_dropout=True)
-TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_WINDOW   # SURVEY.md §8d: fwd + dgrad + wgrad, no recompute counted
+# ------------------------------------------------------------------------------------------------ our arm: training
+class Ctx:
+    pass
 
 
-def measure_train(args, A, synth, dev, rank, world, dist, local):
-    """Train step of config 4 (train.py:259-332): forward with tape, backward, NCCL gradient all-reduce, AdamW + clip.
-    B windows per GPU per step (weak scaling, global batch = B x world).  Returns the "train" object of the JSON line."""
+def _max_over_ranks(ctx, x: float) -> float:
+    import torch
+    t = torch.tensor([x], device=ctx.dev, dtype=torch.float64)
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(ctx):
+    import torch
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    torch.cuda.synchronize()
+
+
+def measure_train(ctx, args, eng, B, K, label, e2e=True):
+    """One training configuration: B windows per GPU per step; forward with tape, backward, gradient all-reduce (a2m_allreduce_grads:
+    NCCL inside the library, bucket 0 under the CNN backward), AdamW + clip, weight re-pack (train.py:259-332)."""
     import torch
     from audio_to_midi_b200 import train as T
-    B = args.train_batch
-    model = A.OutputSequenceGenerator(A.model_config, key=SEED)
-    eng = T.TrainEngine(model, local)
+    A, synth, rank, world = ctx.A, ctx.synth, ctx.rank, ctx.world
     cfg = T.OptimizerConfig()
-    eng.set_lr_multipliers(T.layer_lr_multipliers(eng.paths, cfg.layer_lr_decay))
     sched = T.create_learning_rate_schedule(cfg.base_learning_rate, cfg.warmup_steps, cfg.num_steps)
-    rope = A.precompute_frequencies(A.model_config["attention_size"], 300)
+    rope = ctx.rope
     R = 3
     host = [synth.make_windows_fast(B, SEED + 31 * (rank * R + r)) for r in range(R)]
     rng = np.random.Generator(np.random.PCG64(SEED + rank))
     host_y = [np.clip((rng.random((B, 250, 90)) < 0.02).astype(np.float32), 0.005, 0.995) for _ in range(R)]
-    dev_x = [torch.tensor(h, device=dev) for h in host]
-    dev_y = [torch.tensor(h, device=dev) for h in host_y]
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    W, K = max(args.warmup, 3), args.train_steps
+    dev_x = [torch.tensor(h, device=ctx.dev) for h in host]
+    dev_y = [torch.tensor(h, device=ctx.dev) for h in host_y]
+    W = max(args.warmup, 3)
+    step0 = eng.step_count + 1000      # past the zero-lr first update of the warm-up schedule
     for i in range(W):
-        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(i + 1), dropout_rate=DROPOUT, key=SEED)
-    barrier()
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(step0 + i), dropout_rate=DROPOUT, key=SEED)
+    _barrier(ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(W + i + 1), dropout_rate=DROPOUT, key=SEED)
+        eng.training_step(dev_x[i % R], dev_y[i % R], rope, cfg, sched(step0 + W + i), dropout_rate=DROPOUT, key=SEED)
     e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    _barrier(ctx)
+    ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
     loss_last = float(eng.loss.item())
-    # phase breakdown (one rank's events; separate untimed pass)
+    # phase breakdown (this rank's events; separate untimed pass).  "allreduce" is the EXPOSED time: from the end of the backward
+    # on the compute stream to the point where that stream holds the fully reduced gradients.
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     acc = np.zeros(4)
     cos, sin = eng._rope_tensors(rope)
@@ -236,145 +266,321 @@ def measure_train(args, A, synth, dev, rank, world, dist, local):
         ev[2].record()
         eng.allreduce_grads()
         ev[3].record()
-        eng.optimizer_step(sched(W + K + i + 1), cfg)
+        eng.optimizer_step(sched(step0), cfg)
         ev[4].record()
         torch.cuda.synchronize()
         acc += np.array([ev[j].elapsed_time(ev[j + 1]) for j in range(4)])
     acc /= 3
-    # end to end: pinned host audio + labels copied in every step, loss read back every step
-    pin_x = [torch.tensor(h).pin_memory() for h in host]
-    pin_y = [torch.tensor(h).pin_memory() for h in host_y]
-    batches = [(pin_x[i % R], pin_y[i % R]) for i in range(K)]
-    eng.train_pipelined(batches[:2], rope, cfg, sched, first_step=W + K + 4, dropout_rate=DROPOUT, key=SEED)   # warm the copy path
-    barrier()
-    t0 = time.perf_counter()
-    losses = eng.train_pipelined(batches, rope, cfg, sched, first_step=W + K + 6, dropout_rate=DROPOUT, key=SEED)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    lv = losses[-1]
-    t = torch.tensor([dt], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    value = world * B * K / (ms / 1e3)
-    peaks = _peaks()
-    cpu_train = None
-    if rank == 0:
-        cores = len(os.sched_getaffinity(0))
-        rate, sec = cpu_train_rate(4, 2, cores)
-        cpu_train = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                     "sample": f"forward + backward of 4 windows x 2 iterations ({sec:.2f} s each), torch autograd of the oracle's loss_fn "
-                               f"(oracle/model_torch.py); JAX reference not installable (SURVEY F1)"}
-    return {
-        "cpu_baseline": cpu_train,
-        "metric": "train samples/sec", "value": value, "unit": "samples/s", "ms_per_step": ms / K, "steps": K, "warmup": W,
-        "batch_per_gpu": B, "global_batch": B * world, "scaling": "weak",
-        "step": "forward with tape + backward + gradient all-reduce (NCCL) + AdamW/clip + weight re-pack (train.py:259-332)",
+    out = {
+        "metric": "train samples/sec", "value": world * B * K / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / K, "steps": K,
+        "warmup": W, "batch_per_gpu": B, "global_batch": B * world, "scaling": label,
+        "step": "forward with tape + backward + gradient all-reduce (a2m_allreduce_grads: NCCL, two buckets, the first under the CNN "
+                "backward) + AdamW/clip + weight re-pack (train.py:259-332)",
         "dtype": "bf16 operands, fp32 accumulate / master weights / optimizer state (reference: fp16 forward+backward, fp32 master)",
-        "dropout": DROPOUT,
-        "breakdown_ms": {"forward": round(acc[0], 3), "backward": round(acc[1], 3), "allreduce": round(acc[2], 3),
-                         "adamw_repack": round(acc[3], 3)},
+        "dropout": DROPOUT, "allreduce_backend": "a2m (in-library NCCL)" if eng.comm_ready else ("torch.distributed" if world > 1 else "none"),
+        "breakdown_ms": {"forward": round(float(acc[0]), 3), "backward": round(float(acc[1]), 3),
+                         "allreduce_exposed": round(float(acc[2]), 3), "adamw_repack": round(float(acc[3]), 3)},
         "tflops": world * B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12,
-        "frac_of_tensor_peak": B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12 / peaks["tensor_sustained"],
-        "e2e": {"value": world * B * K / dt, "unit": "samples/s", "h2d_bytes_per_step": B * (2 * 80000 + 250 * 90) * 4,
-                "d2h_bytes_per_step": 4,
-                "api": "TrainEngine.train_pipelined (next batch's H2D on a copy stream, loss read back every step, consumed one step later)"},
-        "gpu_launches": eng.launch_count() * K, "last_loss": lv, "loss_after_timed": loss_last,
-        "allreduce_bytes": eng.n_params * 4,
+        "frac_of_tensor_peak": B * TRAIN_FLOPS_PER_SAMPLE / (ms / K / 1e3) / 1e12 / _peaks()["tensor_sustained"],
+        "gpu_launches": eng.launch_count() * K, "loss_after_timed": loss_last, "allreduce_bytes": eng.n_params * 4,
     }
+    if e2e:
+        # end to end: pinned host audio + labels copied in every step, loss + validity read back every step
+        pin_x = [torch.tensor(h).pin_memory() for h in host]
+        pin_y = [torch.tensor(h).pin_memory() for h in host_y]
+        batches = [(pin_x[i % R], pin_y[i % R]) for i in range(K)]
+        eng.train_pipelined(batches[:2], rope, cfg, sched, first_step=step0, dropout_rate=DROPOUT, key=SEED)   # warm the copy path
+        _barrier(ctx)
+        t0 = time.perf_counter()
+        losses = eng.train_pipelined(batches, rope, cfg, sched, first_step=step0, dropout_rate=DROPOUT, key=SEED)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(ctx, time.perf_counter() - t0)
+        out["e2e"] = {"value": world * B * K / dt, "unit": "samples/s", "h2d_bytes_per_step": B * (2 * 80000 + 250 * 90) * 4,
+                      "d2h_bytes_per_step": 8,
+                      "api": "TrainEngine.train_pipelined (next batch's H2D on a copy stream; loss and grads_valid read back every step, "
+                             "consumed one step later)"}
+        out["last_loss"] = losses[-1]
+    return out
 
 
+def train_roofline(eng):
+    """Dominant kernel family of the training step (per-launch CUDA events of both plans), against the tensor roof."""
+    peaks = _peaks()
+    fam = {}
+    for which in (0, 1):
+        for k, pms, fl, by in eng.profile_steps(which, repeats=3):
+            f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            f["ms"] += pms; f["flops"] += fl; f["bytes"] += by; f["n"] += 1
+    total = sum(f["ms"] for f in fam.values())
+    name, f = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    ach = f["flops"] / (f["ms"] / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+            "frac": ach / peaks["tensor_sustained"], "traffic": None, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
+            "share_of_serialised_step": f["ms"] / total,
+            "hbm": {"achieved": f["bytes"] / (f["ms"] / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": f["bytes"] / (f["ms"] / 1e3) / 1e9 / peaks["hbm"]},
+            "note": "per-launch times are serialised (side-stream wgrad kernels overlap the main chain in the real step)",
+            "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+
+
+def dp_selfcheck(ctx, eng_small):
+    """Data-parallel correctness on the GPUs: the gradients after the all-reduce over `world` ranks x b windows
+    equal the 1-rank gradients of the concatenated batch.  Dropout off (masks are indexed by the local sample position)."""
+    import torch
+    A, synth, rank, world = ctx.A, ctx.synth, ctx.rank, ctx.world
+    b = 2
+    audio, labels = synth.make_windows(b * world, SEED + 5, with_labels=True)      # identical on every rank (same seed)
+    x = torch.tensor(audio, device=ctx.dev)
+    y = torch.tensor(labels, device=ctx.dev)
+    out = {}
+    for backend in (["a2m", "torch"] if eng_small.comm_ready else ["torch"]):
+        eng_small.zero_grad()
+        eng_small.set_dropout(0.0, 0)
+        eng_small.forward_backward(x[rank * b:(rank + 1) * b], y[rank * b:(rank + 1) * b], ctx.rope)
+        eng_small.allreduce_grads(backend=backend)
+        torch.cuda.synchronize()
+        out[backend] = (eng_small.grads.clone(), float(eng_small.loss.item()))
+    eng_small.zero_grad()
+    eng_small.forward_backward(x, y, ctx.rope)
+    torch.cuda.synchronize()
+    g1, l1 = eng_small.grads.clone(), float(eng_small.loss.item())
+    res = {"ranks": world, "windows_per_rank": b}
+    for backend, (g, l) in out.items():
+        rel = float(((g - g1).norm() / g1.norm()).item())
+        res[backend] = {"grad_rel_l2_vs_one_rank": rel, "loss_rel": abs(l - l1) / abs(l1), "ok": bool(rel < 1e-3)}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ our arm: configs 5 and 3
+def measure_clip(ctx, model):
+    """BASELINE config 5: a 10-minute clip (9.6 M samples per channel) -> device normalise + slice (134 windows at 0.5 s overlap) ->
+    this rank's block through the batched forward -> rank-ordered all_gather of the probabilities -> rank 0 stitches (30 175 frames)
+    and eventizes.  Host clip in page-locked memory; the timed region starts at the H2D copy and ends when rank 0 holds the events."""
+    import torch
+    from audio_to_midi_b200 import infer as I
+    base = ctx.synth.make_clip(30.0, SEED + 9)
+    rng = np.random.Generator(np.random.PCG64(SEED + 10))
+    clip = np.concatenate([base * np.float32(g) for g in rng.uniform(0.7, 1.3, size=20)], axis=1).astype(np.float32)
+    assert clip.shape == (2, 9_600_000)
+    pin = torch.tensor(clip).pin_memory()
+    times, n_events, frames, n_windows = [], 0, 0, 0
+    for it in range(4):
+        _barrier(ctx)
+        t0 = time.perf_counter()
+        dev_clip = pin.to(ctx.dev, non_blocking=True)
+        events, stitched, probs = I.transcribe_clip(model, dev_clip, overlap=0.5, max_batch=64)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(ctx, time.perf_counter() - t0)
+        if it > 0:
+            times.append(dt)
+        if ctx.rank == 0:
+            n_events, frames, n_windows = len(events), int(stitched.shape[0]), int(probs.shape[0])
+    best = statistics.median(times)
+    return {"metric": "clip audio-seconds/sec transcribed end to end", "value": 600.0 / best, "unit": "audio-s/s", "seconds_per_clip": best,
+            "clip_seconds": 600.0, "windows": n_windows, "windows_per_gpu": -(-n_windows // ctx.world), "stitched_frames": frames, "events": n_events,
+            "h2d_bytes": int(clip.nbytes) * ctx.world, "gather": "all_gather of [windows/N, 250, 90] fp32 blocks (NCCL), rank 0 stitches + eventizes (C++)" if ctx.world > 1 else "none (one rank)",
+            "what": "BASELINE.json configs[4]; infer.transcribe_clip; median of 3 after 1 warm-up; every rank uploads and normalises the whole clip "
+                    "(the loudness statistics need all of it), then forwards only its block of windows"}
+
+
+def measure_eval(ctx, model):
+    """BASELINE config 3: validation loss / hit-rate over 512 annotated windows, windows batch-partitioned over the ranks; per-window
+    BCE and event metrics on the device, [512, 6] floats gathered in rank order."""
+    import torch
+    from audio_to_midi_b200 import infer as I
+    a, y = ctx.synth.make_windows(32, SEED + 3, with_labels=True)
+    audio = np.tile(a, (16, 1, 1))
+    labels = np.tile(y, (16, 1, 1))
+    times = []
+    for it in range(3):
+        _barrier(ctx)
+        t0 = time.perf_counter()
+        lo, hi, losses, details = I.compute_testset_loss(model, audio, labels, max_batch=64)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(ctx, time.perf_counter() - t0)
+        if it > 0:
+            times.append(dt)
+    best = statistics.median(times)
+    hit = float(np.mean([d["hit_rate"] for d in details]))
+    return {"metric": "validation windows/sec", "value": 512 / best, "unit": "windows/s", "seconds": best, "windows": 512,
+            "mean_loss": float(np.mean(losses)), "mean_hit_rate": hit, "results_gathered": int(len(losses)),
+            "what": "BASELINE.json configs[2]; infer.compute_testset_loss from pageable host arrays (H2D inside), a2m_window_losses + "
+                    "a2m_event_metrics on the device, gather of [n, 6] floats; random-init weights, so the hit rate itself is meaningless"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm: forward
 def run_ours(args):
     import torch
     import audio_to_midi_b200 as A
+    from audio_to_midi_b200 import hostbind
+    from audio_to_midi_b200 import train as T
     from oracle import synth  # synthetic inputs only (seeded generator); not on the measured path
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    ctx = Ctx()
+    ctx.A, ctx.synth = A, synth
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
+    placement = hostbind.bind_to_gpu_numa(local)       # before any page-locked allocation
+    ctx.dev = dev = torch.device("cuda", local)
+
+    # ---- CPU baselines: N = 1 only, BEFORE any process group exists (no rank ever waits in a collective for CPU work)
+    cpu_fwd = cpu_train = None
+    if world == 1 and not args.no_cpu:
+        cores = _CORES
+        cpu_n, cpu_iters = 64, 3
+        rate, sec = cpu_forward_rate(cpu_n, cpu_iters, cores)
+        rate1, sec1 = cpu_forward_rate(1, 5, cores)
+        cpu_fwd = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                   "sample": f"the same {cpu_n}-window step x {cpu_iters} iterations ({sec:.2f} s each); {PORT_NOTE}",
+                   "config1_batch1": {"value": rate1, "unit": "audio-s/s", "ms_per_window": sec1 * 1e3,
+                                      "what": "BASELINE.json configs[0]: one 5 s window, batch 1, CPU"}}
+        trate, tsec = cpu_train_rate(8, 2, cores)
+        cpu_train = {"value": trate, "unit": "samples/s", "cores": cores, "kind": "port",
+                     "sample": f"forward + backward of 8 windows x 2 iterations ({tsec:.2f} s each), torch autograd of the oracle's loss_fn; {PORT_NOTE}"}
+
+    ctx.dist = dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        ctx.dist = dist
 
     B = args.batch
     model = A.OutputSequenceGenerator(A.model_config, key=SEED)      # random-init weights of the reference architecture
-    rope = A.precompute_frequencies(A.model_config["attention_size"], 300)
+    ctx.rope = rope = A.precompute_frequencies(A.model_config["attention_size"], 300)
     # inputs: R distinct batches so that consecutive steps read different audio (R * B * 640 KB > 126 MB L2)
     R = max(2, -(-140_000_000 // (B * 640_000)))
     host_batches = [synth.make_windows_fast(B, SEED + 17 * (rank * R + r)) for r in range(R)]
     dev_batches = [torch.tensor(h, device=dev) for h in host_batches]
     predict = A.vmap(model.predict, in_axes=(None, 0, None))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    W = max(args.warmup, 3)
 
     # ---- warm-up (also builds plan + CUDA graph)
-    for i in range(max(args.warmup, 3)):
+    for i in range(W):
         predict(None, dev_batches[i % R], rope)
     torch.cuda.synchronize()
     launches_per_step = model.last_launch_count(local)
 
     # ---- device-resident timing: exactly K steps between two events on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(ctx)
     with ClockSampler(local) as clocks:
         e0.record()
         for i in range(args.steps):
             predict(None, dev_batches[i % R], rope)
         e1.record()
-        barrier()
+        _barrier(ctx)
         ms = e0.elapsed_time(e1)
         # keep the sampler alive long enough for at least a few samples under load
         t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
         while time.perf_counter() < t_end:
             predict(None, dev_batches[0], rope)
         torch.cuda.synchronize()
-    t = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = _max_over_ranks(ctx, ms)
     value = world * B * WINDOW_S * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with HOST buffers: every step's H2D (from page-locked memory) and D2H
-    # are inside the timed region.  model.predict_pipelined keeps two batches in flight (copy/compute overlap).
-    pinned = []
+    # ---- end to end through the public API with HOST buffers: every step's H2D (from page-locked memory) and D2H are inside the
+    # timed region.  model.predict_pipelined keeps two batches in flight (copy/compute overlap).  Three byte budgets:
+    #   headline  f16 audio in (lossless: the loader rounds to f16, python.rs:235-264), probabilities only, fp32 (what infer.py:41 keeps)
+    #   compact   f16 in, probabilities only, f16 out
+    #   full_f32  fp32 in, logits + probabilities fp32 out (round 1's path)
+    def e2e_run(pinned, **kw):
+        for _ in model.predict_pipelined((pinned[i % R] for i in range(3)), rope, **kw):
+            pass
+        _barrier(ctx)
+        t0 = time.perf_counter()
+        n_done, last = 0, None
+        for _lg, pr in model.predict_pipelined((pinned[i % R] for i in range(args.steps)), rope, **kw):
+            n_done += 1
+            last = pr
+        dt = time.perf_counter() - t0
+        assert n_done == args.steps and float(last[0, 0, 0]) == float(last[0, 0, 0])
+        return world * B * WINDOW_S * args.steps / _max_over_ranks(ctx, dt)
+
+    pinned32, pinned16 = [], []
     for hb in host_batches:
-        pb = A.pinned_empty(hb.shape)
-        pb[...] = hb
-        pinned.append(pb)
-    for _lg, _pr in model.predict_pipelined((pinned[i % R] for i in range(3)), rope):
-        pass
-    barrier()
-    t0 = time.perf_counter()
-    n_done = 0
-    for _lg, pr in model.predict_pipelined((pinned[i % R] for i in range(args.steps)), rope):
-        n_done += 1
-    dt = time.perf_counter() - t0
-    assert n_done == args.steps and float(pr[0, 0, 0]) == float(pr[0, 0, 0])
-    t = torch.tensor([dt], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * B * WINDOW_S * args.steps / float(t.item())
+        p32 = A.pinned_empty(hb.shape)
+        p32[...] = hb
+        p16 = A.pinned_empty(hb.shape, np.float16)
+        p16[...] = hb                                   # exact: the synthetic audio is f16-rounded like the loader's
+        pinned32.append(p32)
+        pinned16.append(p16)
+    e2e = e2e_run(pinned16, want_logits=False)
+    e2e_compact = e2e_run(pinned16, want_logits=False, probs_dtype=np.float16)
+    e2e_full = e2e_run(pinned32)
     # the plain synchronous call (numpy in, numpy out, pageable memory), for comparison
     predict(None, host_batches[0], rope)
     t0 = time.perf_counter()
     for i in range(min(args.steps, 5)):
         predict(None, host_batches[i % R], rope)
     e2e_sync = B * WINDOW_S * min(args.steps, 5) / (time.perf_counter() - t0)
+    del pinned32, pinned16
 
-    # ---- training step (config 4); shares the device with the forward model, runs after it
-    train = None
+    # ---- roofline of the dominant kernel, from per-launch CUDA-event timings of the same plan (rank 0)
+    roof = None
+    if rank == 0:
+        peaks = _peaks()
+        prof = model.profile_steps(B, repeats=5, device=local)
+        fam = {}
+        for k, pms, fl, by in prof:
+            f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            f["ms"] += pms; f["flops"] += fl; f["bytes"] += by; f["n"] += 1
+        total_ms = sum(f["ms"] for f in fam.values())
+        name, f = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        # SURVEY 8d: the path is held against the TENSOR roof (intensity 8 800 FLOP/B against a balance of ~210); the kernel's
+        # algorithmic bytes against the HBM peak are kept as a second figure
+        achieved = f["flops"] / (f["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                "hbm": {"achieved": f["bytes"] / (f["ms"] / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": f["bytes"] / (f["ms"] / 1e3) / 1e9 / peaks["hbm"],
+                        "note": "algorithmic bytes of the kernel / its time; its operands are L2-resident in the steady state"}}
+        try:
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            with open(tf) as fh:
+                roof["traffic"] = json.load(fh).get(name)
+            roof["traffic_source"] = os.path.relpath(tf, ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+        except Exception:
+            pass
+        roof.update({"kernel": name, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
+                     "share_of_step": f["ms"] / total_ms, "peak_source": peaks["src"] + ", sustained bf16 figure",
+                     "flops_per_launch_avg": f["flops"] / f["n"], "bytes_per_launch_avg": f["bytes"] / f["n"],
+                     "whole_step_tflops": B * FLOPS_PER_WINDOW / (ms / args.steps / 1e3) / 1e12,
+                     "whole_step_frac": B * FLOPS_PER_WINDOW / (ms / args.steps / 1e3) / 1e12 / peaks["tensor_sustained"],
+                     "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}})
+
+    # ---- configs 5 and 3 (inference-side, sharded by windows)
+    clip = evalr = None
+    if not args.no_extra:
+        clip = measure_clip(ctx, model)
+        evalr = measure_eval(ctx, model)
+
+    # ---- training step (config 4): weak scaling (64 windows per GPU) and the reference's own global batch of 64 (strong)
+    train = train_b64 = None
     if not args.no_train:
         del dev_batches
         torch.cuda.empty_cache()
-        train = measure_train(args, A, synth, dev, rank, world, dist, local)
+        tmodel = A.OutputSequenceGenerator(A.model_config, key=SEED)
+        eng = T.TrainEngine(tmodel, local)
+        eng.set_lr_multipliers(T.layer_lr_multipliers(eng.paths, T.OptimizerConfig().layer_lr_decay))
+        if world > 1:
+            eng.init_comm()
+        train = measure_train(ctx, args, eng, args.train_batch, args.train_steps, "weak")
+        if rank == 0:
+            train["roofline"] = train_roofline(eng)
+        train["cpu_baseline"] = cpu_train
+        if world > 1 and 64 % world == 0:
+            train_b64 = measure_train(ctx, args, eng, 64 // world, args.train_steps, "strong", e2e=False)
+            train_b64["what"] = "the reference's own configuration: global batch 64 (train.py:743-744), 64 / N windows per GPU"
+            train_b64["dp_selfcheck"] = dp_selfcheck(ctx, eng)
+        elif world == 1:
+            train_b64 = {"same_as": "train (one GPU: global batch 64 = 64 windows per GPU)", "value": train["value"], "unit": "samples/s",
+                         "ms_per_step": train["ms_per_step"], "global_batch": 64, "scaling": "strong"}
+        eng.close()
 
     if rank != 0:
         if dist is not None:
@@ -382,70 +588,30 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, from per-launch CUDA-event timings of the same plan
-    peaks = _peaks()
-    prof = model.profile_steps(B, repeats=5, device=local)
-    fam = {}
-    for k, pms, fl, by in prof:
-        f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
-        f["ms"] += pms; f["flops"] += fl; f["bytes"] += by; f["n"] += 1
-    total_ms = sum(f["ms"] for f in fam.values())
-    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    name, f = top
-    # which roof bounds the kernel: its algorithmic intensity (FLOP per byte) against the machine balance of the measured peaks
-    balance = peaks["tensor_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
-    tensor_bound = f["bytes"] > 0 and f["flops"] / f["bytes"] > balance
-    if tensor_bound:
-        achieved = f["flops"] / (f["ms"] / 1e3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tensor_sustained"], "traffic": None}
-    else:
-        achieved = f["bytes"] / (f["ms"] / 1e3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm"], "traffic": None}
-    # measured DRAM traffic of that kernel (one ncu --set full capture per round, profiles/*_traffic.json), per launch
-    try:
-        import glob
-        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
-        with open(tf) as fh:
-            roof["traffic"] = json.load(fh).get(name)
-        roof["traffic_source"] = os.path.relpath(tf, ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
-    except Exception:
-        pass
-    roof.update({"kernel": name, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
-                 "share_of_step": f["ms"] / total_ms, "peak_source": peaks["src"] + ", sustained bf16 figure",
-                 "intensity_flop_per_byte": f["flops"] / max(f["bytes"], 1.0), "machine_balance": balance,
-                 "flops_per_launch_avg": f["flops"] / f["n"], "bytes_per_launch_avg": f["bytes"] / f["n"],
-                 "whole_step_tflops": B * FLOPS_PER_WINDOW / (ms / args.steps / 1e3) / 1e12,
-                 "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}})
-
-    # ---- CPU baseline on this host (bounded sample)
-    cores = len(os.sched_getaffinity(0))
-    cpu_n, cpu_iters = 8, 3
-    cpu_rate, cpu_s = cpu_forward_rate(cpu_n, cpu_iters, cores)
-
     line = {
         "metric": "audio-seconds/sec transcribed (fwd)", "value": value, "unit": "audio-s/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"batched forward of the default model, {B} synthetic 5 s windows per GPU "
                                f"(BASELINE.json configs[1]), random-init weights, windows batch-partitioned across GPUs",
                    "batch_per_gpu": B, "l2": f"inputs rotated over {R} distinct batches ({R * B * 0.64:.0f} MB > 126 MB L2); "
                                              "weights and activations stay L2-resident as in steady-state serving",
-                   "accumulate": "fp32", "residual_stream": "fp32", "cuda_graph": True},
+                   "accumulate": "fp32", "residual_stream": "fp32", "cuda_graph": True, "host_placement": placement},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * 2 * 80000 * 4,
-                "d2h_bytes_per_step": 2 * B * 250 * 90 * 4,
-                "api": "model.predict_pipelined (two batches in flight, page-locked host buffers)",
+        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * 2 * 80000 * 2, "d2h_bytes_per_step": B * 250 * 90 * 4,
+                "api": "model.predict_pipelined(want_logits=False) over a2m_submit_host_ex: f16 audio from page-locked memory (lossless, the "
+                       "loader rounds to f16), fp32 probabilities back (infer.py:41 keeps only those); two batches in flight",
+                "compact_value": e2e_compact, "compact_bytes_per_step": [B * 2 * 80000 * 2, B * 250 * 90 * 2],
+                "full_f32_value": e2e_full, "full_f32_bytes_per_step": [B * 2 * 80000 * 4, 2 * B * 250 * 90 * 4],
                 "sync_call_value": e2e_sync},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
-        "cpu_baseline": {"value": cpu_rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{cpu_n} windows x {cpu_iters} iterations ({cpu_s:.2f} s each), PyTorch-CPU fp32 "
-                                   f"restatement (oracle/model_torch.py); JAX reference not installable (SURVEY F1)"},
+        "cpu_baseline": cpu_fwd if cpu_fwd is not None else {"value": None, "unit": "audio-s/s", "cores": _CORES, "kind": "port",
+                                                              "sample": "timed at N = 1 only (and by --impl reference at every N)"},
     }
-    if train is not None:
-        line["train"] = train
+    for k, v in (("train", train), ("train_b64", train_b64), ("clip", clip), ("eval", evalr)):
+        if v is not None:
+            line[k] = v
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -458,9 +624,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU per step")
-    ap.add_argument("--train-batch", type=int, default=64, help="training windows per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=64, help="training windows per GPU per step (weak scaling)")
     ap.add_argument("--train-steps", type=int, default=30)
-    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the clip (config 5) and validation (config 3) measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -293,3 +293,56 @@ def test_lr_schedule_is_zero_based():
     s = T.create_learning_rate_schedule(1e-4, 1000, 200_000)
     assert s(0) == 0.0 and abs(s(1) - 1e-7) < 1e-15 and abs(s(1000) - 1e-4) < 1e-12
     assert s(1001) < 1e-4 and abs(s(1000 + 200_000)) < 1e-12
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audio_to_midi_b200 import infer as I
+    n = 7                                                        # ragged: blocks of 3, 2, 2 over three ranks
+    lo, hi = I.shard_windows(n, world, rank)
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 4, 3)     # window w carries the value w
+    full = I.gather_window_blocks(local, n, world, rank)
+    q.put((rank, lo, hi, full[:, 0, 0].tolist(), tuple(full.shape)))
+    dist.destroy_process_group()
+
+
+def test_rank_ordered_gather_world3_gloo():
+    """The gather that follows the sharded forward of configs 3 and 5 (infer.gather_window_blocks): ragged contiguous blocks,
+    padded to the largest, one equal-size all_gather, concatenated in rank order == window order, on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 150
+    ps = [ctx.Process(target=_gather_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert [(g[1], g[2]) for g in got] == [(0, 3), (3, 5), (5, 7)]
+    for g in got:
+        assert g[3] == [float(i) for i in range(7)] and g[4] == (7, 4, 3)
+
+
+def test_xla_ffi_source_type_checks():
+    """csrc/a2m_xla_ffi.cc (the jax.ffi handlers) cannot be built here -- jaxlib's headers are absent (F1) -- but it is
+    type-checked against a stub of the part of xla/ffi/api/ffi.h it uses (tests/stubs): every handler Impl must be callable with
+    exactly the argument / result / attribute types its binding declares, and every a2m_* call must match include/a2m.h."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "audio-to-midi_b200", "csrc", "a2m_xla_ffi.cc")
+    res = subprocess.run([gxx, "-fsyntax-only", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "tests", "stubs"),
+                          "-I/usr/local/cuda/include", src], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    text = open(src).read()
+    for sym in ("A2mForward", "A2mForwardTrain", "A2mBackward", "A2mLossAndGrad", "A2mAllReduce", "A2mAdamW"):
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({sym}," in text
+    binding = open(os.path.join(ROOT, "audio-to-midi_b200", "jax_binding.py")).read()
+    for sym in ("A2mForward", "A2mForwardTrain", "A2mBackward", "A2mLossAndGrad", "A2mAllReduce", "A2mAdamW"):
+        assert f'"{sym}"' in binding
