@@ -4,9 +4,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB, build
+from .build import LIBS, build
 
-_lib = None
+_libs = {}
 
 
 class A2mError(RuntimeError):
@@ -42,7 +42,7 @@ EXPORTS = [
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
     "a2m_create_ex", "a2m_submit_host_ex", "a2m_event_metrics", "a2m_set_params", "a2m_get_opt_state", "a2m_set_opt_state",
-    "a2m_backward_dlogits", "a2m_allreduce_grads", "a2m_comm_unique_id", "a2m_comm_init", "a2m_comm_get", "a2m_comm_destroy",
+    "a2m_operand_format", "a2m_debug_round_operand", "a2m_backward_dlogits", "a2m_allreduce_grads", "a2m_comm_unique_id", "a2m_comm_init", "a2m_comm_get", "a2m_comm_destroy",
 ]
 
 
@@ -56,17 +56,19 @@ class A2mConfig(C.Structure):   # include/a2m.h
 F32, F16 = 0, 1
 
 
-def lib() -> C.CDLL:
-    """Loads (building in-tree first if a compiler is present and the .so is stale) the C-ABI library."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = LIB
+def lib(precision: str = "bf16") -> C.CDLL:
+    """Loads (building in-tree first if a compiler is present and the .so is stale) the C-ABI library in one of its two
+    operand-format variants: "bf16" (training + inference) or "f16" (inference, binary16 tensor-core operands)."""
+    if precision not in LIBS:
+        raise ValueError(f"precision must be one of {sorted(LIBS)}, got {precision!r}")
+    if precision in _libs:
+        return _libs[precision]
+    path = LIBS[precision]
     if not os.path.exists(path) or os.environ.get("A2M_REBUILD") == "1":
-        path = build()
+        path = build(precision=precision)
     else:
         try:
-            path = build()  # no-op when up to date
+            path = build(precision=precision)  # no-op when up to date
         except RuntimeError:
             pass  # no nvcc on this box: use the prebuilt library that travelled with the tree
     L = C.CDLL(path)
@@ -172,11 +174,17 @@ def lib() -> C.CDLL:
     L.a2m_comm_get.restype = vp
     L.a2m_comm_destroy.argtypes = [vp]
     L.a2m_comm_destroy.restype = C.c_int
-    _lib = L
+    L.a2m_operand_format.argtypes = []
+    L.a2m_operand_format.restype = C.c_char_p
+    L.a2m_debug_round_operand.argtypes = [vp, vp, C.c_int64]
+    L.a2m_debug_round_operand.restype = C.c_int
+    if L.a2m_operand_format().decode() != precision:
+        raise A2mError(f"{path} reports operand format {L.a2m_operand_format().decode()!r}, expected {precision!r}")
+    _libs[precision] = L
     return L
 
 
-def check(handle, rc: int, what: str):
+def check(handle, rc: int, what: str, L=None):
     if rc != 0:
-        msg = lib().a2m_last_error(handle)
+        msg = (L or lib()).a2m_last_error(handle)
         raise A2mError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

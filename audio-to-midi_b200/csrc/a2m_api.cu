@@ -78,6 +78,36 @@ uint16_t f32_to_bf16(float f) {
   u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
   return static_cast<uint16_t>(u >> 16);
 }
+// IEEE binary16, round to nearest even, overflow to infinity, gradual underflow (what cvt.rn.f16.f32 does on the device)
+uint16_t f32_to_f16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return static_cast<uint16_t>(sign | 0x7e00u);          // NaN
+  if (u >= 0x477ff000u) return static_cast<uint16_t>(sign | 0x7c00u);         // >= 65520 rounds to infinity
+  if (u < 0x38800000u) {                                                      // below 2^-14: subnormal half
+    if (u < 0x33000000u) return static_cast<uint16_t>(sign);                  // below 2^-25: zero
+    const int shift = 126 - static_cast<int>(u >> 23);                        // 14 .. 24
+    uint32_t man = (u & 0x7fffffu) | 0x800000u;
+    const uint32_t lost = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    man >>= shift;
+    if (lost > half || (lost == half && (man & 1u))) ++man;
+    return static_cast<uint16_t>(sign | man);
+  }
+  uint32_t h = ((u - 0x38000000u) >> 13);
+  const uint32_t lost = u & 0x1fffu;
+  if (lost > 0x1000u || (lost == 0x1000u && (h & 1u))) ++h;
+  return static_cast<uint16_t>(sign | h);
+}
+// 16-bit tensor-core operand of this build variant (ptx.cuh: kOpFmt)
+uint16_t f32_to_op16(float f) {
+#ifdef A2M_OP_F16
+  return f32_to_f16(f);
+#else
+  return f32_to_bf16(f);
+#endif
+}
 
 // Host image of the device weights arena.  In map mode (training) the "values" being packed are 1-based indices into
 // the fp32 master parameter blob (0 = constant zero) and the arena records, per packed element, where it comes from,
@@ -111,7 +141,7 @@ struct Arena {
     n_elems += v.size();
     for (size_t i = 0; i < v.size(); ++i) {
       const float x = (mulv.empty() || std::isnan(mulv[i])) ? v[i] : v[i] * mulv[i];
-      if (bf16) reinterpret_cast<uint16_t*>(bytes.data() + off)[i] = f32_to_bf16(x);
+      if (bf16) reinterpret_cast<uint16_t*>(bytes.data() + off)[i] = f32_to_op16(x);
       else reinterpret_cast<float*>(bytes.data() + off)[i] = x;
     }
     return off;
@@ -1678,6 +1708,21 @@ void a2m_host_free(void* p) {
 }
 
 int32_t a2m_last_launch_count(const A2mHandle* h) { return h ? h->last_launches : 0; }
+
+const char* a2m_operand_format(void) {
+#ifdef A2M_OP_F16
+  return "f16";
+#else
+  return "bf16";
+#endif
+}
+
+// Host-side rounding of fp32 values to this build's 16-bit operand format (what a2m_load_weights applies to the weights).
+int a2m_debug_round_operand(const float* in_host, uint16_t* out_host, int64_t n) {
+  if (!in_host || !out_host || n < 0) return A2M_EINVAL;
+  for (int64_t i = 0; i < n; ++i) out_host[i] = f32_to_op16(in_host[i]);
+  return A2M_OK;
+}
 
 int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels_dev, int32_t batch, float* losses_dev, void* stream) {
   if (!h) return A2M_EINVAL;

@@ -31,7 +31,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2_att(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  __nv_bfloat162 v = op2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -153,19 +153,19 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int colb = key0 & 63;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(p[8 * q], p[8 * q + 1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(p[8 * q + 2], p[8 * q + 3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(p[8 * q + 4], p[8 * q + 5]);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(p[8 * q + 6], p[8 * q + 7]);
+      __nv_bfloat162 h0 = op2_rn(p[8 * q], p[8 * q + 1]);
+      __nv_bfloat162 h1 = op2_rn(p[8 * q + 2], p[8 * q + 3]);
+      __nv_bfloat162 h2 = op2_rn(p[8 * q + 4], p[8 * q + 5]);
+      __nv_bfloat162 h3 = op2_rn(p[8 * q + 6], p[8 * q + 7]);
       // the row sum must match what the tensor core will see: accumulate the ROUNDED probabilities
       sum += __low2float(h0) + __high2float(h0) + __low2float(h1) + __high2float(h1) + __low2float(h2) +
              __high2float(h2) + __low2float(h3) + __high2float(h3);
       if (dthresh != 0u) {   // the P.V operand is the dropped-out weights; the normaliser above is not
         const uint32_t i0 = dbase + key0 + 8 * q;
-        h0 = __floats2bfloat162_rn(p[8 * q] * drop_mul(dkey, i0, dthresh, dinv), p[8 * q + 1] * drop_mul(dkey, i0 + 1, dthresh, dinv));
-        h1 = __floats2bfloat162_rn(p[8 * q + 2] * drop_mul(dkey, i0 + 2, dthresh, dinv), p[8 * q + 3] * drop_mul(dkey, i0 + 3, dthresh, dinv));
-        h2 = __floats2bfloat162_rn(p[8 * q + 4] * drop_mul(dkey, i0 + 4, dthresh, dinv), p[8 * q + 5] * drop_mul(dkey, i0 + 5, dthresh, dinv));
-        h3 = __floats2bfloat162_rn(p[8 * q + 6] * drop_mul(dkey, i0 + 6, dthresh, dinv), p[8 * q + 7] * drop_mul(dkey, i0 + 7, dthresh, dinv));
+        h0 = op2_rn(p[8 * q] * drop_mul(dkey, i0, dthresh, dinv), p[8 * q + 1] * drop_mul(dkey, i0 + 1, dthresh, dinv));
+        h1 = op2_rn(p[8 * q + 2] * drop_mul(dkey, i0 + 2, dthresh, dinv), p[8 * q + 3] * drop_mul(dkey, i0 + 3, dthresh, dinv));
+        h2 = op2_rn(p[8 * q + 4] * drop_mul(dkey, i0 + 4, dthresh, dinv), p[8 * q + 5] * drop_mul(dkey, i0 + 5, dthresh, dinv));
+        h3 = op2_rn(p[8 * q + 6] * drop_mul(dkey, i0 + 6, dthresh, dinv), p[8 * q + 7] * drop_mul(dkey, i0 + 7, dthresh, dinv));
       }
       uint4 v;
       v.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -213,10 +213,10 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 v;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
+      __nv_bfloat162 h0 = op2_rn(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
+      __nv_bfloat162 h1 = op2_rn(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
+      __nv_bfloat162 h2 = op2_rn(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
+      __nv_bfloat162 h3 = op2_rn(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
       v.x = *reinterpret_cast<uint32_t*>(&h0);
       v.y = *reinterpret_cast<uint32_t*>(&h1);
       v.z = *reinterpret_cast<uint32_t*>(&h2);

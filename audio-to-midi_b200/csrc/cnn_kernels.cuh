@@ -516,14 +516,14 @@ struct RowMap {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if constexpr (VW == 4) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(x[4 * g], x[4 * g + 1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(x[4 * g + 2], x[4 * g + 3]);
+        __nv_bfloat162 a = op2_rn(x[4 * g], x[4 * g + 1]);
+        __nv_bfloat162 b = op2_rn(x[4 * g + 2], x[4 * g + 3]);
         uint2 q;
         q.x = *reinterpret_cast<uint32_t*>(&a);
         q.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(row + chan(lane, g)) = q;
       } else {
-        *reinterpret_cast<__nv_bfloat162*>(row + chan(lane, g)) = __floats2bfloat162_rn(x[2 * g], x[2 * g + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(row + chan(lane, g)) = op2_rn(x[2 * g], x[2 * g + 1]);
       }
     }
   }

@@ -89,7 +89,7 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  __nv_bfloat162 v = op2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -304,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int hc = col0 - g.vt_col0;  // = h * 64 + d0
               __nv_bfloat16* dst = g.vt_out + (static_cast<size_t>(win) * 256 + hc) * g.rows_per_window + pos;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * g.rows_per_window] = __float2bfloat16_rn(v[j]);
+              for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * g.rows_per_window] = op1_rn(v[j]);
             } else {
               store_row32_bf16(g.out16 + static_cast<size_t>(row) * g.ld16 + col0, v);
             }

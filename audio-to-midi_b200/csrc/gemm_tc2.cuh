@@ -354,7 +354,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   const int hc = col0 - g.vt_col0;
                   __nv_bfloat16* dst = g.vt_out + (static_cast<size_t>(win) * 256 + hc) * g.rows_per_window + pos;
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * g.rows_per_window] = __float2bfloat16_rn(v[j]);
+                  for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * g.rows_per_window] = op1_rn(v[j]);
                 }
                 continue;
               }

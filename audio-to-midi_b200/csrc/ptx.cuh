@@ -16,6 +16,32 @@ namespace a2m {
 __device__ long long g_ffn_timing[128];
 #endif
 
+// ---------------------------------------------------------------- tensor-core operand format (build variant)
+// tcgen05 kind::f16 takes bf16 OR IEEE binary16 operands at the same rate.  The library is built twice from the same sources:
+//   libaudio2midi_b200.so      bf16 operands (8-bit significand, fp32 exponent range): training, and inference when asked;
+//   libaudio2midi_b200_f16.so  -DA2M_OP_F16: binary16 operands (11-bit significand, 8x smaller rounding) for INFERENCE -- the
+//                              reference infers in fp32 and trains in fp16 (infer.py:234, train.py:36-37), so fp16 range is known
+//                              to suffice for its checkpoints; the residual stream, accumulators and LN / softmax statistics are
+//                              fp32 in both.  a2m_train_init is refused in this variant (the backward's unpack helpers are bf16).
+// Only three things differ: how two floats are rounded into a 16-bit pair (op2_rn / op1_rn), the operand-format bits of the UMMA
+// instruction descriptor (kOpFmt), and the host-side weight image (f32_to_op16 in a2m_api.cu).  `__nv_bfloat16*` pointers are
+// 16-bit carriers in both variants.
+#ifdef A2M_OP_F16
+constexpr uint32_t kOpFmt = 0;   // instruction-descriptor A/B format: 0 = f16
+__device__ __forceinline__ __nv_bfloat162 op2_rn(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<__nv_bfloat162*>(&h);
+}
+__device__ __forceinline__ __nv_bfloat16 op1_rn(float x) {
+  __half h = __float2half_rn(x);
+  return *reinterpret_cast<__nv_bfloat16*>(&h);
+}
+#else
+constexpr uint32_t kOpFmt = 1;   // 1 = bf16
+__device__ __forceinline__ __nv_bfloat162 op2_rn(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ __nv_bfloat16 op1_rn(float x) { return __float2bfloat16_rn(x); }
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -237,11 +263,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // start-address field.
 __device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
 
-// Instruction descriptor: kind::f16, A = B = bf16, D = fp32, both operands K-major, dense.
-//   bits [4,6) D format (1 = f32); [7,10) A format (1 = bf16); [10,13) B format (1 = bf16);
+// Instruction descriptor: kind::f16, A = B = bf16 (or f16 in the A2M_OP_F16 build), D = fp32, both operands K-major, dense.
+//   bits [4,6) D format (1 = f32); [7,10) A format (0 = f16, 1 = bf16); [10,13) B format (likewise);
 //   bit 15/16 A/B major (0 = K); [17,23) N >> 3; [24,29) M >> 4.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+  return (1u << 4) | (kOpFmt << 7) | (kOpFmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // Same, with the B operand MN-major: B is stored as [K rows][N contiguous] (e.g. V[key][d] for P.V), i.e. the

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) bce_grad_kernel(const float* __restrict__
       d = (p - y) * gscale;
       l = (fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)))) * lscale;
     }
-    dz[idx] = __float2bfloat16_rn(d);
+    dz[idx] = op1_rn(d);
   }
   l = warp_sum(l);
   __shared__ float sl[8];
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) dlogits_pack_kernel(const float* __restri
   const int col = idx & 127, row = (idx >> 7) & 255, b = idx >> 15;
   float d = 0.f;
   if (col < 90 && row < 250) d = dlogits[(static_cast<size_t>(b) * 250 + row) * 90 + col];
-  dz[idx] = __float2bfloat16_rn(d);
+  dz[idx] = op1_rn(d);
 }
 
 // Per-window validation loss (train.py:99-102 testset_loss_function): out[b] = sum_{t,c} BCEWithLogits(z, y), one CTA per window.
@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
       if (m >= 0) v *= master[m];
     }
     const uint32_t d = dst_off[i];
-    if (d & 0x80000000u) *reinterpret_cast<__nv_bfloat16*>(arena + (d & 0x7fffffffu)) = __float2bfloat16_rn(v);
+    if (d & 0x80000000u) *reinterpret_cast<__nv_bfloat16*>(arena + (d & 0x7fffffffu)) = op1_rn(v);
     else *reinterpret_cast<float*>(arena + d) = v;
   }
 }

@@ -50,6 +50,26 @@ def get_model_metadata():         # model.py:36-41
             "data_prep": {"sample_rate": SAMPLE_RATE, "audio_length": MODEL_AUDIO_LENGTH}}
 
 
+# Operand format of inference handles unless change_fp_precision says otherwise: "f16" (IEEE binary16 tensor-core operands, the
+# libaudio2midi_b200_f16.so build) or "bf16".  Accumulators, the residual stream and LN / softmax statistics are fp32 either way.
+import os as _os
+DEFAULT_INFERENCE_PRECISION = _os.environ.get("A2M_INFER_PRECISION", "bf16")
+
+
+def change_fp_precision(model, dtype):
+    """infer.py:27-32: the reference casts every inexact leaf (fp32 for inference, infer.py:234; fp16 for training, train.py:36-37).
+    Here the leaves stay fp32 masters and `dtype` picks the tensor-core OPERAND format the model's inference handles are built
+    with: float16 -> "f16" (11-bit significand), bfloat16 -> "bf16" (8-bit); float32 maps to "f16", the closest the sm_100a
+    kind::f16 path offers (its 2^-11 operand rounding is TF32's).  Returns the model (changed in place)."""
+    name = getattr(dtype, "__name__", None) or getattr(dtype, "name", None) or str(dtype)
+    name = name.replace("torch.", "").replace("jnp.", "")
+    table = {"float16": "f16", "f16": "f16", "half": "f16", "float32": "f16", "f32": "f16", "bfloat16": "bf16", "bf16": "bf16"}
+    if name not in table:
+        raise ValueError(f"unsupported precision {dtype!r}")
+    model.precision = table[name]
+    return model
+
+
 # ----------------------------------------------------------------------------------------------- pytree
 class Module:
     """Minimal stand-in for eqx.Module: ordered fields, leaves are numpy arrays (or None)."""
@@ -259,8 +279,9 @@ class _Engine:
     its engines (`OutputSequenceGenerator._engines`), a TrainEngine owns its own: handles are never shared or stolen, so a
     model and a trainer -- or two models -- can be resident on the same GPU at the same time."""
 
-    def __init__(self, device: int):
-        self.L = _lib.lib()
+    def __init__(self, device: int, precision: str = "bf16"):
+        self.L = _lib.lib(precision)
+        self.precision = precision
         h = C.c_void_p()
         cfg = default_config_struct(device)
         rc = self.L.a2m_create_ex(C.byref(cfg), C.byref(h))
@@ -337,8 +358,10 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         self._version = 0
         self._rope_cache = {}
         self._out_ring = {}
-        self._engines = {}        # device -> _Engine owned by this model
+        self._engines = {}        # (device, precision) -> _Engine owned by this model
+        self.precision = DEFAULT_INFERENCE_PRECISION   # tensor-core operand format of this model's inference (change_fp_precision)
         self._trainers = {}       # device -> weakref to the live TrainEngine built from this model (train.py)
+        self._own_trainers = {}   # device -> TrainEngine created implicitly by model(..., enable_dropout=True)
 
     # -- pytree helpers (what eqx.tree_at / tree_deserialise_leaves would be used for)
     def load_leaves(self, leaves: Dict[str, np.ndarray]):
@@ -371,9 +394,9 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         t = self._live_trainer(device)
         if t is not None:
             return t.eng
-        eng = self._engines.get(device)
+        eng = self._engines.get((device, self.precision))
         if eng is None:
-            eng = self._engines[device] = _Engine(device)
+            eng = self._engines[(device, self.precision)] = _Engine(device, self.precision)
         if eng.weights_token != self._version:
             eng.load(self)
         return eng
@@ -398,7 +421,9 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         single = samples.ndim == 2
         x = samples.reshape((-1, 2, 80000)).to(torch.float32).contiguous()
         dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
-        t = self._live_trainer(dev) or TrainEngine(self, dev)
+        t = self._live_trainer(dev)
+        if t is None:
+            t = self._own_trainers[dev] = TrainEngine(self, dev)      # kept alive by the model: the backward needs its tape
         seed = fold_key(key)
         t.set_dropout(model_config["transformer_dropout_rate"], seed)
         logits, probs = t.forward_train(x, rope_freqs, want_probs=True)

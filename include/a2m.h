@@ -145,6 +145,14 @@ int a2m_window_losses(A2mHandle* h, const float* logits_dev, const float* labels
 int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expected_dev, int32_t batch, int32_t frames,
                       float* metrics_dev, float* pred_frames_dev, int32_t* n_events_dev, void* stream);
 
+/* Tensor-core operand format of THIS build of the library: "bf16" (libaudio2midi_b200.so: training and inference) or "f16"
+ * (libaudio2midi_b200_f16.so, the inference variant: IEEE binary16 operands, 8x smaller operand rounding at the same tcgen05
+ * rate; a2m_train_init is refused).  Accumulation, residual stream and LayerNorm / softmax statistics are fp32 in both.
+ * This is the choice change_fp_precision makes in the reference (infer.py:27-32, 234). */
+const char* a2m_operand_format(void);
+/* test hook: host-side rounding of fp32 values to the operand format (what a2m_load_weights applies to the weights) */
+int a2m_debug_round_operand(const float* in_host, uint16_t* out_host, int64_t n);
+
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
 /* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between

@@ -9,11 +9,13 @@ from audio_to_midi_b200 import _lib
 from oracle import params as P
 
 
-def make_model(seed, **kw):
-    """Product model carrying exactly the oracle's parameter arrays."""
+def make_model(seed, precision=None, **kw):
+    """Product model carrying exactly the oracle's parameter arrays (precision: "bf16" | "f16" operand variant, None = default)."""
     tree = P.init_params(seed, **kw)
     m = A.OutputSequenceGenerator(A.model_config, key=0)
     m.load_leaves(P.flatten(tree))
+    if precision is not None:
+        m.precision = precision
     return m, tree
 
 

@@ -194,3 +194,42 @@ def test_host_path_f16_in_probs_only_f16_out(setup):
     assert pr3.dtype == np.float16 and np.array_equal(pr3, pr.astype(np.float16))
     (lg4, pr4), = list(model.predict_pipelined([a32], rope, copy=True, want_logits=True, probs_dtype=np.float16))
     assert np.array_equal(lg4, lg) and np.array_equal(pr4, pr3)
+
+
+def test_f16_operands_tighten_parity():
+    """a17 / change_fp_precision (infer.py:27-32, 234): the same kernels built with IEEE binary16 tensor-core operands
+    (libaudio2midi_b200_f16.so) against the fp32 CPU twin, next to the bf16 build, on 8 windows of the "active" model (every
+    Block matters, probabilities spread over (0, 1)).  binary16 carries 3 more significand bits than bf16, so the probability
+    error must drop several-fold; both variants launch the same plan and both residual taps agree with the twin."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model, tap
+    from oracle import model_torch as T
+    from oracle import synth
+    audio = synth.make_windows(8, 77)
+    rope = A.precompute_frequencies(64, 300)
+    errs, launches = {}, {}
+    taps_ref = {}
+    for precision in ("bf16", "f16"):
+        model, tree = make_model(77, precision=precision, **ACTIVE)
+        if not taps_ref:
+            with torch.no_grad():
+                zref, pref = T.forward(T.to_torch(tree), torch.tensor(audio), taps=taps_ref)
+            pref = pref.numpy()
+        _, probs = model.predict(None, torch.tensor(audio).cuda(), rope)
+        probs = probs.cpu().numpy()
+        errs[precision] = float(np.abs(probs - pref).max())
+        launches[precision] = model.last_launch_count(0)
+        assert model._engine(0).precision == precision
+        for label, shape in (("stage5", (8 * 500, 128)), ("tl7_global", (8 * 256, 256))):
+            got = tap(model, torch.tensor(audio).cuda(), label, shape[0] * shape[1]).reshape(shape)
+            ref = taps_ref[label].numpy()
+            if label.startswith("tl"):
+                got = got.reshape(8, 256, 256)[:, :250]
+            else:
+                got = got.reshape(8, 500, 128)
+            rel = _rel(got, ref)
+            assert rel < (4e-2 if precision == "bf16" else 1e-2), (precision, label, rel)
+    print(f"max |dprob| vs the fp32 twin: bf16 operands {errs['bf16']:.3e}, f16 operands {errs['f16']:.3e}")
+    assert launches["bf16"] == launches["f16"]
+    assert errs["bf16"] < 3e-2
+    assert errs["f16"] < 8e-3 and errs["f16"] < 0.5 * errs["bf16"]

@@ -346,3 +346,45 @@ def test_xla_ffi_source_type_checks():
     binding = open(os.path.join(ROOT, "audio-to-midi_b200", "jax_binding.py")).read()
     for sym in ("A2mForward", "A2mForwardTrain", "A2mBackward", "A2mLossAndGrad", "A2mAllReduce", "A2mAdamW"):
         assert f'"{sym}"' in binding
+
+
+def test_operand_format_variants_and_host_rounding():
+    """The two builds of the library (ptx.cuh: A2M_OP_F16): same exports, they name their tensor-core operand format, and the
+    host-side weight rounding of the f16 variant is IEEE round-to-nearest-even binary16 (numpy's), of the bf16 variant the
+    top 16 bits with RNE -- including subnormals, overflow to infinity, signed zero and NaN."""
+    import ctypes as C
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = np.concatenate([rng.normal(0, 1, 4000), rng.normal(0, 1e-6, 2000), rng.normal(0, 3e4, 2000),
+                        np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, -70000.0, 2.0 ** -24, 2.0 ** -25, 1.5 * 2.0 ** -25, 2.0 ** -14,
+                                  np.inf, -np.inf, np.nan, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11])]).astype(np.float32)
+    for precision in ("bf16", "f16"):
+        L = _lib.lib(precision)
+        assert L.a2m_operand_format().decode() == precision
+        for name in _lib.EXPORTS:
+            assert hasattr(L, name), (precision, name)
+        out = np.zeros(x.size, np.uint16)
+        assert L.a2m_debug_round_operand(x.ctypes.data, out.ctypes.data, x.size) == 0
+        if precision == "f16":
+            with np.errstate(over="ignore"):
+                ref = x.astype(np.float16)
+            got = out.view(np.float16)
+            nan = np.isnan(ref)
+            assert np.array_equal(np.isnan(got), nan)
+            assert np.array_equal(got[~nan].view(np.uint16), ref[~nan].view(np.uint16))
+        else:
+            import torch
+            ref = torch.tensor(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+            nan = np.isnan(x)
+            assert np.array_equal(out[~nan], ref[~nan])
+            assert np.all((out[nan] & 0x7F80) == 0x7F80) and np.all(out[nan] & 0x7F)
+
+
+def test_change_fp_precision_selects_the_operand_variant():
+    """infer.py:27-32: change_fp_precision(model, dtype) -> the operand format of the model's inference handles."""
+    m = A.OutputSequenceGenerator(A.model_config, key=1)
+    assert m.precision in ("bf16", "f16")
+    assert A.change_fp_precision(m, np.float16) is m and m.precision == "f16"
+    assert A.change_fp_precision(m, "bfloat16").precision == "bf16"
+    assert A.change_fp_precision(m, np.float32).precision == "f16"
+    with pytest.raises(ValueError):
+        A.change_fp_precision(m, np.int8)
