@@ -158,8 +158,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __nv_bfloat162 h2 = op2_rn(p[8 * q + 4], p[8 * q + 5]);
       __nv_bfloat162 h3 = op2_rn(p[8 * q + 6], p[8 * q + 7]);
       // the row sum must match what the tensor core will see: accumulate the ROUNDED probabilities
-      sum += __low2float(h0) + __high2float(h0) + __low2float(h1) + __high2float(h1) + __low2float(h2) +
-             __high2float(h2) + __low2float(h3) + __high2float(h3);
+      sum += (op2_sum(h0) + op2_sum(h1)) + (op2_sum(h2) + op2_sum(h3));
       if (dthresh != 0u) {   // the P.V operand is the dropped-out weights; the normaliser above is not
         const uint32_t i0 = dbase + key0 + 8 * q;
         h0 = op2_rn(p[8 * q] * drop_mul(dkey, i0, dthresh, dinv), p[8 * q + 1] * drop_mul(dkey, i0 + 1, dthresh, dinv));

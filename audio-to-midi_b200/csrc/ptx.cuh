@@ -36,10 +36,15 @@ __device__ __forceinline__ __nv_bfloat16 op1_rn(float x) {
   __half h = __float2half_rn(x);
   return *reinterpret_cast<__nv_bfloat16*>(&h);
 }
+__device__ __forceinline__ float op2_sum(__nv_bfloat162 v) {   // lo + hi of a rounded pair, as floats
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&v));
+  return f.x + f.y;
+}
 #else
 constexpr uint32_t kOpFmt = 1;   // 1 = bf16
 __device__ __forceinline__ __nv_bfloat162 op2_rn(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
 __device__ __forceinline__ __nv_bfloat16 op1_rn(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float op2_sum(__nv_bfloat162 v) { return __low2float(v) + __high2float(v); }
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

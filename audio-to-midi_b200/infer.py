@@ -74,7 +74,7 @@ def prepare_windows_device(model, audio_samples, overlap: float = 0.25, device=N
     out = torch.empty((nw, 2, 80000), dtype=torch.float32, device=tdev)
     stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
     rc = eng.L.a2m_prepare_windows(eng.h, clip.data_ptr(), n, float(overlap), out.data_ptr(), nw, stream)
-    _lib.check(eng.h, rc, "a2m_prepare_windows")
+    _lib.check(eng.h, rc, "a2m_prepare_windows", eng.L)
     return out
 
 
@@ -178,7 +178,7 @@ def detailed_event_loss_device(model, probs, expected, want_frames: bool = False
     stream = C.c_void_p(torch.cuda.current_stream(probs.device).cuda_stream)
     rc = eng.L.a2m_event_metrics(eng.h, probs.data_ptr(), expected.data_ptr(), B, F, out.data_ptr(),
                                  frames.data_ptr() if want_frames else None, None, stream)
-    _lib.check(eng.h, rc, "a2m_event_metrics")
+    _lib.check(eng.h, rc, "a2m_event_metrics", eng.L)
     return (out, frames) if want_frames else out
 
 
@@ -216,7 +216,7 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
         logits, probs = model.predict(None, x, rope_freqs)
         out = torch.empty(j - i, dtype=torch.float32, device=tdev)
         stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
-        _lib.check(eng.h, eng.L.a2m_window_losses(eng.h, logits.data_ptr(), y.data_ptr(), j - i, out.data_ptr(), stream), "a2m_window_losses")
+        _lib.check(eng.h, eng.L.a2m_window_losses(eng.h, logits.data_ptr(), y.data_ptr(), j - i, out.data_ptr(), stream), "a2m_window_losses", eng.L)
         if device_metrics:
             m = detailed_event_loss_device(model, probs, y)
         else:

@@ -14,6 +14,11 @@ import numpy as np
 from ._lib import MidiEvent, lib
 
 
+_EVENT_DTYPE = np.dtype({"names": ["attack_time", "note", "duration", "velocity"], "formats": ["<u8", "u1", "<u8", "u1"],
+                         "offsets": [0, 8, 16, 24], "itemsize": 32})
+assert C.sizeof(MidiEvent) == _EVENT_DTYPE.itemsize
+
+
 def stitch_probs(all_probs, overlap: float, duration_per_frame: float) -> np.ndarray:
     p = np.ascontiguousarray(all_probs, dtype=np.float32)
     if p.ndim != 3:
@@ -35,9 +40,14 @@ def extract_events(probs) -> list:
     if not lst:
         raise MemoryError("a2m_extract_events returned NULL")
     try:
-        n = lst.contents.length
-        ev = lst.contents.ptr
-        return [(int(ev[i].attack_time), int(ev[i].note), int(ev[i].duration), int(ev[i].velocity)) for i in range(n)]
+        n = int(lst.contents.length)
+        if n == 0:
+            return []
+        # one vectorised view of the #[repr(C)] MidiEvent array (cbinds.rs:9-15: u64, u8, u64, u8 at offsets 0, 8, 16, 24 of 32
+        # bytes) instead of four ctypes attribute reads per event: a 10-minute clip yields > 10 000 events
+        buf = (C.c_char * (n * C.sizeof(MidiEvent))).from_address(C.addressof(lst.contents.ptr.contents))
+        ev = np.frombuffer(buf, dtype=_EVENT_DTYPE, count=n)
+        return list(zip(ev["attack_time"].tolist(), ev["note"].tolist(), ev["duration"].tolist(), ev["velocity"].tolist()))
     finally:
         L.free_midi_events(lst)
 
@@ -46,9 +56,11 @@ def to_frame_events(all_events, frame_count: int) -> list:
     L = lib()
     out = []
     for events in all_events:
-        arr = (MidiEvent * max(len(events), 1))()
-        for i, (a, k, d, v) in enumerate(events):
-            arr[i].attack_time, arr[i].note, arr[i].duration, arr[i].velocity = int(a), int(k), int(d), int(v)
+        rec = np.zeros(max(len(events), 1), dtype=_EVENT_DTYPE)
+        if len(events):
+            cols = np.asarray(events, dtype=np.int64).reshape(len(events), 4)
+            rec["attack_time"], rec["note"], rec["duration"], rec["velocity"] = cols[:, 0], cols[:, 1], cols[:, 2], cols[:, 3]
+        arr = rec.ctypes.data_as(C.POINTER(MidiEvent))
         frames = np.empty((frame_count, 90), dtype=np.float32)
         rc = L.a2m_to_frame_events(arr, len(events), frame_count, frames.ctypes.data)
         if rc != 0:

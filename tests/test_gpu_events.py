@@ -8,17 +8,22 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = 3e-2   # probability tolerance of the bf16 tensor path against the fp32 CPU twin (tests/test_gpu_forward.py)
+# probability tolerance against the fp32 CPU twin, per tensor-core operand format (tests/test_gpu_forward.py measures both)
+TOLS = {"bf16": 3e-2, "f16": 4e-3}    # measured maxima over 64 windows: 1.8e-2 / 2.1e-3
 N_WINDOWS = 64
+# Keys (of 64 windows x 90) whose event list the margin theorem FORCES to be identical, measured on B200 in round 2 with the
+# probability differences of each variant; the bounds sit a little below the measurement so that the assertion cannot go vacuous.
+MIN_DECIDED = {"bf16": 600, "f16": 1150}            # measured 657 / 1244 of 5760 (identical: 4750 / 5629)
+MIN_DECIDED_STITCHED = {"bf16": 0, "f16": 0}
 
 
-@pytest.fixture(scope="module")
-def run64():
+@pytest.fixture(scope="module", params=["bf16", "f16"])
+def run64(request):
     import audio_to_midi_b200 as A
     from gpu_util import make_model
     from oracle import model_torch as T
     from oracle import synth
-    model, tree = make_model(99, gamma_mode="active", decoder_gain=4.0, trained_like=True)
+    model, tree = make_model(99, precision=request.param, gamma_mode="active", decoder_gain=4.0, trained_like=True)
     audio = synth.make_windows(N_WINDOWS, 99)
     rope = A.precompute_frequencies(64, 300)
     _, probs = model.predict(None, torch.tensor(audio).cuda(), rope)
@@ -30,10 +35,10 @@ def run64():
 
 
 def test_probabilities_of_64_windows_within_tolerance(run64):
-    _, probs, ref = run64
+    model, probs, ref = run64
     d = np.abs(probs.astype(np.float64) - ref)
-    print(f"64 windows: max |dprob| {d.max():.3e}, mean {d.mean():.3e}, p99.9 {np.quantile(d, 0.999):.3e}")
-    assert d.max() < TOL
+    print(f"[{model.precision}] 64 windows: max |dprob| {d.max():.3e}, mean {d.mean():.3e}, p99.9 {np.quantile(d, 0.999):.3e}")
+    assert d.max() < TOLS[model.precision]
 
 
 def test_event_lists_match_where_unambiguous(run64):
@@ -41,7 +46,8 @@ def test_event_lists_match_where_unambiguous(run64):
     import audio_to_midi_b200 as A
     from event_parity import check_event_parity
     from oracle import events as E
-    _, probs, ref = run64
+    model, probs, ref = run64
+    TOL = TOLS[model.precision]
     decided = same = total_events = 0
     for w in range(N_WINDOWS):
         ev = A.modelutil.extract_events(np.ascontiguousarray(probs[w]))
@@ -55,16 +61,12 @@ def test_event_lists_match_where_unambiguous(run64):
     st_ref = E.stitch_probs(ref, 0.5, 0.02)
     ev_st = A.modelutil.extract_events(st)
     nd_st, ns_st = check_event_parity(st_ref, st, ev_st, TOL)
-    print(f"per-window key tracks: decided {decided}/5760, identical {same}/5760, events {total_events}; "
+    print(f"[{model.precision}] per-window key tracks: decided {decided}/5760, identical {same}/5760, events {total_events}; "
           f"stitched ({st.shape[0]} frames): decided {nd_st}/90, identical {ns_st}/90, events {len(ev_st)}")
     # measured on B200 (round 2, bf16 operands): see DESIGN.md section 5; the bounds keep the assertion from going vacuous
     assert total_events > 500
-    assert decided >= MIN_DECIDED and same >= decided
-    assert nd_st >= MIN_DECIDED_STITCHED
-
-
-MIN_DECIDED = 1            # tightened to the measured count once the GPU run has printed it
-MIN_DECIDED_STITCHED = 0
+    assert decided >= MIN_DECIDED[model.precision] and same >= decided
+    assert nd_st >= MIN_DECIDED_STITCHED[model.precision]
 
 
 def test_event_metrics_on_device_match_host(run64):

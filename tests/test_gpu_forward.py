@@ -228,8 +228,8 @@ def test_f16_operands_tighten_parity():
             else:
                 got = got.reshape(8, 500, 128)
             rel = _rel(got, ref)
-            assert rel < (4e-2 if precision == "bf16" else 1e-2), (precision, label, rel)
+            assert rel < (4e-2 if precision == "bf16" else 4e-3), (precision, label, rel)     # measured 1.0e-2 / 1.0e-3
     print(f"max |dprob| vs the fp32 twin: bf16 operands {errs['bf16']:.3e}, f16 operands {errs['f16']:.3e}")
     assert launches["bf16"] == launches["f16"]
     assert errs["bf16"] < 3e-2
-    assert errs["f16"] < 8e-3 and errs["f16"] < 0.5 * errs["bf16"]
+    assert errs["f16"] < 5e-3 and errs["f16"] < 0.25 * errs["bf16"]                        # measured 2.0e-2 / 2.4e-3

@@ -267,7 +267,7 @@ def test_train_then_predict_then_train_and_sync():
     p_before = p_before.clone()
     eng = T.TrainEngine(model, 0)
     _, p_live0 = model.predict(None, x, rope)                        # now the trainer's handle, same weights (un-folded kv path)
-    assert (p_live0 - p_before).abs().max().item() < 2e-2
+    assert (p_live0 - p_before).abs().max().item() < 3e-2    # the model's own handle has f16 operands, the trainer's bf16
     for i in range(3):
         loss, valid, _ = eng.training_step(x, y, rope, cfg, 1e-2, key=1)
         assert bool(valid.item())
@@ -289,7 +289,7 @@ def test_train_then_predict_then_train_and_sync():
     _, p_sync = model.predict(None, x, rope)                         # still the trainer's handle
     eng.close()
     _, p_closed = model.predict(None, x, rope)                       # the model's own handle, re-loaded with the trained leaves
-    assert (p_closed - p_sync).abs().max().item() < 2e-2
+    assert (p_closed - p_sync).abs().max().item() < 3e-2
 
 
 def test_non_finite_gradients_leave_state_untouched():
