@@ -207,6 +207,7 @@ struct Workspace {
   __nv_bfloat16* Vt16;
   __nv_bfloat16* O16;
   __nv_bfloat16* QKV16;   // folded path: q | k | v, [B*256, 768]
+  float* rope;            // cos [300, 32] then sin [300, 32]: the RoPE table of the calls that run on THIS workspace
 };
 
 size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
@@ -223,6 +224,7 @@ size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
   const size_t qc = take(b * kTP * kQC * 2), kv = take(b * kTP * kKV * 2);
   const size_t vt = take(b * 65536 * 2), o16 = take(b * 65536 * 2);
   const size_t qkv = take(b * kTP * 768 * 2);
+  const size_t rope = take(sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM);
   if (ws) {
     ws->base = base;
     ws->X[0] = reinterpret_cast<float*>(base + x0);
@@ -235,6 +237,7 @@ size_t ws_carve(int B, uint8_t* base, Workspace* ws) {
     ws->Vt16 = reinterpret_cast<__nv_bfloat16*>(base + vt);
     ws->O16 = reinterpret_cast<__nv_bfloat16*>(base + o16);
     ws->QKV16 = reinterpret_cast<__nv_bfloat16*>(base + qkv);
+    ws->rope = reinterpret_cast<float*>(base + rope);
   }
   return off;
 }
@@ -277,8 +280,13 @@ struct A2mHandle {
   uint8_t* arena_dev = nullptr;
   size_t arena_bytes = 0;
   float* rope_dev = nullptr;  // cos [300,32] then sin [300,32]
-  uint8_t* own_ws = nullptr;
-  size_t own_ws_bytes = 0;
+  // Handle-owned workspaces ("lanes").  Lane 0 serves a2m_forward(workspace_dev = NULL) and the profiling hooks; the two
+  // slots of the pipelined host path run on lane 0 / lane 1 with a compute stream each, so that two consecutive batches are in
+  // flight at once: every kernel of the plan is at most one wave at 64 windows, and a second, independent step fills the SMs
+  // and wave tails the first leaves idle (measured: 1.32 ms per 64-window step with two lanes against 1.55 ms with one).
+  uint8_t* lane_ws[2] = {nullptr, nullptr};
+  size_t lane_ws_bytes[2] = {0, 0};
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
   std::vector<std::unique_ptr<Plan>> plans;
   bool use_graph = true;
   bool use_pdl = true;     // programmatic dependent launch between the kernels of the plan
@@ -299,7 +307,7 @@ struct A2mHandle {
     void* user_probs = nullptr;
     size_t logits_bytes = 0, probs_bytes = 0;
     bool out_direct = false;
-  } slots[2];
+  } slots[A2M_HOST_SLOTS];
   float* pin_rope = nullptr;
   float* dev_rope_in = nullptr;
   std::vector<float> rope_host_cache;
@@ -381,8 +389,6 @@ static bool g_fuse_dgelu = false;     // A2M_FUSE_DGELU=1: GELU backward in the 
                                       // CTA evaluate gelu' for the whole tile while a full-chip elementwise kernel does it at 4.4 TB/s)
 static bool g_mid_bwd_tc = true;     // debug switch (A2M_MID_BWD_TC=0): CUDA-core block_small_bwd_kernel for stages 2-3
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
-static bool g_qkv_pair = false;  // A2M_QKV_PAIR=1: cta_group::2 qkv_pair_kernel instead of the single-CTA qkv_fused_kernel (correct, but
-                                 // measured 17.2 us against 13.2 us: its chunk period is 6.3-7.5 k cycles against 4.6 k)
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
 static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
@@ -533,7 +539,6 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(qkv_pair_kernel, QP_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block256_fused_kernel, B6_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(gemm_pair_kernel<128>, gemm_pair_smem_bytes<128>())) != cudaSuccess) return e;
@@ -1097,8 +1102,8 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
              static_cast<size_t>(Mt) * kD);
   }
   // ---- transformer stack (model.py:649-670): per scan step a local then a global TransformerLayer
-  const float* rope_cos = h->rope_dev;
-  const float* rope_sin = h->rope_dev + kRopeRows * A2M_ROPE_DIM;
+  const float* rope_cos = ws.rope;
+  const float* rope_sin = ws.rope + kRopeRows * A2M_ROPE_DIM;
   for (int i = 0; i < 2 * kNumTL; ++i) {
     const bool local = (i % 2 == 0);
     const TLayerW& t = w.tl[i];
@@ -1126,14 +1131,6 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         if (!make_tmap_t(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, Mt, 768, 768, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
         const float* lw = dev_ptr<float>(h, t.ln1w);
         const float* lb = dev_ptr<float>(h, t.ln1b);
-        if (g_qkv_pair) {
-          CUtensorMap twp;   // each CTA of a pair loads its 128 of a chunk's 256 rows of W
-          if (!make_tmap(h, &twp, dev_ptr<__nv_bfloat16>(h, t.wqkv), 768, kD, kD, 64, 128)) return false;
-          add_step(p, Meta{"qkv_pair_kernel", 0.0, 4.0 * Mt * kD + 2.0 * Mt * 768 + 2.0 * 768 * kD}, [=](cudaStream_t st) {
-            return launch_k(PF_FUSED, qkv_pair_kernel, dim3(Mt / FF_ROWS), dim3(QF_THREADS), QP_SMEM, st, twp, to,
-                            static_cast<const float*>(xt), Mt, lw, lb, rope_cos, rope_sin, kTP);
-          });
-        } else
         add_step(p, Meta{"qkv_fused_kernel", 0.0, 4.0 * Mt * kD + 2.0 * Mt * 768 + 2.0 * 768 * kD}, [=](cudaStream_t st) {
           return launch_k(PF_FUSED, qkv_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(QF_THREADS), QF_SMEM, st, tw, to,
                           static_cast<const float*>(xt), Mt, lw, lb, rope_cos, rope_sin, kTP);
@@ -1291,26 +1288,27 @@ Plan* get_plan(A2mHandle* h, int B, uint8_t* ws_base) {
   return h->plans.back().get();
 }
 
-int ensure_own_ws(A2mHandle* h, int B) {
+int ensure_lane_ws(A2mHandle* h, int lane, int B) {
   const size_t need = ws_carve(B, nullptr, nullptr);
-  if (h->own_ws_bytes >= need) return A2M_OK;
-  // plans built on the old buffer are stale
+  if (h->lane_ws_bytes[lane] >= need) return A2M_OK;
+  // plans built on the old buffer are stale (the other lane's plans go too: growth is rare, and in-flight work is drained first)
+  CUDA_TRY(cudaDeviceSynchronize());
   for (auto& p : h->plans)
     if (p->graph) cudaGraphExecDestroy(p->graph);
   h->plans.clear();
-  if (h->own_ws) cudaFree(h->own_ws);
-  h->own_ws = nullptr;
-  h->own_ws_bytes = 0;
-  CUDA_TRY(cudaMalloc(&h->own_ws, need));
-  CUDA_TRY(cudaMemset(h->own_ws, 0, need));
-  h->own_ws_bytes = need;
+  if (h->lane_ws[lane]) cudaFree(h->lane_ws[lane]);
+  h->lane_ws[lane] = nullptr;
+  h->lane_ws_bytes[lane] = 0;
+  CUDA_TRY(cudaMalloc(&h->lane_ws[lane], need));
+  CUDA_TRY(cudaMemset(h->lane_ws[lane], 0, need));
+  h->lane_ws_bytes[lane] = need;
   return A2M_OK;
 }
 
 // audio: fp32, or IEEE binary16 when audio_f16; outputs: any of logits / probs (fp32) / probs16 (binary16) may be null
 int run_forward(A2mHandle* h, const void* audio, bool audio_f16, int B, const float* cos_in, const float* sin_in, int max_pos,
                 float* logits, float* probs, __half* probs16, void* workspace, size_t ws_bytes, cudaStream_t stream,
-                const char* tap_label, float* tap_out, size_t tap_elems) {
+                const char* tap_label, float* tap_out, size_t tap_elems, int lane = 0) {
   if (!h->loaded) { h->err = "a2m_forward before a2m_load_weights"; return A2M_ESTATE; }
   if (B <= 0 || !audio || !cos_in || !sin_in) { h->err = "bad forward arguments"; return A2M_EINVAL; }
   if (max_pos < kT) { h->err = "rope table needs at least 250 positions"; return A2M_EINVAL; }
@@ -1323,9 +1321,9 @@ int run_forward(A2mHandle* h, const void* audio, bool audio_f16, int B, const fl
     }
     ws_base = static_cast<uint8_t*>(workspace);
   } else {
-    int rc = ensure_own_ws(h, B);
+    int rc = ensure_lane_ws(h, lane, B);
     if (rc) return rc;
-    ws_base = h->own_ws;
+    ws_base = h->lane_ws[lane];
   }
   Plan* p = get_plan(h, B, ws_base);
   if (!p) return A2M_ECUDA;
@@ -1333,8 +1331,8 @@ int run_forward(A2mHandle* h, const void* audio, bool audio_f16, int B, const fl
   int launches = 0;
   // RoPE table is an input of the call (rope.py:5-22): copy the rows the model can address
   const int rows = std::min(max_pos, kRopeRows);
-  CUDA_TRY(cudaMemcpyAsync(h->rope_dev, cos_in, sizeof(float) * rows * A2M_ROPE_DIM, cudaMemcpyDeviceToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(h->rope_dev + kRopeRows * A2M_ROPE_DIM, sin_in, sizeof(float) * rows * A2M_ROPE_DIM,
+  CUDA_TRY(cudaMemcpyAsync(p->ws.rope, cos_in, sizeof(float) * rows * A2M_ROPE_DIM, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(p->ws.rope + kRopeRows * A2M_ROPE_DIM, sin_in, sizeof(float) * rows * A2M_ROPE_DIM,
                            cudaMemcpyDeviceToDevice, stream));
   {
     const int total = B * kLens[0];
@@ -1436,12 +1434,13 @@ int a2m_create(int device, A2mHandle** out) {
   CUDA_TRY(cudaMalloc(&h->rope_dev, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
   CUDA_TRY(cudaMemset(h->rope_dev, 0, sizeof(float) * 2 * kRopeRows * A2M_ROPE_DIM));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->lane_stream[0] = h->own_stream;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));
   if (const char* e = std::getenv("A2M_PDL")) h->use_pdl = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_PDL_MASK")) g_pdl_mask = static_cast<unsigned>(std::strtoul(e, nullptr, 0));
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_QKV_PAIR")) g_qkv_pair = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;
@@ -1480,7 +1479,8 @@ void a2m_destroy(A2mHandle* h) {
     if (p->graph) cudaGraphExecDestroy(p->graph);
   if (h->arena_dev) cudaFree(h->arena_dev);
   if (h->rope_dev) cudaFree(h->rope_dev);
-  if (h->own_ws) cudaFree(h->own_ws);
+  for (auto w : h->lane_ws) if (w) cudaFree(w);
+  if (h->lane_stream[1]) cudaStreamDestroy(h->lane_stream[1]);
   for (auto& sl : h->slots) {
     if (sl.dev_audio) cudaFree(sl.dev_audio);
     if (sl.dev_out) cudaFree(sl.dev_out);
@@ -1577,7 +1577,7 @@ static bool is_pinned(const void* p) {
 int a2m_submit_host_ex(A2mHandle* h, int32_t slot, const void* audio_host, int32_t audio_dtype, int32_t batch, const float* rope_cos_host,
                        const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, void* probs_host, int32_t out_dtype) {
   if (!h) return A2M_EINVAL;
-  if (slot < 0 || slot > 1 || batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !probs_host || rope_max_pos < kT ||
+  if (slot < 0 || slot >= A2M_HOST_SLOTS || batch <= 0 || !audio_host || !rope_cos_host || !rope_sin_host || !probs_host || rope_max_pos < kT ||
       (audio_dtype != A2M_F32 && audio_dtype != A2M_F16) || (out_dtype != A2M_F32 && out_dtype != A2M_F16)) {
     h->err = "bad submit_host arguments";
     return A2M_EINVAL;
@@ -1615,16 +1615,18 @@ int a2m_submit_host_ex(A2mHandle* h, int32_t slot, const void* audio_host, int32
     CUDA_TRY(cudaMalloc(&h->dev_rope_in, 2 * kRopeRows * A2M_ROPE_DIM * 4));
     CUDA_TRY(cudaMemset(h->dev_rope_in, 0, 2 * kRopeRows * A2M_ROPE_DIM * 4));
   }
-  cudaStream_t cs = h->own_stream;  // compute stream shared by both slots: forwards are serialised, one workspace
+  const int lane = slot & 1;
+  cudaStream_t cs = h->lane_stream[lane];  // two compute lanes (stream + workspace each): slots 0, 2 run on lane 0, slots 1, 3 on lane 1
   if (h->rope_host_cache.size() != 2 * r_elems || std::memcmp(h->rope_host_cache.data(), rope_cos_host, r_elems * 4) != 0 ||
       std::memcmp(h->rope_host_cache.data() + r_elems, rope_sin_host, r_elems * 4) != 0) {
-    CUDA_TRY(cudaStreamSynchronize(cs));  // the staging buffer may still feed an earlier upload
+    CUDA_TRY(cudaStreamSynchronize(h->lane_stream[0]));  // the staging buffer and the device table may still feed earlier work
+    CUDA_TRY(cudaStreamSynchronize(h->lane_stream[1]));
     h->rope_host_cache.assign(rope_cos_host, rope_cos_host + r_elems);
     h->rope_host_cache.insert(h->rope_host_cache.end(), rope_sin_host, rope_sin_host + r_elems);
     std::memset(h->pin_rope, 0, 2 * kRopeRows * A2M_ROPE_DIM * 4);
     std::memcpy(h->pin_rope, rope_cos_host, r_elems * 4);
     std::memcpy(h->pin_rope + kRopeRows * A2M_ROPE_DIM, rope_sin_host, r_elems * 4);
-    CUDA_TRY(cudaMemcpyAsync(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpy(h->dev_rope_in, h->pin_rope, 2 * kRopeRows * A2M_ROPE_DIM * 4, cudaMemcpyHostToDevice));
   }
   // input: straight from the caller's buffer when it is page-locked, else through the slot's staging buffer
   const void* src = audio_host;
@@ -1640,7 +1642,7 @@ int a2m_submit_host_ex(A2mHandle* h, int32_t slot, const void* audio_host, int32
   uint8_t* d_probs = sl.dev_out + o_elems * 4;
   int rc = run_forward(h, sl.dev_audio, in16, batch, h->dev_rope_in, h->dev_rope_in + kRopeRows * A2M_ROPE_DIM, rows, d_logits,
                        out16 ? nullptr : reinterpret_cast<float*>(d_probs), out16 ? reinterpret_cast<__half*>(d_probs) : nullptr,
-                       nullptr, 0, cs, nullptr, nullptr, 0);
+                       nullptr, 0, cs, nullptr, nullptr, 0, lane);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(sl.ev_done, cs));
   CUDA_TRY(cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
@@ -1671,7 +1673,7 @@ int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t
 
 int a2m_collect_host(A2mHandle* h, int32_t slot) {
   if (!h) return A2M_EINVAL;
-  if (slot < 0 || slot > 1) { h->err = "bad slot"; return A2M_EINVAL; }
+  if (slot < 0 || slot >= A2M_HOST_SLOTS) { h->err = "bad slot"; return A2M_EINVAL; }
   A2mHandle::Slot& sl = h->slots[slot];
   if (!sl.pending) { h->err = "nothing submitted on this slot"; return A2M_ESTATE; }
   sl.pending = false;
@@ -1795,9 +1797,9 @@ int32_t a2m_profile_steps(A2mHandle* h, int32_t batch, int32_t repeats, int32_t 
   if (!h || batch <= 0 || repeats <= 0) return A2M_EINVAL;
   if (!h->loaded) { h->err = "a2m_profile_steps before a2m_load_weights"; return A2M_ESTATE; }
   if (cudaSetDevice(h->device) != cudaSuccess) return A2M_ECUDA;
-  int rc = ensure_own_ws(h, batch);
+  int rc = ensure_lane_ws(h, 0, batch);
   if (rc) return rc;
-  Plan* p = get_plan(h, batch, h->own_ws);
+  Plan* p = get_plan(h, batch, h->lane_ws[0]);
   if (!p) return A2M_ECUDA;
   const int n = static_cast<int>(p->steps.size());
   if (!out) return n;

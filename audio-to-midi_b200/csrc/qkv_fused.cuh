@@ -214,224 +214,4 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   }
 }
 
-constexpr int QP_NST = 4;                         // pair variant: stages of 16 KB (this CTA's 128 of the chunk's 256 rows of W)
-constexpr int QP_STAGE = 16 * 1024;
-constexpr int QP_MAIN_BYTES = FF_A_BYTES + QP_NST * QP_STAGE;     // 128 KB
-constexpr size_t QP_SMEM = 1024 + QP_MAIN_BYTES + QF_OUT_BYTES + QF_ROPE_BYTES + 256;
-
-// CTA-PAIR variant (tcgen05 cta_group::2, recipe of gemm_pair.cuh): the two CTAs of a cluster own the two 128-row tiles of
-// one window; each streams only HALF of every weight stage (its 128 of the chunk's 256 rows of W, 16 KB) and the leader
-// issues M = 256 MMAs that read both halves, so the L2 weight stream and the shared-memory operand reads per SM are halved
-// (the two roofs of the single-CTA kernel).  The peer's otherwise idle MMA warp forwards "A operand ready",
-// "accumulator buffer drained" and "stage landed" to the leader with remote mbarrier arrives, in the order the leader waits.
-// tmW: Wqkv [768, 256] bf16, box {64, 128}.  tmO: out [M, 768] bf16, box {32, 128}, 64B swizzle.  X: fp32 [M, 256].
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QF_THREADS, 1)
-qkv_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const float* X, int M,
-                 const float* __restrict__ lnw, const float* __restrict__ lnb, const float* __restrict__ rope_cos,
-                 const float* __restrict__ rope_sin, int rows_per_window) {
-  using RM = RowMap<FF_D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;
-  uint8_t* sW = sA + FF_A_BYTES;
-  uint8_t* sOut = smem + QP_MAIN_BYTES;
-  float* sCos = reinterpret_cast<float*>(sOut + QF_OUT_BYTES);
-  float* sSin = sCos + FF_ROWS * 32;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sSin + FF_ROWS * 32);
-  uint64_t* bar_empty = bar_full + QP_NST;
-  uint64_t* bar_peer = bar_empty + QP_NST;   // leader: the peer's half of the stage has landed
-  uint64_t* bar_a = bar_peer + QP_NST;
-  uint64_t* bar_dfull = bar_a + 1;      // [2]
-  uint64_t* bar_dfree = bar_dfull + 2;  // [2]
-  uint64_t* bar_apeer = bar_dfree + 2;        // leader: the peer's A operand is ready
-  uint64_t* bar_dfree_peer = bar_apeer + 1;   // leader [2]: the peer has drained the accumulator buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_dfree_peer + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile0 = blockIdx.x * FF_ROWS;
-  const uint32_t rank = cluster_ctarank();
-  const int pos0 = tile0 % rows_per_window;    // a tile never straddles windows (rows_per_window is a multiple of 128)
-
-  pdl_launch_dependents();
-  if (threadIdx.x == 0) FF_STAMP(80);
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmO);
-    for (int s = 0; s < QP_NST; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
-      mbar_init(&bar_peer[s], 1);
-    }
-    mbar_init(bar_apeer, 1);
-    mbar_init(&bar_dfree_peer[0], 1);
-    mbar_init(&bar_dfree_peer[1], 1);
-    mbar_init(bar_a, FF_CTHREADS);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_dfull[i], 1);
-      mbar_init(&bar_dfree[i], FF_CTHREADS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
-  // RoPE rows pos0 .. pos0+127 (constants): 128 x 8 float4 each for cos and sin; all loads of a thread before its stores
-  {
-    constexpr int NV = 2 * FF_ROWS * 8, PER = (NV + QF_THREADS - 1) / QF_THREADS;
-    float4 v[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = threadIdx.x + k * QF_THREADS;
-      const int which = i >> 10, r = (i >> 3) & 127, q = i & 7;
-      if (i < NV) v[k] = __ldg(reinterpret_cast<const float4*>((which ? rope_sin : rope_cos) + (pos0 + r) * 32) + q);
-    }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = threadIdx.x + k * QF_THREADS;
-      const int which = i >> 10, r = (i >> 3) & 127, q = i & 7;
-      if (i < NV) *reinterpret_cast<float4*>((which ? sSin : sCos) + r * 32 + 4 * (q ^ (r & 7))) = v[k];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // both CTAs' barriers exist before a remote arrive or a multicast commit can reach them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) FF_STAMP(81);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      uint32_t s = 0, ph = 0;
-      for (int n = 0; n < QF_NCHUNK; ++n)
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait_cluster(&bar_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&bar_full[s], QP_STAGE);
-          tma_load_2d(sW + s * QP_STAGE, &tmW, &bar_full[s], kb * 64, n * 256 + static_cast<int>(rank) * 128);
-          if (++s == QP_NST) { s = 0; ph ^= 1; }
-        }
-    }
-  } else if (warp == 1) {
-    if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
-      uint32_t s = 0, ph = 0;
-      mbar_wait(bar_a, 0);
-      mbar_wait_cluster(bar_apeer, 0);
-      tc_fence_after();
-      for (int n = 0; n < QF_NCHUNK; ++n) {
-        mbar_wait(&bar_dfree[n & 1], ((n >> 1) & 1) ^ 1);
-        mbar_wait_cluster(&bar_dfree_peer[n & 1], (n >> 1) & 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (n & 1) * 256;
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&bar_full[s], ph);
-          mbar_wait_cluster(&bar_peer[s], ph);
-          tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * (FF_ROWS * 128)));
-          const uint64_t db = umma_desc_sw128(smem_u32(sW + s * QP_STAGE));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_pair(d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&bar_empty[s]);
-          if (++s == QP_NST) { s = 0; ph ^= 1; }
-        }
-        umma_commit_pair(&bar_dfull[n & 1]);
-      }
-    } else if (rank == 1 && elect_one()) {
-      // forwarder: mirrors the leader's waits, in the same order
-      uint32_t s = 0, ph = 0;
-      mbar_wait(bar_a, 0);
-      mbar_arrive_remote(mapa_shared(bar_apeer, 0));
-      for (int n = 0; n < QF_NCHUNK; ++n) {
-        mbar_wait(&bar_dfree[n & 1], ((n >> 1) & 1) ^ 1);
-        mbar_arrive_remote(mapa_shared(&bar_dfree_peer[n & 1], 0));
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&bar_full[s], ph);
-          mbar_arrive_remote(mapa_shared(&bar_peer[s], 0));
-          if (++s == QP_NST) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else {
-    const int cw = warp - 2;
-    const int quad = warp & 3;
-    const int cq = cw >> 2;             // head index inside the chunk
-    const int row = quad * 32 + lane;
-    const uint32_t t_row = static_cast<uint32_t>(quad * 32) << 16;
-
-    ff_layer_norm_to_operand(X, M, tile0, lnw, lnb, sA, cw, lane);
-    fence_proxy_async_smem();
-    mbar_arrive(bar_a);
-    if (threadIdx.x == 64) FF_STAMP(82);
-
-    const uint32_t rsw = static_cast<uint32_t>(row >> 1) & 3u;   // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
-    const bool storer = threadIdx.x == 64;
-#pragma unroll 1
-    for (int n = 0; n < QF_NCHUNK; ++n) {
-      mbar_wait_cluster(&bar_dfull[n & 1], (n >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 64) FF_STAMP(104 + n * 2);
-      const uint32_t d = tmem_base + (n & 1) * 256 + t_row + cq * 64;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld_x32(d + half * 32, r);
-        tmem_ld_wait();
-        if (half == 1) {   // this thread's part of the accumulator is in registers: hand the buffer back
-          tc_fence_before();
-          mbar_arrive(&bar_dfree[n & 1]);
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (n < 2) {   // q and k: rotate pairs (2i, 2i+1), i = half * 16 + 4 q + t  (rope.py:43-52)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int q4 = (half * 4 + q) ^ (row & 7);
-            const float4 cc = *reinterpret_cast<const float4*>(sCos + row * 32 + 4 * q4);
-            const float4 ss = *reinterpret_cast<const float4*>(sSin + row * 32 + 4 * q4);
-            const float c4[4] = {cc.x, cc.y, cc.z, cc.w}, s4[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float x1 = v[8 * q + 2 * t], x2 = v[8 * q + 2 * t + 1];
-              v[8 * q + 2 * t] = x1 * c4[t] - x2 * s4[t];
-              v[8 * q + 2 * t + 1] = x1 * s4[t] + x2 * c4[t];
-            }
-          }
-        }
-        // staging tiles are double buffered by half: the stores of the previous half (other buffer) are waited for just
-        // before this half's barrier, so the buffer the NEXT half overwrites is known to be drained by then
-        uint8_t* sbuf = sOut + half * (4 * QF_OUT_TILE);
-        uint8_t* stile = sbuf + cq * QF_OUT_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
-          o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-          o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-          o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-          *reinterpret_cast<uint4*>(stile + row * 64 + ((static_cast<uint32_t>(q) ^ rsw) << 4)) = o;
-        }
-        fence_proxy_async_smem();
-        if (storer) bulk_wait_read<0>();
-        named_bar_sync(1, FF_CTHREADS);
-        if (storer) {
-#pragma unroll
-          for (int hd = 0; hd < 4; ++hd) tma_store_2d(&tmO, sbuf + hd * QF_OUT_TILE, n * 256 + hd * 64 + half * 32, tile0);
-          bulk_commit();
-        }
-      }
-    }
-    if (threadIdx.x == 64) FF_STAMP(110);
-    if (storer) bulk_wait_all<0>();   // the stores must have landed before the grid counts as complete
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // neither CTA frees its tensor memory or exits while the pair's MMAs / remote arrives can touch it
-  if (threadIdx.x == 0) FF_STAMP(111);
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair<512>(tmem_base);
-  }
-}
-
-
 }  // namespace a2m

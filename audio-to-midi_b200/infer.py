@@ -43,6 +43,10 @@ def predict_and_stitch(model, state, samples, window_duration: float, overlap: f
         parts = (samples[i:i + max_batch] for i in range(0, samples.shape[0], max_batch))
         for _logits, p in model.predict_pipelined(parts, rope_freqs, state=state, copy=True):
             chunks.append(p)
+    elif hasattr(samples, "is_cuda") and samples.shape[0] > max_batch:
+        # device windows in several batches: two in flight on two streams / workspaces (model.predict_many)
+        parts = [samples[i:i + max_batch] for i in range(0, samples.shape[0], max_batch)]
+        chunks = [p.cpu().numpy() for _logits, p in model.predict_many(state, parts, rope_freqs)]
     else:
         predict = vmap(model.predict, in_axes=(None, 0, None))
         for i in range(0, samples.shape[0], max_batch):
@@ -123,10 +127,8 @@ def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int 
     n_total = int(windows.shape[0])
     lo, hi = shard_windows(n_total, world_size, rank)
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
-    chunks = []
-    for i in range(lo, hi, max_batch):
-        _lg, p = model.predict(None, windows[i:min(i + max_batch, hi)], rope_freqs)
-        chunks.append(p)
+    parts = [windows[i:min(i + max_batch, hi)] for i in range(lo, hi, max_batch)]
+    chunks = [p for _lg, p in model.predict_many(None, parts, rope_freqs)]     # consecutive batches overlap on two streams
     local = torch.cat(chunks) if chunks else torch.zeros((0, 250, 90), dtype=torch.float32, device=windows.device)
     if world_size > 1:
         if not gather or (explicit and dworld != world_size):

@@ -39,6 +39,7 @@ extern "C" {
 #define A2M_FRAMES 250           /* model output frames per window */
 #define A2M_VOCAB 90             /* audio_to_midi_dataset.py:26 MIDI_EVENT_VOCCAB_SIZE */
 #define A2M_ROPE_DIM 32          /* rope.py:12-22 with dim = attention_size = 64 */
+#define A2M_HOST_SLOTS 4         /* batches in flight on the pipelined host path (a2m_submit_host*) */
 
 typedef struct A2mHandle A2mHandle;
 
@@ -93,7 +94,10 @@ size_t a2m_workspace_bytes(const A2mHandle* h, int32_t batch, int32_t training);
  *   rope_cos_dev / rope_sin_dev [rope_max_pos, 32] fp32, rope_max_pos >= 250   (RopeFreqs, rope.py:5-22)
  *   logits_dev, probs_dev [batch, 250, 90] fp32   (return value of model.predict, model.py:771-773)
  *   workspace_dev: NULL, or >= a2m_workspace_bytes(h, batch, 0) bytes, 1024-byte aligned, zero-initialised
- *                  once by the caller before its first use. */
+ *                  once by the caller before its first use.
+ * Calls on DIFFERENT streams may be in flight at the same time if each uses its own workspace_dev (one launch plan and CUDA
+ * graph is kept per (batch, workspace)); that is how consecutive independent batches are overlapped (two lanes: 1.32 ms per
+ * 64-window batch against 1.55 ms back to back).  workspace_dev = NULL is the handle's single default workspace. */
 int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float* rope_cos_dev,
                 const float* rope_sin_dev, int32_t rope_max_pos, float* logits_dev, float* probs_dev,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
@@ -103,9 +107,10 @@ int a2m_forward(A2mHandle* h, const float* audio_dev, int32_t batch, const float
 int a2m_forward_host(A2mHandle* h, const float* audio_host, int32_t batch, const float* rope_cos_host,
                      const float* rope_sin_host, int32_t rope_max_pos, float* logits_host, float* probs_host);
 
-/* Pipelined host path: two slots (0, 1).  a2m_submit_host enqueues H2D copy -> forward -> D2H copy for one batch
- * and returns; a2m_collect_host waits for that slot's results.  Copies of one slot overlap the compute of the
- * other (separate copy streams, one compute stream).  Buffers allocated with a2m_host_alloc (page-locked) are
+/* Pipelined host path: A2M_HOST_SLOTS slots (0 .. 3).  a2m_submit_host enqueues H2D copy -> forward -> D2H copy for one
+ * batch and returns; a2m_collect_host waits for that slot's results.  Each slot has its own copy stream and device buffers;
+ * the forwards run on two compute lanes (stream + workspace; slot & 1), so with four batches in flight two are computing --
+ * overlapping each other -- while one uploads and one downloads.  Buffers allocated with a2m_host_alloc (page-locked) are
  * copied from / to directly; pageable buffers go through an internal staging copy.  The caller's buffers must
  * stay valid and untouched until the slot has been collected. */
 int a2m_submit_host(A2mHandle* h, int32_t slot, const float* audio_host, int32_t batch, const float* rope_cos_host,

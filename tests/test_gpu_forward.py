@@ -141,7 +141,7 @@ def test_fused_and_unfused_paths_agree(tmp_path):
     outs = {}
     settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_POST": "0", "A2M_FUSE_FFN": "0", "A2M_MID_TC": "0",
                                            "A2M_FUSE_B256": "0", "A2M_FUSE_SMALL": "0"},
-                "ffn_only": {"A2M_FUSE_POST": "0"}, "qkv_pair": {"A2M_QKV_PAIR": "1"},
+                "ffn_only": {"A2M_FUSE_POST": "0"},
                 "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
     for name, env in settings.items():
         out = tmp_path / f"{name}.npy"
@@ -153,8 +153,6 @@ def test_fused_and_unfused_paths_agree(tmp_path):
     for name in ("unfused", "ffn_only"):
         d = np.abs(outs[name] - outs["default"]).max()
         assert 0 < d < 2e-2, (name, d)
-    # the CTA-pair (tcgen05 cta_group::2) q|k|v kernel accumulates the same products in the same order
-    assert np.abs(outs["qkv_pair"] - outs["default"]).max() < 1e-3
 
 
 def test_batch_invariance_bitwise():
@@ -233,3 +231,28 @@ def test_f16_operands_tighten_parity():
     assert launches["bf16"] == launches["f16"]
     assert errs["bf16"] < 3e-2
     assert errs["f16"] < 5e-3 and errs["f16"] < 0.25 * errs["bf16"]                        # measured 2.0e-2 / 2.4e-3
+
+
+def test_predict_many_overlaps_batches_bitwise():
+    """model.predict_many: consecutive independent batches alternate over two streams / workspaces / launch plans.  Results are
+    bit-identical to one predict call per batch (windows are independent and each lane runs the same kernels), for ragged batch
+    sizes, repeated calls, and with work enqueued on the caller's stream before and after (stream-ordered, no host sync)."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model
+    from oracle import synth
+    model, _ = make_model(4321, **ACTIVE)
+    rope = A.precompute_frequencies(64, 300)
+    wins = torch.tensor(synth.make_windows_fast(23, 5)).cuda()
+    parts = [wins[0:8], wins[8:16], wins[16:21], wins[21:23], wins[0:8]]
+    ref = [model.predict(None, p, rope) for p in parts]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        scaled = [p * 1.0 for p in parts]                      # produced on the current stream right before the call
+        got = model.predict_many(None, scaled, rope)
+        total = sum(float(pr.sum()) for _, pr in got)          # consumed on the current stream right after it
+        assert np.isfinite(total)
+        assert len(got) == len(ref)
+        for (lg, pr), (rl, rp) in zip(got, ref):
+            assert torch.equal(lg, rl) and torch.equal(pr, rp)
+    one = model.predict_many(None, [wins[:3]], rope)
+    assert torch.equal(one[0][1], model.predict(None, wins[:3], rope)[1])
