@@ -384,9 +384,6 @@ static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Bloc
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
 static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
 static bool g_local_bwd_tc = true;   // debug switch (A2M_LOCAL_BWD_TC=0): CUDA-core attn_local_bwd_kernel in the training backward
-static bool g_fuse_dgelu = false;     // A2M_FUSE_DGELU=1: GELU backward in the dgrad GEMM's epilogue instead of gelu_bwd_kernel.  Correct but slower
-                                      // (measured: dgrad GEMMs +0.33 ms per step against 0.30 ms of gelu_bwd_kernel saved; four epilogue warps per
-                                      // CTA evaluate gelu' for the whole tile while a full-chip elementwise kernel does it at 4.4 TB/s)
 static bool g_mid_bwd_tc = true;     // debug switch (A2M_MID_BWD_TC=0): CUDA-core block_small_bwd_kernel for stages 2-3
 static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
@@ -459,8 +456,6 @@ cudaError_t launch_gemm2(int BN, int mode, bool resid, const CUtensorMap& a, con
     case G2_BF16 * 10000 + 640: return launch_gemm2_t<64, G2_BF16, false>(a, b, c, r, g, num_sms, s);
     case G2_BF16 * 10000 + 1280: return launch_gemm2_t<128, G2_BF16, false>(a, b, c, r, g, num_sms, s);
     case G2_BF16 * 10000 + 2560: return launch_gemm2_t<256, G2_BF16, false>(a, b, c, r, g, num_sms, s);
-    case G2_BF16 * 10000 + 1281: return launch_gemm2_t<128, G2_BF16, true>(a, b, c, r, g, num_sms, s);
-    case G2_BF16 * 10000 + 2561: return launch_gemm2_t<256, G2_BF16, true>(a, b, c, r, g, num_sms, s);
     case G2_GLU * 10000 + 2560: return launch_gemm2_t<256, G2_GLU, false>(a, b, c, r, g, num_sms, s);
     case G2_ROPE * 10000 + 640: return launch_gemm2_t<64, G2_ROPE, false>(a, b, c, r, g, num_sms, s);
     case G2_ROPE * 10000 + 1280: return launch_gemm2_t<128, G2_ROPE, false>(a, b, c, r, g, num_sms, s);
@@ -484,10 +479,6 @@ bool gemm2_route(A2mHandle* h, int mode, const GemmArgs& g, int* mode2, bool* re
     }
     if (g.flags & (GF_GAMMA | GF_RESID)) return false;
     *mode2 = G2_BF16;
-    if (g.flags & GF_DGELU) {
-      *resid = true;
-      if (!make_tmap(h, tr, g.dgelu_u, g.M, g.N, g.dgelu_ld, 64, 128)) return false;
-    }
     return make_tmap(h, tc, g.out16, g.M, g.N, g.ld16, 64, 128);
   }
   if (mode == GEMM_GLU) {
@@ -531,8 +522,6 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<64, G2_BF16, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<128, G2_BF16, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<256, G2_BF16, false>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
-  if ((e = set_smem(gemm_tc2_kernel<128, G2_BF16, true>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
-  if ((e = set_smem(gemm_tc2_kernel<256, G2_BF16, true>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<256, G2_GLU, false>, gemm2_smem_bytes<256>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<64, G2_ROPE, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
@@ -1448,7 +1437,6 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_LOCAL_BWD_TC")) g_local_bwd_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_MID_BWD_TC")) g_mid_bwd_tc = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_FUSE_DGELU")) g_fuse_dgelu = std::atoi(e) != 0;
   return A2M_OK;
 }
 

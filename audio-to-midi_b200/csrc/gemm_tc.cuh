@@ -26,7 +26,6 @@ enum GemmMode : int {
 
 enum GemmFlags : uint32_t {
   GF_BIAS = 1u, GF_GELU = 2u, GF_GAMMA = 4u, GF_RESID = 8u, GF_OUT32 = 16u, GF_OUT16 = 32u,
-  GF_DGELU = 64u,   // bf16 out (gemm_tc2 only): out = acc * gelu'(dgelu_u[row][col]) -- the GELU backward fused into the dgrad GEMM
 };
 
 struct GemmArgs {
@@ -56,9 +55,6 @@ struct GemmArgs {
   // training: dropout of (acc + bias) before the residual add (FeedForwardBlock, model.py:237); gemm_tc2 G2_F32 only
   const DropParams* drop;
   uint32_t drop_site;
-  // GF_DGELU: the pre-activation the forward kept (bf16 [M, N], leading dimension dgelu_ld)
-  const __nv_bfloat16* dgelu_u;
-  int dgelu_ld;
 };
 
 constexpr int GEMM_BM = 128;

@@ -47,8 +47,8 @@ template <int BN, int MODE, bool RESID>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
-  // RESID: G2_F32 -- fp32 residual tile added in place;  G2_BF16 -- bf16 pre-activation tile u, out = acc * gelu'(u)
-  static_assert(!RESID || MODE == G2_F32 || MODE == G2_BF16, "the staged second operand exists for the fp32 and plain bf16 epilogues");
+  // RESID: G2_F32 -- fp32 residual tile added in place
+  static_assert(!RESID || MODE == G2_F32, "the staged second operand exists for the fp32 epilogue");
   constexpr int STAGES = g2_stages<BN>();
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -323,20 +323,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (g.flags & GF_GELU) {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-                }
-                if constexpr (RESID) {
-                  // the staged tile holds u (bf16) where the result goes: multiply by gelu'(u), then overwrite in place
-                  if (half == 0) mbar_wait(&bar_cfull[cb], (ck / G2_NCH) & 1);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint4 uu = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + q) ^ rsw) << 4));
-                    const uint32_t w4[4] = {uu.x, uu.y, uu.z, uu.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                      v[8 * q + 2 * t] *= gelu_tanh_deriv(__uint_as_float(w4[t] << 16));
-                      v[8 * q + 2 * t + 1] *= gelu_tanh_deriv(__uint_as_float(w4[t] & 0xffff0000u));
-                    }
-                  }
                 }
               } else if (col0 < g.rope_cols) {  // rope.py:43-52, pairs (2i, 2i+1), i = (col % 64) / 2
                 constexpr int kPairsPerHalf = 16;  // output chunks start at multiples of 64 columns

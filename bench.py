@@ -500,8 +500,8 @@ def run_ours(args):
     #   compact   f16 in, probabilities only, f16 out
     #   full_f32  fp32 in, logits + probabilities fp32 out (round 1's path)
     def e2e_run(pinned, **kw):
-        for _ in model.predict_pipelined((pinned[i % R] for i in range(3)), rope, **kw):
-            pass
+        for _ in model.predict_pipelined((pinned[i % R] for i in range(A.model.HOST_SLOTS + 3)), rope, **kw):
+            pass                                           # every slot's device buffers and the whole page-locked output ring exist now
         _barrier(ctx)
         t0 = time.perf_counter()
         n_done, last = 0, None

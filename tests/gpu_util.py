@@ -44,7 +44,7 @@ def debug_gemm(eng, bn, A_bf16, W_bf16, flags, bias=None, gamma=None, resid=None
     M, K = A_bf16.shape
     N = W_bf16.shape[0]
     out32 = torch.zeros((M, N), dtype=torch.float32, device="cuda:0") if want32 else None
-    out16 = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda:0") if want16 else None
+    out16 = torch.zeros((M, N), dtype=A_bf16.dtype, device="cuda:0") if want16 else None
     ptr = lambda t: None if t is None else t.data_ptr()
     stream = torch.cuda.current_stream().cuda_stream
     rc = eng.L.a2m_debug_gemm(eng.h, bn, M, N, K, A_bf16.data_ptr(), A_bf16.stride(0), W_bf16.data_ptr(), flags,

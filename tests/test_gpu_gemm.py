@@ -10,11 +10,15 @@ def _gelu(x):
     return 0.5 * x * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * x ** 3)))
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["bf16", "f16"])
+def eng(request):
+    """One handle per operand-format build of the library; operands are generated in that build's 16-bit format."""
     from gpu_util import engine, make_model
-    m, _ = make_model(1)
-    return engine(m)
+    m, _ = make_model(1, precision=request.param)
+    e = engine(m)
+    e.op_dtype = torch.bfloat16 if request.param == "bf16" else torch.float16
+    e.keep_model = m
+    return e
 
 
 @pytest.mark.parametrize("bn,M,N,K", [
@@ -24,8 +28,8 @@ def eng():
 def test_gemm_plain(eng, bn, M, N, K):
     from gpu_util import debug_gemm
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
-    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
-    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(torch.bfloat16).cuda()
+    a = torch.randn(M, K, generator=g).to(eng.op_dtype).cuda()
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(eng.op_dtype).cuda()
     out32, _ = debug_gemm(eng, bn, a, w, 16)
     ref = a.double().cpu().numpy() @ w.double().cpu().numpy().T
     err = np.abs(out32.cpu().numpy() - ref).max()
@@ -36,8 +40,8 @@ def test_gemm_fused_epilogue(eng):
     from gpu_util import debug_gemm
     M, N, K = 1500, 256, 128
     g = torch.Generator(device="cpu").manual_seed(5)
-    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
-    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(torch.bfloat16).cuda()
+    a = torch.randn(M, K, generator=g).to(eng.op_dtype).cuda()
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(eng.op_dtype).cuda()
     bias = torch.randn(N, generator=g).cuda()
     gamma = torch.rand(N, generator=g).cuda() + 0.5
     resid = torch.randn(M, N, generator=g).cuda()
@@ -57,9 +61,9 @@ def test_gemm_strided_a(eng):
     from gpu_util import debug_gemm
     M, N, K = 700, 128, 64
     g = torch.Generator(device="cpu").manual_seed(9)
-    full = torch.randn(M, 320, generator=g).to(torch.bfloat16).cuda()
+    full = torch.randn(M, 320, generator=g).to(eng.op_dtype).cuda()
     a = full[:, 256:]
-    w = (torch.randn(N, K, generator=g) / 8).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / 8).to(eng.op_dtype).cuda()
     o32, _ = debug_gemm(eng, 128, a, w, 16)
     ref = a.double().cpu().numpy() @ w.double().cpu().numpy().T
     assert np.abs(o32.cpu().numpy() - ref).max() < 2e-3
@@ -71,7 +75,7 @@ def test_cta_pair_gemm(M, N, K):
     import ctypes as C
     from audio_to_midi_b200 import _lib
     from gpu_util import engine, make_model
-    m, _ = make_model(1)
+    m, _ = make_model(1, precision="bf16")
     eng = engine(m)
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     A_ = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()

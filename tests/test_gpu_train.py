@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
                                                      (16384, 1024, 256, 0), (3000, 256, 512, 0), (64, 128, 64, 0)])
 def test_wgrad_gemm(tokens, n_out, k_out, pad):
     """dW += dY^T X on tcgen05 with both operands MN-major (gemm_wgrad.cuh) vs fp64."""
-    m, _ = make_model(1)
+    m, _ = make_model(1, precision="bf16")      # the wgrad kernel is part of the (bf16) training path
     eng = engine(m)
     g = torch.Generator(device="cpu").manual_seed(tokens + n_out)
     dY = (torch.randn(tokens, n_out, generator=g) * 0.5).to(torch.bfloat16).cuda()
@@ -165,7 +165,7 @@ def test_tensor_core_backward_kernels_agree_with_cuda_core_ones(tmp_path):
         "l, g, z, eng = U.cuda_grads(tree, audio, labels, dropout=0.1, seed=99)\n"
         "np.savez(sys.argv[1], loss=l, **{k: v for k, v in g.items() if v is not None})\n")
     outs = {}
-    for name, env in {"tc": {}, "cuda_core": {"A2M_LOCAL_BWD_TC": "0", "A2M_MID_BWD_TC": "0"}, "dgelu": {"A2M_FUSE_DGELU": "1"}}.items():
+    for name, env in {"tc": {}, "cuda_core": {"A2M_LOCAL_BWD_TC": "0", "A2M_MID_BWD_TC": "0"}}.items():
         out = tmp_path / f"{name}.npz"
         res = subprocess.run([sys.executable, "-c", script, str(out)], env={**os.environ, **env}, capture_output=True, text=True,
                              timeout=600)
@@ -184,10 +184,6 @@ def test_tensor_core_backward_kernels_agree_with_cuda_core_ones(tmp_path):
         differ += int(rel > 0)
     assert worst < 0.03, worst
     assert differ > 100, differ
-    # the GELU backward fused into the dgrad GEMM's epilogue (off by default: slower) computes the same gradients
-    worst = max(float(np.linalg.norm(outs["dgelu"][k].astype(np.float64) - b.astype(np.float64)) / max(float(np.linalg.norm(b)), 1e-30))
-                for k, b in outs["tc"].items() if k != "loss" and not k.endswith("stochastic_depth_dropout.p"))
-    assert worst < 0.03, worst
 
 
 def test_train_pipelined_matches_step_by_step():
