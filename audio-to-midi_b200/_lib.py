@@ -42,7 +42,7 @@ EXPORTS = [
     "a2m_adamw_step", "a2m_train_launch_count", "a2m_debug_wgrad", "a2m_profile_train_steps",
     "a2m_stitch_probs", "a2m_extract_events", "extract_midi_events", "free_midi_events", "a2m_to_frame_events",
     "a2m_create_ex", "a2m_submit_host_ex", "a2m_event_metrics", "a2m_set_params", "a2m_get_opt_state", "a2m_set_opt_state",
-    "a2m_operand_format", "a2m_debug_round_operand", "a2m_backward_dlogits", "a2m_allreduce_grads", "a2m_comm_unique_id", "a2m_comm_init", "a2m_comm_get", "a2m_comm_destroy",
+    "a2m_operand_format", "a2m_debug_round_operand", "a2m_stitch_probs_dev", "a2m_extract_events_dev", "a2m_backward_dlogits", "a2m_allreduce_grads", "a2m_comm_unique_id", "a2m_comm_init", "a2m_comm_get", "a2m_comm_destroy",
 ]
 
 
@@ -174,6 +174,10 @@ def lib(precision: str = "bf16") -> C.CDLL:
     L.a2m_comm_get.restype = vp
     L.a2m_comm_destroy.argtypes = [vp]
     L.a2m_comm_destroy.restype = C.c_int
+    L.a2m_stitch_probs_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, f64, f64, vp, C.c_int64, vp]
+    L.a2m_stitch_probs_dev.restype = C.c_int64
+    L.a2m_extract_events_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, i32, vp]
+    L.a2m_extract_events_dev.restype = C.c_int
     L.a2m_operand_format.argtypes = []
     L.a2m_operand_format.restype = C.c_char_p
     L.a2m_debug_round_operand.argtypes = [vp, vp, C.c_int64]

@@ -315,6 +315,8 @@ struct A2mHandle {
   TrainState* train = nullptr;   // training path (a2m_train.inc)
   bool train_configured = false; // dynamic-smem opt-in of the training kernels done on this handle's device
   void* clip_stats = nullptr;    // device ClipStats of a2m_prepare_windows
+  long long* row0_dev = nullptr; // a2m_stitch_probs_dev: first stitched row of every window
+  size_t row0_cap = 0;
   float* em_pred = nullptr;      // a2m_event_metrics: rasterised predictions when the caller does not want them
   size_t em_pred_elems = 0;
   ncclComm_t comm = nullptr;     // a2m_comm_init (data-parallel training); owned by the handle
@@ -1484,6 +1486,7 @@ void a2m_destroy(A2mHandle* h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->clip_stats) cudaFree(h->clip_stats);
   if (h->em_pred) cudaFree(h->em_pred);
+  if (h->row0_dev) cudaFree(h->row0_dev);
   train_free(h);
   comm_free(h);
   delete h;
@@ -1733,6 +1736,7 @@ int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expecte
   if (!pred) {
     if (h->em_pred_elems < elems) {
       if (h->em_pred) cudaFree(h->em_pred);
+  if (h->row0_dev) cudaFree(h->row0_dev);
       h->em_pred = nullptr;
       h->em_pred_elems = 0;
       CUDA_TRY(cudaMalloc(&h->em_pred, elems * 4));
@@ -1747,6 +1751,61 @@ int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expecte
   }
   event_metrics_kernel<<<batch, EM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(probs_dev, expected_dev, frames, A2M_VOCAB, pred, metrics_dev,
                                                                                      n_events_dev, d);
+  CUDA_TRY(cudaGetLastError());
+  return A2M_OK;
+}
+
+// stitch_probs (common.rs:13-45) on the device.  Returns the number of stitched frames, or a negative code: A2M_EINVAL also when
+// consecutive cross-fades would chain (overlap >= half a window), which only the sequential host code handles.
+int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windows, int64_t frames, int64_t cats, double overlap,
+                             double duration_per_frame, float* out_dev, int64_t out_capacity_frames, void* stream_v) {
+  if (!h) return A2M_EINVAL;
+  if (!probs_dev || windows <= 0 || frames <= 0 || cats <= 0 || !(duration_per_frame > 0.0)) { h->err = "bad stitch arguments"; return A2M_EINVAL; }
+  const double ov = overlap / duration_per_frame;
+  const int64_t out_frames = windows * frames - static_cast<int64_t>(ov) * (windows - 1);
+  if (!out_dev) return out_frames;
+  const int64_t blend_until = static_cast<int64_t>(std::ceil(ov));
+  if (out_frames <= 0 || out_capacity_frames < out_frames || ov < 0.0 || frames - blend_until - 1 <= blend_until) {
+    h->err = "stitch: output too small, or overlap too large for the device path (use a2m_stitch_probs)";
+    return A2M_EINVAL;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<long long> row0(static_cast<size_t>(windows));
+  double base = 0.0;
+  for (int64_t w = 0; w < windows; ++w) {              // common.rs:41: the base advances by the FRACTIONAL amount, rows truncate it
+    row0[static_cast<size_t>(w)] = static_cast<long long>(base);
+    base += static_cast<double>(frames) - ov;
+  }
+  if (h->row0_cap < static_cast<size_t>(windows)) {
+    if (h->row0_dev) cudaFree(h->row0_dev);
+    h->row0_dev = nullptr;
+    h->row0_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->row0_dev, sizeof(long long) * static_cast<size_t>(windows)));
+    h->row0_cap = static_cast<size_t>(windows);
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->row0_dev, row0.data(), sizeof(long long) * row0.size(), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));             // row0 is a stack-lifetime host vector
+  const long long total = out_frames * cats;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16ll));
+  stitch_probs_kernel<<<grid, 256, 0, stream>>>(probs_dev, h->row0_dev, static_cast<int>(windows), static_cast<int>(frames),
+                                                static_cast<int>(cats), ov, static_cast<int>(blend_until), out_frames, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return out_frames;
+}
+
+// extract_events (common.rs:47-144) on the device: events_dev [notes][cap] of (attack, duration) uint32 pairs, counts_dev [notes].
+// A count above cap means that key overflowed (the caller falls back to a2m_extract_events).  Velocity is the constant 7.
+int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint32_t* events_dev, int32_t* counts_dev,
+                           int32_t cap, void* stream_v) {
+  if (!h) return A2M_EINVAL;
+  if (!probs_dev || !events_dev || !counts_dev || frames <= 0 || frames > 0x7fffffff || notes <= 0 || notes > EX_THREADS || cap <= 0) {
+    h->err = "bad extract_events_dev arguments";
+    return A2M_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  extract_events_kernel<<<1, EX_THREADS, 0, static_cast<cudaStream_t>(stream_v)>>>(probs_dev, static_cast<int>(frames), static_cast<int>(notes),
+                                                                                    reinterpret_cast<uint2*>(events_dev), counts_dev, cap);
   CUDA_TRY(cudaGetLastError());
   return A2M_OK;
 }

@@ -97,3 +97,106 @@ __global__ void __launch_bounds__(EM_THREADS) event_metrics_kernel(const float* 
 }
 
 }  // namespace a2m
+
+// ============================================================================================= long-clip post-processing
+// stitch_probs (common.rs:13-45) and extract_events (common.rs:47-144) on the device, so that the probabilities of a long clip
+// (config 5: 134 windows -> 30 175 stitched frames) never travel to the host: only the event list does.
+namespace a2m {
+
+// out[row, c] for every stitched row.  The reference writes windows in order into a zero-filled track: window w, frame f goes to
+// row row0[w] + f (row0 = the truncated running sum of frames - overlap, accumulated in f64 on the host exactly as common.rs:41
+// does); for w > 0 and f <= ceil(overlap) the write is the f64 blend (1 - f / ov) * old + (f / ov) * new.  Every row is therefore
+// decided by the LAST window that covers it, and `old` is the previous window's plain value (or 0 where that window has ended);
+// the host only takes this path when cross-fades cannot chain (frames - ceil(ov) - 1 > ceil(ov)).  No FMA contraction: the host
+// code rounds the two products and the sum separately.
+__global__ void __launch_bounds__(256) stitch_probs_kernel(const float* __restrict__ probs, const long long* __restrict__ row0, int W, int F,
+                                                           int cats, double ov, int blend_until, long long out_frames,
+                                                           float* __restrict__ out) {
+  const long long total = out_frames * cats;
+  const double step = static_cast<double>(F) - ov;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / cats;
+    const int c = static_cast<int>(i - r * cats);
+    int w = step > 0.0 ? static_cast<int>(static_cast<double>(r) / step) : 0;
+    w = min(max(w, 0), W - 1);
+    while (w + 1 < W && row0[w + 1] <= r) ++w;
+    while (w > 0 && row0[w] > r) --w;
+    const long long f = r - row0[w];
+    float v = 0.f;
+    if (f < F) {
+      const float x = probs[(static_cast<long long>(w) * F + f) * cats + c];
+      if (w > 0 && f <= blend_until) {
+        const long long fp = r - row0[w - 1];
+        const float old = fp < F ? probs[(static_cast<long long>(w - 1) * F + fp) * cats + c] : 0.f;
+        const double t = static_cast<double>(f) / ov;       // 0 / 0 = NaN when overlap == 0, as in the reference
+        v = static_cast<float>(__dadd_rn(__dmul_rn(1.0 - t, static_cast<double>(old)), __dmul_rn(t, static_cast<double>(x))));
+      } else {
+        v = x;
+      }
+    }
+    out[i] = v;
+  }
+}
+
+constexpr int EX_TILE = 64;      // frames per shared-memory tile
+constexpr int EX_HALO = 6;       // the re-attack test looks 6 frames back and 6 ahead (common.rs:93-112)
+constexpr int EX_THREADS = 96;
+
+// One CTA, one thread per key (notes <= 96): the state machine of event_metrics_kernel over the F frames of a stitched track,
+// fed through shared-memory tiles of EX_TILE + 2 * EX_HALO frames (coalesced loads; the machine itself is sequential per key).
+// events[key][k] = (attack, duration) for k < counts[key] <= cap; counts may exceed cap (overflow: the caller re-runs on the host).
+__global__ void __launch_bounds__(EX_THREADS) extract_events_kernel(const float* __restrict__ probs, int F, int notes, uint2* __restrict__ events,
+                                                                    int* __restrict__ counts, int cap) {
+  __shared__ float tile[EX_TILE + 2 * EX_HALO][EX_THREADS];
+  const int key = threadIdx.x;
+  int started = -1, count = 0;
+  auto emit = [&](int start, int dur) {
+    if (key < notes && count < cap) events[static_cast<size_t>(key) * cap + count] = make_uint2(static_cast<uint32_t>(start), static_cast<uint32_t>(dur));
+    ++count;
+  };
+  for (int f0 = 0; f0 < F; f0 += EX_TILE) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (EX_TILE + 2 * EX_HALO) * notes; i += EX_THREADS) {
+      const int rr = i / notes, cc = i - rr * notes;
+      const int f = f0 - EX_HALO + rr;
+      tile[rr][cc] = (f >= 0 && f < F) ? probs[static_cast<size_t>(f) * notes + cc] : 0.f;
+    }
+    __syncthreads();
+    if (key >= notes) continue;
+    const int fend = min(f0 + EX_TILE, F);
+    for (int f = f0; f < fend; ++f) {
+      const int r = f - f0 + EX_HALO;
+      const float cur = tile[r][key];
+      if (started < 0) {
+        if (cur > 0.5f) started = f;
+        continue;
+      }
+      if (cur < 0.1f) {
+        emit(started, max(f - started, 1));
+        started = -1;
+        continue;
+      }
+      bool rising = false;
+      if (static_cast<float>(f) - static_cast<float>(started) > 5.0f) {      // f - 6 >= started >= 0, so the look-back is in range
+        float before = 0.f, after = 0.f;
+        for (int i = -6; i < 0; ++i) before = __fadd_rn(before, tile[r + i][key]);
+        before = __fdiv_rn(before, 6.0f);
+        const int n = min(6, F - f);
+        for (int i = 0; i < n; ++i) after = __fadd_rn(after, tile[r + i][key]);
+        after = __fdiv_rn(after, 6.0f);
+        rising = __fsub_rn(after, before) > 0.1f;
+      }
+      if (f < F - 1 && cur < tile[r + 1][key]) continue;
+      if (cur > 0.4f && rising) {
+        emit(started, max(f - 1 - started, 1));
+        started = f;
+      }
+    }
+  }
+  if (key < notes) {
+    if (started >= 0) emit(started, max(F - started, 1));
+    counts[key] = count;
+  }
+}
+
+}  // namespace a2m

@@ -110,14 +110,69 @@ def _dist_world():
     return 0, 1
 
 
+def stitch_probs_device(model, probs, overlap: float, duration_per_frame: float):
+    """modelutil.stitch_probs on the device (a2m_stitch_probs_dev, bit-identical to the host function): probs torch CUDA
+    [W, F, 90] -> torch CUDA [F', 90].  Falls back to the host function when the overlap is so large that cross-fades chain."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    dev = probs.device.index if probs.device.index is not None else torch.cuda.current_device()
+    eng = model._engine(dev)
+    probs = probs.to(torch.float32).contiguous()
+    W, F, K = (int(v) for v in probs.shape)
+    stream = C.c_void_p(torch.cuda.current_stream(probs.device).cuda_stream)
+    n = int(eng.L.a2m_stitch_probs_dev(eng.h, probs.data_ptr(), W, F, K, float(overlap), float(duration_per_frame), None, 0, stream))
+    if n > 0:
+        out = torch.empty((n, K), dtype=torch.float32, device=probs.device)
+        rc = int(eng.L.a2m_stitch_probs_dev(eng.h, probs.data_ptr(), W, F, K, float(overlap), float(duration_per_frame), out.data_ptr(), n, stream))
+        if rc == n:
+            return out
+    return torch.as_tensor(modelutil.stitch_probs(probs.cpu().numpy(), overlap, duration_per_frame)).to(probs.device)
+
+
+def extract_events_device(model, stitched, cap: int = 4096):
+    """modelutil.extract_events on the device (a2m_extract_events_dev: one thread per key runs the hysteresis state machine over
+    the frames of its key): stitched torch CUDA [F, 90] -> the same sorted list of (attack, key, duration, velocity) tuples.
+    Only the per-key event tables (a few KB) return to the host, which merges and sorts them as common.rs:142 does."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    dev = stitched.device.index if stitched.device.index is not None else torch.cuda.current_device()
+    eng = model._engine(dev)
+    stitched = stitched.to(torch.float32).contiguous()
+    F, K = (int(v) for v in stitched.shape)
+    if K > 96:
+        return modelutil.extract_events(stitched.cpu().numpy())
+    ev = torch.empty((K, cap, 2), dtype=torch.int32, device=stitched.device)
+    cnt = torch.empty(K, dtype=torch.int32, device=stitched.device)
+    stream = C.c_void_p(torch.cuda.current_stream(stitched.device).cuda_stream)
+    rc = eng.L.a2m_extract_events_dev(eng.h, stitched.data_ptr(), F, K, ev.data_ptr(), cnt.data_ptr(), cap, stream)
+    _lib.check(eng.h, rc, "a2m_extract_events_dev", eng.L)
+    counts = cnt.cpu().numpy()
+    if int(counts.max(initial=0)) > cap:                       # a key overflowed its table: the host extractor has no limit
+        return modelutil.extract_events(stitched.cpu().numpy())
+    used = int(counts.max(initial=0))
+    if used == 0:
+        return []
+    table = ev[:, :used].cpu().numpy().view(np.uint32)          # [K, used, 2]
+    keys, slots = np.nonzero(np.arange(used)[None, :] < counts[:, None])
+    attack = table[keys, slots, 0].astype(np.int64)
+    dur = table[keys, slots, 1].astype(np.int64)
+    order = np.lexsort((dur, keys, attack))                     # (attack, key, duration, velocity) ascending; velocity is constant
+    return list(zip(attack[order].tolist(), keys[order].tolist(), dur[order].tolist(), [7] * len(order)))
+
+
 def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 64, rank: int = None, world_size: int = None,
-                    gather: bool = True):
+                    gather: bool = True, want_arrays: bool = True):
     """Long-audio transcription (BASELINE config 5; infer.py:339 / audio_to_midi.py:38-53): normalise + slice on the
     device, batched forward of this rank's block of windows, rank-ordered gather of the probabilities, then stitch and
     eventize.  rank / world_size default to the torch.distributed process group (1 process: no collective at all).
     Returns (events, stitched_probs, probs): with several ranks, rank 0 gets the whole clip's events / stitched track and
     every rank the gathered probabilities; with gather=False (or explicit rank / world_size without a process group, as the
-    single-process partition tests use) a rank returns (None, None, probabilities of its own block)."""
+    single-process partition tests use) a rank returns (None, None, probabilities of its own block).
+    Stitching and event extraction run on the device (stitch_probs_device / extract_events_device, bit-identical to modelutil):
+    with want_arrays=False the probabilities never leave the GPU -- only the event list does, which is all audio_to_midi.py:53-56
+    needs to write the MIDI file -- and (events, None, None) is returned."""
     import torch
     drank, dworld = _dist_world()
     explicit = rank is not None or world_size is not None
@@ -133,13 +188,16 @@ def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int 
     if world_size > 1:
         if not gather or (explicit and dworld != world_size):
             return None, None, local.cpu().numpy().astype(np.float32)
-        probs = gather_window_blocks(local, n_total, world_size, rank).cpu().numpy().astype(np.float32)
+        probs_dev = gather_window_blocks(local, n_total, world_size, rank)
         if rank != 0:
-            return None, None, probs
+            return None, None, (probs_dev.cpu().numpy() if want_arrays else None)
     else:
-        probs = local.cpu().numpy().astype(np.float32)
-    stitched = modelutil.stitch_probs(probs, overlap, MODEL_AUDIO_LENGTH / probs.shape[1])
-    return modelutil.extract_events(stitched), stitched, probs
+        probs_dev = local
+    stitched_dev = stitch_probs_device(model, probs_dev, overlap, MODEL_AUDIO_LENGTH / probs_dev.shape[1])
+    events = extract_events_device(model, stitched_dev)
+    if not want_arrays:
+        return events, None, None
+    return events, stitched_dev.cpu().numpy(), probs_dev.cpu().numpy()
 
 
 _METRIC_KEYS = ("full_diff", "phantom_notes_diff", "missed_notes_diff", "notes_hit", "hit_rate")

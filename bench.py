@@ -368,17 +368,19 @@ def measure_clip(ctx, model):
         _barrier(ctx)
         t0 = time.perf_counter()
         dev_clip = pin.to(ctx.dev, non_blocking=True)
-        events, stitched, probs = I.transcribe_clip(model, dev_clip, overlap=0.5, max_batch=64)
+        events, _st, _pr = I.transcribe_clip(model, dev_clip, overlap=0.5, max_batch=64, want_arrays=False)
         torch.cuda.synchronize()
         dt = _max_over_ranks(ctx, time.perf_counter() - t0)
         if it > 0:
             times.append(dt)
         if ctx.rank == 0:
-            n_events, frames, n_windows = len(events), int(stitched.shape[0]), int(probs.shape[0])
+            n_windows = int(model._engine(ctx.dev.index).L.a2m_window_count(clip.shape[1], 0.5))
+            n_events, frames = len(events), n_windows * 250 - 25 * (n_windows - 1)
     best = statistics.median(times)
     return {"metric": "clip audio-seconds/sec transcribed end to end", "value": 600.0 / best, "unit": "audio-s/s", "seconds_per_clip": best,
             "clip_seconds": 600.0, "windows": n_windows, "windows_per_gpu": -(-n_windows // ctx.world), "stitched_frames": frames, "events": n_events,
-            "h2d_bytes": int(clip.nbytes) * ctx.world, "gather": "all_gather of [windows/N, 250, 90] fp32 blocks (NCCL), rank 0 stitches + eventizes (C++)" if ctx.world > 1 else "none (one rank)",
+            "h2d_bytes": int(clip.nbytes) * ctx.world, "d2h": "the event list only (per-key tables of (attack, duration), a few KB): stitch_probs and extract_events run on the device",
+            "gather": "all_gather of [windows/N, 250, 90] fp32 blocks (NCCL), rank 0 stitches + eventizes on its GPU" if ctx.world > 1 else "none (one rank)",
             "what": "BASELINE.json configs[4]; infer.transcribe_clip; median of 3 after 1 warm-up; every rank uploads and normalises the whole clip "
                     "(the loudness statistics need all of it), then forwards only its block of windows"}
 

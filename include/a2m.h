@@ -158,6 +158,19 @@ const char* a2m_operand_format(void);
 /* test hook: host-side rounding of fp32 values to the operand format (what a2m_load_weights applies to the weights) */
 int a2m_debug_round_operand(const float* in_host, uint16_t* out_host, int64_t n);
 
+/* stitch_probs (common.rs:13-45) and extract_events (common.rs:47-144) on the device ("extract_events is
+ * independent per key"), so that the probabilities of a long clip never travel to the host -- only its event list does.
+ * a2m_stitch_probs_dev: probs_dev [windows, frames, cats] -> out_dev [out_frames, cats], bit-identical to a2m_stitch_probs;
+ * returns out_frames (out_dev = NULL queries it), or A2M_EINVAL (also when overlap >= about half a window, where consecutive
+ * cross-fades would chain: use the host function).  a2m_extract_events_dev: probs_dev [frames, notes <= 96] ->
+ * events_dev [notes][cap][2] uint32 (attack, duration) in attack order per key and counts_dev [notes]; a count above cap means
+ * that key overflowed.  The caller merges the per-key lists and sorts them (attack, key, duration, velocity = 7), as
+ * common.rs:142 does. */
+int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windows, int64_t frames, int64_t cats, double overlap,
+                             double duration_per_frame, float* out_dev, int64_t out_capacity_frames, void* stream);
+int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint32_t* events_dev,
+                           int32_t* counts_dev, int32_t cap, void* stream);
+
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);
 /* Per-launch profile of the forward plan for `batch` windows: every step of the plan (all launches between

@@ -12,7 +12,7 @@ rep, kern = sys.argv[1], sys.argv[2]
 ntop = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 section = sys.argv[4] if len(sys.argv) > 4 else kern   # e.g. block_fused_kernelILi128ELb0 to pick one template instance
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(root, "audio-to-midi_b200", "_build", "libaudio2midi_b200.so")
+lib = os.environ.get("A2M_PROFILE_LIB") or os.path.join(root, "audio-to-midi_b200", "_build", "libaudio2midi_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "modelutil" not in f][0]
