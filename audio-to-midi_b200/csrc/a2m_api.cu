@@ -384,12 +384,7 @@ static thread_local bool tl_pdl = false;
 static unsigned g_pdl_mask = 0xffffffffu;
 static bool g_fuse_b256 = true;  // debug switch (A2M_FUSE_B256=0): stage-6 Blocks as dwconv_ln + two GEMM launches
 static bool g_fuse_small = true; // debug switch (A2M_FUSE_SMALL=0): stages 0-1 as three block_small_kernel launches each
-static bool g_mid_two = true;    // debug switch (A2M_MID_TWO=0): block_mid_kernel (one thread per token) instead of block_mid2_kernel
-static bool g_local_bwd_tc = true;   // debug switch (A2M_LOCAL_BWD_TC=0): CUDA-core attn_local_bwd_kernel in the training backward
-static bool g_mid_bwd_tc = true;     // debug switch (A2M_MID_BWD_TC=0): CUDA-core block_small_bwd_kernel for stages 2-3
-static bool g_mid_tc = true;     // debug switch (A2M_MID_TC=0): CUDA-core block_small_kernel for stages 1-3
 static bool g_fuse_qkv = true;   // debug switch (A2M_FUSE_QKV=0): separate attention_norm and q|k|v projection launches
-static bool g_fuse_post = true;  // debug switch (A2M_FUSE_POST=0): output projection as its own GEMM launch, then ffn_fused_kernel
 static bool g_fuse_ffn = true;   // debug switch (A2M_FUSE_FFN=0): un-fused LN / FFN-1 / FFN-2 launches
 enum PdlFamily { PF_SMALL = 0, PF_LN = 1, PF_GEMM = 2, PF_FUSED = 3, PF_ATTN = 4 };
 
@@ -528,7 +523,6 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(gemm_tc2_kernel<64, G2_ROPE, false>, gemm2_smem_bytes<64>())) != cudaSuccess) return e;
   if ((e = set_smem(gemm_tc2_kernel<128, G2_ROPE, false>, gemm2_smem_bytes<128>())) != cudaSuccess) return e;
   if ((e = set_smem(attn_global_kernel, AG_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(ffn_fused_kernel, FF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(qkv_fused_kernel, QF_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(postattn_fused_kernel, PA_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block256_fused_kernel, B6_SMEM)) != cudaSuccess) return e;
@@ -539,10 +533,6 @@ cudaError_t configure_kernels() {
   if ((e = set_smem(block_fused_kernel<128, false>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<64, true>, FusedBlockCfg<64>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_fused_kernel<128, true>, FusedBlockCfg<128>::SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(block_small_kernel<32>, small_block_smem<32>())) != cudaSuccess) return e;
-  if ((e = set_smem(block_mid_kernel<8>, MidBlockCfg<8>::SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(block_mid_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(block_mid_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid2_kernel<16>, MidBlockCfg<16>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(block_mid2_kernel<32>, MidBlockCfg<32>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(down_mid_kernel<16>, MidDownCfg<16>::SMEM)) != cudaSuccess) return e;
@@ -937,7 +927,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (s <= 4) {
         const float* prm = dev_ptr<float>(h, w.small_down[s]);
         const Meta md{"downsample_small_kernel", 2.0 * M * C * C, 8.0 * M * C};
-        if (s >= 3 && g_mid_tc) {
+        if (s >= 3) {   // Cin = 16, 32: the k2 s2 convolution as one small UMMA per tile (block_mid.cuh)
           const float* dp = dev_ptr<float>(h, w.down_p[s]);
           const uint4* dw = dev_ptr<uint4>(h, w.down_w[s]);
           const Meta mdt{"down_mid_kernel", 2.0 * M * C * C, 8.0 * M * C};
@@ -946,12 +936,10 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
             add_step(p, mdt, [=](cudaStream_t st) { return launch_k(PF_SMALL, down_mid_kernel<16>, grid, dim3(BM_TOK), MidDownCfg<16>::SMEM, st, in, out, M, dp, dw); });
           else
             add_step(p, mdt, [=](cudaStream_t st) { return launch_k(PF_SMALL, down_mid_kernel<32>, grid, dim3(BM_TOK), MidDownCfg<32>::SMEM, st, in, out, M, dp, dw); });
-        } else
-        switch (s) {
-          case 1: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); }); break;
-          case 2: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); }); break;
-          case 3: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<16>(in, out, M, prm, st); }); break;
-          default: add_step(p, md, [=](cudaStream_t st) { return launch_small_down<32>(in, out, M, prm, st); }); break;
+        } else if (s == 1) {
+          add_step(p, md, [=](cudaStream_t st) { return launch_small_down<4>(in, out, M, prm, st); });
+        } else {
+          add_step(p, md, [=](cudaStream_t st) { return launch_small_down<8>(in, out, M, prm, st); });
         }
       } else {
         // LN over the input channels -> bf16 [2M, Cin] == [M, 2*Cin]; conv k2 s2 == GEMM with K = 2*Cin
@@ -996,29 +984,20 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         const float* prm = dev_ptr<float>(h, w.small_block[s][j]);
         const size_t te = static_cast<size_t>(M) * C;
         const Meta mb{"block_small_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
-        if (s >= 2 && g_mid_tc) {   // C = 8 stays on the CUDA cores: per-tile set-up outweighs its 128 x 16 x 16 products
-          // pointwise convolutions on tcgen05 (block_mid.cuh)
+        if (s >= 2) {   // C = 16, 32: pointwise convolutions on tcgen05 (block_mid.cuh); C = 8 stays on the CUDA cores (per-tile set-up
+                        // outweighs its 128 x 16 x 16 products)
           const float* mp = dev_ptr<float>(h, w.mid_p[s][j]);
           const uint4* mw = dev_ptr<uint4>(h, w.mid_w[s][j]);
           const Meta mm{"block_mid_kernel", 2.0 * M * (7.0 * C + 4.0 * C * C), 8.0 * M * C};
-          const dim3 grid((M + BM_TOK - 1) / BM_TOK);
-          switch (s) {
-            case 1: add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<8>, grid, dim3(BM_TOK), MidBlockCfg<8>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te); break;
-            case 2:
-              if (g_mid_two) add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<16>, dim3(std::min<unsigned>(grid.x, h->num_sms * bm2_ctas_per_sm<16>())), dim3(BM2_THREADS), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
-              else add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<16>, grid, dim3(BM_TOK), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
-              break;
-            default:
-              if (g_mid_two) add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<32>, dim3(std::min<unsigned>(grid.x, h->num_sms * bm2_ctas_per_sm<32>())), dim3(BM2_THREADS), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
-              else add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid_kernel<32>, grid, dim3(BM_TOK), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
-              break;
-          }
-        } else
-        switch (s) {
-          case 0: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te); break;
-          case 1: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te); break;
-          case 2: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<16>(in, out, L, M, prm, st); }, label, out, te); break;
-          default: add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<32>(in, out, L, M, prm, st); }, label, out, te); break;
+          const unsigned tiles = (M + BM_TOK - 1) / BM_TOK;
+          if (s == 2)
+            add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<16>, dim3(std::min<unsigned>(tiles, h->num_sms * bm2_ctas_per_sm<16>())), dim3(BM2_THREADS), MidBlockCfg<16>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+          else
+            add_step(p, mm, [=](cudaStream_t st) { return launch_k(PF_SMALL, block_mid2_kernel<32>, dim3(std::min<unsigned>(tiles, h->num_sms * bm2_ctas_per_sm<32>())), dim3(BM2_THREADS), MidBlockCfg<32>::SMEM, st, in, out, L, M, mp, mw); }, label, out, te);
+        } else if (s == 0) {
+          add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<4>(in, out, L, M, prm, st); }, label, out, te);
+        } else {
+          add_step(p, mb, [=](cudaStream_t st) { return launch_small_block<8>(in, out, L, M, prm, st); }, label, out, te);
         }
         cur ^= 1;
       } else if (C <= 128) {
@@ -1189,7 +1168,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
         return launch_k(PF_ATTN, attn_global_kernel, dim3(2, ATT_HEADS, B), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, o16, kD, 256, static_cast<float*>(nullptr), static_cast<const DropParams*>(nullptr), 0u);
       });
     }
-    if (g_fuse_ffn && g_fuse_post) {
+    if (g_fuse_ffn) {
       // output projection + residual + feed_forward_norm + FFN + residual in one launch (postattn_fused.cuh)
       CUtensorMap to, two, tx, tw1, tw2;
       if (!make_tmap(h, &to, o16, Mt, kD, kD, 64, 128)) return false;
@@ -1216,22 +1195,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       g.resid = xt; g.ldr = kD; g.out32 = xt; g.ld32 = kD;
       if (!add_gemm(h, p, 128, GEMM_GENERIC, o16, kD, t.wo, g)) return false;
     }
-    if (g_fuse_ffn) {
-      // LN + FFN-1 + GLU + FFN-2 + residual in one launch (ffn_fused.cuh); x is updated in place
-      CUtensorMap tw1, tw2;
-      if (!make_tmap(h, &tw1, dev_ptr<__nv_bfloat16>(h, t.w1f), 2 * kFF, kD, kD, 64, 128)) return false;
-      if (!make_tmap(h, &tw2, dev_ptr<__nv_bfloat16>(h, t.w2), kD, kFF, kFF, 64, 256)) return false;
-      const float* lw = dev_ptr<float>(h, t.ln2w);
-      const float* lb = dev_ptr<float>(h, t.ln2b);
-      const float* b1f = dev_ptr<float>(h, t.b1f);
-      const float* b2 = dev_ptr<float>(h, t.b2);
-      const std::string label = "tl" + std::to_string(i / 2) + (local ? "_local" : "_global");
-      add_step(p, Meta{"ffn_fused_kernel", 2.0 * Mt * (2.0 * kFF * kD + static_cast<double>(kD) * kFF), 8.0 * Mt * kD + 2.0 * 3 * kFF * kD},
-               [=](cudaStream_t st) {
-                 return launch_k(PF_FUSED, ffn_fused_kernel, dim3((Mt + FF_ROWS - 1) / FF_ROWS), dim3(FF_THREADS), FF_SMEM, st, tw1, tw2, xt, Mt,
-                                 lw, lb, b1f, b2);
-               }, label, xt, static_cast<size_t>(Mt) * kD);
-    } else {
+    {
       {
         const float* lw = dev_ptr<float>(h, t.ln2w);
         const float* lb = dev_ptr<float>(h, t.ln2b);
@@ -1432,13 +1396,8 @@ int a2m_create(int device, A2mHandle** out) {
   if (const char* e = std::getenv("A2M_GRAPH")) h->use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_FFN")) g_fuse_ffn = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_QKV")) g_fuse_qkv = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_FUSE_POST")) g_fuse_post = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_MID_TC")) g_mid_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_SMALL")) g_fuse_small = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_MID_TWO")) g_mid_two = std::atoi(e) != 0;
   if (const char* e = std::getenv("A2M_FUSE_B256")) g_fuse_b256 = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_LOCAL_BWD_TC")) g_local_bwd_tc = std::atoi(e) != 0;
-  if (const char* e = std::getenv("A2M_MID_BWD_TC")) g_mid_bwd_tc = std::atoi(e) != 0;
   return A2M_OK;
 }
 

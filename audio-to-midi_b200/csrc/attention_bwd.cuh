@@ -7,7 +7,6 @@
 //                               dV += P^T dO,  dK += dS^T Q                  (A operand MN-major: P / dS as stored)
 //                               dQ += dS K                                   (B operand MN-major: K as stored)
 //                           then the inverse RoPE rotation of dQ / dK in the epilogue, bf16 stores.
-//   attn_local_bwd_kernel   LocalSelfAttention: 31 windows of 16 x 16 per (b, h) on CUDA cores (tiny tiles).
 //
 // Inputs are the RoPE-rotated bf16 projections the forward wrote (q||c and k||v buffers), the forward output O,
 // the softmax log-sum-exp per (row, head), and dO (bf16).  Outputs: dQ (raw, pre-RoPE) into the q columns of the
@@ -276,164 +275,6 @@ attn_global_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tmem_dealloc<AGB_TMEM_COLS>(tmem);
   }
 }
-
-// ------------------------------------------------------------------------------------------ local (CUDA cores)
-// One CTA per (half mt, head h, window b): output rows = padded rows 128 mt .. 128 mt + 127.  Padded row j (0..255) <->
-// token j - 3; pad tokens are zero rows.  Window w (0..30) covers padded rows 8w .. 8w+15; the output row of padded row
-// j is token-buffer row j (model.py:452-464, the reference's index shift), rows >= 250 are dropped, the mean is over the
-// covering windows.  The CTA stages padded rows 128 mt - 8 .. 128 mt + 135 (the rows of the 17 windows that touch its
-// output rows), recomputes their softmax / dS matrices (phase 1) and gathers dq, dk, dv per row (phase 2): no atomics,
-// the two windows shared with the neighbouring CTA are simply recomputed.
-constexpr int ALB_THREADS = 288;             // 9 warps: 17 x 16 = 272 (window, row) items in one round
-constexpr int ALB_ROWS = 144;
-constexpr int ALB_WIN = 17;
-constexpr int ALB_LD = 66;   // bf16 elements per smem row (odd word stride: conflict-free row-strided reads)
-constexpr size_t ALB_SMEM = 4 * ALB_ROWS * ALB_LD * 2 + 2 * ALB_WIN * 256 * 4;   // q, k, v, dO tiles + P / dS: ~111 KB
-
-// Q [B*256, ldq] (q columns, RoPE-rotated), KV [B*256, ldkv] (k rotated || v at v_col0), dOut [B*256, ldo] bf16:
-// gradient wrt the local-attention output rows (buffer row j = padded row j).  Outputs like the global kernel.
-__global__ void __launch_bounds__(ALB_THREADS, 2)
-attn_local_bwd_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ KV, int ldkv, int v_col0,
-                      const __nv_bfloat16* __restrict__ dOut, int ldo, const float* __restrict__ rope_cos,
-                      const float* __restrict__ rope_sin, __nv_bfloat16* __restrict__ dQ, int lddq,
-                      __nv_bfloat16* __restrict__ dKV, int lddkv, const DropParams* __restrict__ drop, uint32_t drop_site) {
-  extern __shared__ uint8_t smem_raw[];
-  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sk = sq + ALB_ROWS * ALB_LD;
-  __nv_bfloat16* sv = sk + ALB_ROWS * ALB_LD;
-  __nv_bfloat16* sd = sv + ALB_ROWS * ALB_LD;
-  float* sP = reinterpret_cast<float*>(sd + ALB_ROWS * ALB_LD);   // [17][16][16]  wn * softmax
-  float* sS = sP + ALB_WIN * 256;                                  // [17][16][16]  dS (already / 8)
-
-  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = 128 * mt - 8;        // padded row of local row 0
-  const int w0 = 16 * mt - 1;         // window of local window 0
-  pdl_launch_dependents();
-  pdl_wait();
-
-  // ---- stage q, k, v (padded-row indexed, zero pad tokens) and dOut (output-row indexed, zero rows >= 250)
-  for (int idx = threadIdx.x; idx < ALB_ROWS * 32; idx += ALB_THREADS) {
-    const int lr = idx >> 5, cpair = idx & 31;
-    const int j = j0 + lr;
-    const int tok = j - 3;
-    uint32_t q = 0u, k = 0u, v = 0u, d = 0u;
-    if (tok >= 0 && tok < ATT_T) {
-      const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
-      q = __ldg(reinterpret_cast<const uint32_t*>(Q + g * ldq + h * ATT_HD) + cpair);
-      k = __ldg(reinterpret_cast<const uint32_t*>(KV + g * ldkv + h * ATT_HD) + cpair);
-      v = __ldg(reinterpret_cast<const uint32_t*>(KV + g * ldkv + v_col0 + h * ATT_HD) + cpair);
-    }
-    if (j >= 0 && j < ATT_T) d = __ldg(reinterpret_cast<const uint32_t*>(dOut + (static_cast<size_t>(b) * ATT_TP + j) * ldo + h * ATT_HD) + cpair);
-    reinterpret_cast<uint32_t*>(sq + lr * ALB_LD)[cpair] = q;
-    reinterpret_cast<uint32_t*>(sk + lr * ALB_LD)[cpair] = k;
-    reinterpret_cast<uint32_t*>(sv + lr * ALB_LD)[cpair] = v;
-    reinterpret_cast<uint32_t*>(sd + lr * ALB_LD)[cpair] = d;
-  }
-  __syncthreads();
-
-  // ---- phase 1: per (window, row): softmax row and dS row
-  for (int wr = threadIdx.x; wr < ALB_WIN * 16; wr += ALB_THREADS) {
-    const int lw = wr >> 4, r = wr & 15;
-    const int w = w0 + lw;
-    if (w < 0 || w > 30) continue;       // phase 2 never reads windows that do not exist
-    const int j = 8 * w + r;
-    const int lr = 8 * lw + r;
-    const bool has_a = j >= 8, has_b = j < 248;
-    const float wn = (j < ATT_T) ? ((has_a && has_b) ? 0.5f : 1.0f) : 0.f;   // rows >= 250 are dropped by the scatter
-    float s[16], dp[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { s[k] = 0.f; dp[k] = 0.f; }
-    const __nv_bfloat162* qr = reinterpret_cast<const __nv_bfloat162*>(sq + lr * ALB_LD);
-    const __nv_bfloat162* dr = reinterpret_cast<const __nv_bfloat162*>(sd + lr * ALB_LD);
-#pragma unroll 4
-    for (int c = 0; c < 32; ++c) {
-      const float2 qv = __bfloat1622float2(qr[c]), dv = __bfloat1622float2(dr[c]);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float2 kv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sk + (8 * lw + k) * ALB_LD)[c]);
-        const float2 vv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sv + (8 * lw + k) * ALB_LD)[c]);
-        s[k] = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, s[k]));
-        dp[k] = fmaf(dv.x, vv.x, fmaf(dv.y, vv.y, dp[k]));
-      }
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) mx = fmaxf(mx, s[k]);
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { s[k] = __expf((s[k] - mx) * 0.125f); sum += s[k]; }
-    const float inv = wn / sum;
-    // dropout of this window's attention weights (forward: attn_local_tc_kernel): mask the weights used for dV and dP
-    float mk[16];
-    {
-      const uint32_t dthresh = drop ? drop->thresh : 0u;
-      const float dinv = drop ? drop->inv_keep : 1.f;
-      const uint32_t dkey = drop ? drop_key(drop->seed, drop_site) : 0u;
-      const uint32_t i0 = (((static_cast<uint32_t>(b) * ATT_HEADS + h) * 31u + static_cast<uint32_t>(w)) * 16u + static_cast<uint32_t>(r)) * 16u;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) mk[k] = (dthresh != 0u) ? drop_mul(dkey, i0 + k, dthresh, dinv) : 1.f;
-    }
-    float dot = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { s[k] *= inv; dp[k] *= mk[k]; dot = fmaf(s[k], dp[k], dot); }   // s = wn * p, dp masked
-    // d logit_k = wn p_k (dp_k - sum_k' p_k' dp_k') / 8, and dot = wn * sum p dp  ->  s_k (dp_k - dot / wn) / 8
-    const float mean = (wn > 0.f) ? dot / wn : 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      sP[wr * 16 + k] = s[k] * mk[k];
-      sS[wr * 16 + k] = s[k] * (dp[k] - mean) * 0.125f;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: gather per output row; a warp owns a row, a lane owns a pair of head dims
-  for (int lr = 8 + warp; lr < 136; lr += ALB_THREADS / 32) {
-    const int j = j0 + lr;
-    const int tok = j - 3;
-    const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
-    if (tok < 0 || tok >= ATT_T) continue;   // pad tokens carry no gradient
-    float2 aq = make_float2(0.f, 0.f), ak = aq, av = aq;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int w = (j >> 3) - 1 + t;      // the two windows that contain padded row j
-      if (w < 0 || w > 30) continue;
-      const int lw = w - w0;
-      const int r = j - 8 * w;             // row (as a query) / column (as a key) inside the window
-#pragma unroll 4
-      for (int k = 0; k < 16; ++k) {
-        const int o = 8 * lw + k;          // local row of the other token
-        const float ds_qk = sS[(lw * 16 + r) * 16 + k];     // query j, key o
-        const float ds_kq = sS[(lw * 16 + k) * 16 + r];     // query o, key j
-        const float p_kq = sP[(lw * 16 + k) * 16 + r];
-        const float2 kk = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sk + o * ALB_LD)[lane]);
-        const float2 qq = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sq + o * ALB_LD)[lane]);
-        const float2 dd = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sd + o * ALB_LD)[lane]);
-        aq.x = fmaf(ds_qk, kk.x, aq.x); aq.y = fmaf(ds_qk, kk.y, aq.y);
-        ak.x = fmaf(ds_kq, qq.x, ak.x); ak.y = fmaf(ds_kq, qq.y, ak.y);
-        av.x = fmaf(p_kq, dd.x, av.x); av.y = fmaf(p_kq, dd.y, av.y);
-      }
-    }
-    // inverse RoPE at the token's absolute position (the forward rotated q / k with it, see attention.cuh)
-    const float c = __ldg(rope_cos + tok * 32 + lane), s = __ldg(rope_sin + tok * 32 + lane);
-    const float2 rq = make_float2(aq.x * c + aq.y * s, -aq.x * s + aq.y * c);
-    const float2 rk = make_float2(ak.x * c + ak.y * s, -ak.x * s + ak.y * c);
-    reinterpret_cast<uint32_t*>(dQ + g * lddq + h * ATT_HD)[lane] = pack_bf16x2_att(rq.x, rq.y);
-    reinterpret_cast<uint32_t*>(dKV + g * lddkv + h * ATT_HD)[lane] = pack_bf16x2_att(rk.x, rk.y);
-    reinterpret_cast<uint32_t*>(dKV + g * lddkv + v_col0 + h * ATT_HD)[lane] = pack_bf16x2_att(av.x, av.y);
-  }
-  // rows 250..255 of the gradient buffers are zero rows (they feed the padded dgrad / wgrad GEMMs)
-  if (mt == 1) {
-    for (int idx = threadIdx.x; idx < (ATT_TP - ATT_T) * 32; idx += ALB_THREADS) {
-      const int tok = ATT_T + (idx >> 5), cpair = idx & 31;
-      const size_t g = static_cast<size_t>(b) * ATT_TP + tok;
-      reinterpret_cast<uint32_t*>(dQ + g * lddq + h * ATT_HD)[cpair] = 0u;
-      reinterpret_cast<uint32_t*>(dKV + g * lddkv + h * ATT_HD)[cpair] = 0u;
-      reinterpret_cast<uint32_t*>(dKV + g * lddkv + v_col0 + h * ATT_HD)[cpair] = 0u;
-    }
-  }
-}
-
 
 // ------------------------------------------------------------------------------------------ local (tensor cores)
 // LocalSelfAttention backward on tcgen05, one CTA per (window b, head h), built from attn_global_bwd_kernel's pieces.

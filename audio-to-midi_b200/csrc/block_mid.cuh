@@ -6,6 +6,9 @@
 // only do what is per-token and narrow -- depthwise k7 + LayerNorm, one thread per token out of a coalesced, padded
 // shared-memory tile -- and hand bf16 rows to two tiny UMMAs (128 x 2C x C and 128 x C x 2C; K and N zero-padded to 16):
 //
+// (block_mid2_kernel below; Xin / Xout carry no __restrict__ / __ldg: read-only loads of activations may be hoisted above
+// griddepcontrol.wait.  wimg: bf16 image of W1 then gamma*W2 exactly as the tiles sit in shared memory, a2m_api.cu pack_weights.)
+//
 //   1  cooperative coalesced load of tokens tile0-3 .. tile0+130 (fp32) into shared memory
 //   2  thread t: dwconv7 + LN of token tile0+t -> bf16 row t of the A operand (128B-swizzled K-major tile)
 //   3  tcgen05.mma  D1[128 x 2C] = A . W1^T                       (one elected thread; operands pre-swizzled on the host)
@@ -43,205 +46,9 @@ struct MidBlockCfg {
   static constexpr size_t SMEM = 1024 + A_BYTES + ((W1_BYTES + W2_BYTES + 1023) / 1024) * 1024 + X_BYTES + P_TOTAL * 4 + 64 + STAT_BYTES;
 };
 
-// Xin / Xout carry no __restrict__ / __ldg: read-only loads of activations may be hoisted above griddepcontrol.wait.
-// wimg: bf16 image of W1 then gamma*W2 exactly as the tiles sit in shared memory (a2m_api.cu pack_weights).
-template <int C>
-__global__ void __launch_bounds__(BM_TOK, MidBlockCfg<C>::MIN_CTAS)
-block_mid_kernel(const float* Xin, float* Xout, int L, int M, const float* __restrict__ params,
-                 const uint4* __restrict__ wimg) {
-  using Cfg = MidBlockCfg<C>;
-  constexpr int V = C / 4;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                  // A1, then A2
-  uint8_t* sW1 = sA + Cfg::A_BYTES;
-  uint8_t* sW2 = sW1 + Cfg::W1_BYTES;
-  float* sx = reinterpret_cast<float*>(sA + Cfg::A_BYTES + ((Cfg::W1_BYTES + Cfg::W2_BYTES + 1023) / 1024) * 1024);
-  float* sp = sx + (BM_TOK + 6) * Cfg::RS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sp + Cfg::P_TOTAL);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int tile0 = blockIdx.x * BM_TOK;
-
-  pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  copy_const_to_smem<Cfg::P_TOTAL / 4, BM_TOK>(sp, params, threadIdx.x);
-  copy_const_to_smem<(Cfg::W1_BYTES + Cfg::W2_BYTES) / 16, BM_TOK>(sW1, wimg, threadIdx.x);
-  pdl_wait();  // parameters are constants; activations of the previous kernel are read below
-  // rows tile0-3 .. tile0+BM_TOK+2, zero outside [0, M): every load of a thread is issued before its first store
-  {
-    constexpr int NV = (BM_TOK + 6) * V;
-    constexpr int PER = (NV + BM_TOK - 1) / BM_TOK;
-    float4 v[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = threadIdx.x + k * BM_TOK;
-      const int r = i / V, q = i - r * V;
-      const int g = tile0 - 3 + r;
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < NV && g >= 0 && g < M) v[k] = reinterpret_cast<const float4*>(Xin + static_cast<size_t>(g) * C)[q];   // plain load: never hoisted above pdl_wait
-    }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = threadIdx.x + k * BM_TOK;
-      const int r = i / V, q = i - r * V;
-      if (i < NV) reinterpret_cast<float4*>(sx + r * Cfg::RS)[q] = v[k];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d1 = *tmem_slot;          // columns 0 .. N1-1
-  const uint32_t tmem_d2 = tmem_d1;             // columns 0 .. N2-1, after D1 has been drained
-
-  const int row = threadIdx.x;
-  const int tok = tile0 + row;
-  const uint32_t t_row = static_cast<uint32_t>(warp * 32) << 16;
-
-  // ---- 2: depthwise k7 (zero "SAME" padding at the WINDOW boundary) + LayerNorm -> A1 row
-  {
-    const int l = tok % L;
-    float y[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) y[c] = sp[Cfg::P_DWB + c];
-#pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      const int ll = l + t - 3;
-      if (ll >= 0 && ll < L) {
-        const float* xr = sx + (row + t) * Cfg::RS;
-#pragma unroll
-        for (int q = 0; q < V; ++q) {
-          const float4 xv = reinterpret_cast<const float4*>(xr)[q];
-          const float4 wv = reinterpret_cast<const float4*>(sp + t * C)[q];
-          y[4 * q] = fmaf(wv.x, xv.x, y[4 * q]);
-          y[4 * q + 1] = fmaf(wv.y, xv.y, y[4 * q + 1]);
-          y[4 * q + 2] = fmaf(wv.z, xv.z, y[4 * q + 2]);
-          y[4 * q + 3] = fmaf(wv.w, xv.w, y[4 * q + 3]);
-        }
-      }
-    }
-    float mean = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) mean += y[c];
-    mean *= (1.0f / C);
-    float var = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) var += (y[c] - mean) * (y[c] - mean);
-    const float inv = rsqrtf(var * (1.0f / C) + kLnEps);
-    const bool live = tok < M;
-#pragma unroll
-    for (int c = 0; c < C; ++c) y[c] = live ? (y[c] - mean) * inv * sp[Cfg::P_LNW + c] + sp[Cfg::P_LNB + c] : 0.f;
-#pragma unroll
-    for (int q = 0; q < Cfg::K1 / 8; ++q) {
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (8 * q < C) {
-        o.x = pack_bf16x2(y[8 * q], y[8 * q + 1]);
-        o.y = pack_bf16x2(y[8 * q + 2], y[8 * q + 3]);
-        o.z = pack_bf16x2(y[8 * q + 4], y[8 * q + 5]);
-        o.w = pack_bf16x2(y[8 * q + 6], y[8 * q + 7]);
-      }
-      *reinterpret_cast<uint4*>(sA + sw128_offset(row, 8 * q)) = o;
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-
-  // ---- 3: D1 = A1 . W1^T
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    constexpr uint32_t idesc1 = umma_idesc_bf16(128, Cfg::N1);
-    const uint64_t da = umma_desc_sw128(smem_u32(sA));
-    const uint64_t db = umma_desc_sw128(smem_u32(sW1));
-#pragma unroll
-    for (int k = 0; k < Cfg::K1 / 16; ++k)
-      umma_bf16(tmem_d1, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc1, k != 0 ? 1u : 0u);
-    umma_commit(&bars[0]);
-  }
-  __syncwarp();
-  mbar_wait(&bars[0], 0);
-  tc_fence_after();
-
-  // ---- 4: bias + GELU -> A2 row (the MMAs above have finished reading A1)
-#pragma unroll
-  for (int c0 = 0; c0 < Cfg::N1; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld_x16(tmem_d1 + t_row + c0, r);
-    tmem_ld_wait();
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      pk[j] = pack_bf16x2(gelu_tanh_fast(__uint_as_float(r[2 * j]) + sp[Cfg::P_B1 + c0 + 2 * j]),
-                          gelu_tanh_fast(__uint_as_float(r[2 * j + 1]) + sp[Cfg::P_B1 + c0 + 2 * j + 1]));
-    *reinterpret_cast<uint4*>(sA + sw128_offset(row, c0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(sA + sw128_offset(row, c0 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-
-  // ---- 5: D2 = A2 . (gamma W2)^T
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    constexpr uint32_t idesc2 = umma_idesc_bf16(128, Cfg::N2);
-    const uint64_t da = umma_desc_sw128(smem_u32(sA));
-    const uint64_t db = umma_desc_sw128(smem_u32(sW2));
-#pragma unroll
-    for (int k = 0; k < Cfg::K2 / 16; ++k)
-      umma_bf16(tmem_d2, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc2, k != 0 ? 1u : 0u);
-    umma_commit(&bars[1]);
-  }
-  __syncwarp();
-  mbar_wait(&bars[1], 0);
-  tc_fence_after();
-
-  // ---- 6: + gamma b2 + x, in place in the token tile (row + 3 is this token), then coalesced store
-  {
-    float* xr = sx + (row + 3) * Cfg::RS;
-#pragma unroll
-    for (int c0 = 0; c0 < Cfg::N2; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_x16(tmem_d2 + t_row + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (c0 + 4 * q < C) {
-          float4 v = reinterpret_cast<float4*>(xr + c0)[q];
-          v.x += __uint_as_float(r[4 * q]) + sp[Cfg::P_B2 + c0 + 4 * q];
-          v.y += __uint_as_float(r[4 * q + 1]) + sp[Cfg::P_B2 + c0 + 4 * q + 1];
-          v.z += __uint_as_float(r[4 * q + 2]) + sp[Cfg::P_B2 + c0 + 4 * q + 2];
-          v.w += __uint_as_float(r[4 * q + 3]) + sp[Cfg::P_B2 + c0 + 4 * q + 3];
-          reinterpret_cast<float4*>(xr + c0)[q] = v;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  for (int i = threadIdx.x; i < BM_TOK * V; i += BM_TOK) {
-    const int r = i / V, q = i - r * V;
-    const int g = tile0 + r;
-    if (g < M) reinterpret_cast<float4*>(Xout + static_cast<size_t>(g) * C)[q] = reinterpret_cast<const float4*>(sx + (r + 3) * Cfg::RS)[q];
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(*tmem_slot);
-  }
-}
-
-}  // namespace a2m
-
-namespace a2m {
-
 // ------------------------------------------------------------------------------------------ two threads per token
-// block_mid_kernel with 256 threads: thread t and thread t + 128 share token t & 127 (TMEM lane = t & 127 for both: warps
+// 256 threads per 128-token tile (round 1's first version had one thread per token): thread t and thread t + 128 share token
+// t & 127 (TMEM lane = t & 127 for both: warps
 // w and w + 4 address the same TMEM quadrant) and split its channels / hidden units / output columns in halves, so every
 // per-token chain (depthwise taps, LayerNorm, GELU, epilogue) is half as long and twice as many warps are resident for
 // the same shared memory.  LayerNorm statistics: single pass (sum and sum of squares) exchanged once through shared memory.

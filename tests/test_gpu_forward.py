@@ -139,9 +139,7 @@ def test_fused_and_unfused_paths_agree(tmp_path):
         "_, pr = model.predict(None, torch.tensor(audio).cuda(), A.precompute_frequencies(64, 300))\n"
         "np.save(sys.argv[1], pr.cpu().numpy())\n")
     outs = {}
-    settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_POST": "0", "A2M_FUSE_FFN": "0", "A2M_MID_TC": "0",
-                                           "A2M_FUSE_B256": "0", "A2M_FUSE_SMALL": "0"},
-                "ffn_only": {"A2M_FUSE_POST": "0"},
+    settings = {"default": {}, "unfused": {"A2M_FUSE_QKV": "0", "A2M_FUSE_FFN": "0", "A2M_FUSE_B256": "0", "A2M_FUSE_SMALL": "0"},
                 "no_graph_no_pdl": {"A2M_GRAPH": "0", "A2M_PDL": "0"}}
     for name, env in settings.items():
         out = tmp_path / f"{name}.npy"
@@ -150,9 +148,8 @@ def test_fused_and_unfused_paths_agree(tmp_path):
         assert res.returncode == 0, res.stderr[-2000:]
         outs[name] = np.load(out)
     assert np.array_equal(outs["default"], outs["no_graph_no_pdl"])       # same kernels, different launch mechanism
-    for name in ("unfused", "ffn_only"):
-        d = np.abs(outs[name] - outs["default"]).max()
-        assert 0 < d < 2e-2, (name, d)
+    d = np.abs(outs["unfused"] - outs["default"]).max()       # LN / GEMM / GLU launch by launch instead of the fused kernels
+    assert 0 < d < 2e-2, d
 
 
 def test_batch_invariance_bitwise():
