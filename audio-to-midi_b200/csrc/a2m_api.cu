@@ -315,6 +315,8 @@ struct A2mHandle {
   TrainState* train = nullptr;   // training path (a2m_train.inc)
   bool train_configured = false; // dynamic-smem opt-in of the training kernels done on this handle's device
   void* clip_stats = nullptr;    // device ClipStats of a2m_prepare_windows
+  uint8_t* evflags_dev = nullptr; // a2m_extract_events_dev: one flag byte per (frame, key)
+  size_t evflags_cap = 0;
   long long* row0_dev = nullptr; // a2m_stitch_probs_dev: first stitched row of every window
   size_t row0_cap = 0;
   float* em_pred = nullptr;      // a2m_event_metrics: rasterised predictions when the caller does not want them
@@ -1446,6 +1448,7 @@ void a2m_destroy(A2mHandle* h) {
   if (h->clip_stats) cudaFree(h->clip_stats);
   if (h->em_pred) cudaFree(h->em_pred);
   if (h->row0_dev) cudaFree(h->row0_dev);
+  if (h->evflags_dev) cudaFree(h->evflags_dev);
   train_free(h);
   comm_free(h);
   delete h;
@@ -1696,6 +1699,7 @@ int a2m_event_metrics(A2mHandle* h, const float* probs_dev, const float* expecte
     if (h->em_pred_elems < elems) {
       if (h->em_pred) cudaFree(h->em_pred);
   if (h->row0_dev) cudaFree(h->row0_dev);
+  if (h->evflags_dev) cudaFree(h->evflags_dev);
       h->em_pred = nullptr;
       h->em_pred_elems = 0;
       CUDA_TRY(cudaMalloc(&h->em_pred, elems * 4));
@@ -1738,6 +1742,7 @@ int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windo
   }
   if (h->row0_cap < static_cast<size_t>(windows)) {
     if (h->row0_dev) cudaFree(h->row0_dev);
+  if (h->evflags_dev) cudaFree(h->evflags_dev);
     h->row0_dev = nullptr;
     h->row0_cap = 0;
     CUDA_TRY(cudaMalloc(&h->row0_dev, sizeof(long long) * static_cast<size_t>(windows)));
@@ -1758,13 +1763,26 @@ int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windo
 int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint32_t* events_dev, int32_t* counts_dev,
                            int32_t cap, void* stream_v) {
   if (!h) return A2M_EINVAL;
-  if (!probs_dev || !events_dev || !counts_dev || frames <= 0 || frames > 0x7fffffff || notes <= 0 || notes > EX_THREADS || cap <= 0) {
+  if (!probs_dev || !events_dev || !counts_dev || frames <= 0 || frames > 0x7fffffff || notes <= 0 || notes > EX_KEYS || cap <= 0) {
     h->err = "bad extract_events_dev arguments";
     return A2M_EINVAL;
   }
   CUDA_TRY(cudaSetDevice(h->device));
-  extract_events_kernel<<<1, EX_THREADS, 0, static_cast<cudaStream_t>(stream_v)>>>(probs_dev, static_cast<int>(frames), static_cast<int>(notes),
-                                                                                    reinterpret_cast<uint2*>(events_dev), counts_dev, cap);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const size_t need = static_cast<size_t>(frames) * static_cast<size_t>(notes) + 16;
+  if (h->evflags_cap < need) {
+    if (h->evflags_dev) cudaFree(h->evflags_dev);
+    h->evflags_dev = nullptr;
+    h->evflags_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->evflags_dev, need));
+    h->evflags_cap = need;
+  }
+  const long long total = static_cast<long long>(frames) * notes;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16ll));
+  event_flags_kernel<<<grid, 256, 0, stream>>>(probs_dev, static_cast<int>(frames), static_cast<int>(notes), h->evflags_dev);
+  CUDA_TRY(cudaGetLastError());
+  extract_events_kernel<<<1, EX_THREADS, 0, stream>>>(h->evflags_dev, static_cast<int>(frames), static_cast<int>(notes),
+                                                      reinterpret_cast<uint2*>(events_dev), counts_dev, cap);
   CUDA_TRY(cudaGetLastError());
   return A2M_OK;
 }

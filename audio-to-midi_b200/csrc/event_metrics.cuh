@@ -138,60 +138,104 @@ __global__ void __launch_bounds__(256) stitch_probs_kernel(const float* __restri
   }
 }
 
-constexpr int EX_TILE = 64;      // frames per shared-memory tile
-constexpr int EX_HALO = 6;       // the re-attack test looks 6 frames back and 6 ahead (common.rs:93-112)
-constexpr int EX_THREADS = 96;
+// ---- extract_events in two passes -----------------------------------------------------------------------------------------
+// Every comparison the state machine makes is a pure function of the probabilities around a frame, not of the machine's state
+// (common.rs:81-119): p < 0.1, p > 0.5, p > 0.4, p[f] < p[f+1], and the re-attack rise mean(p[f..f+6)) - mean(p[f-6..f)) > 0.1
+// (both sums divided by six, sequential f32 adds starting from 0, as the reference forms them).  Pass 1 evaluates them for all
+// F x notes elements in parallel into one flag byte each; pass 2, one thread per key, walks its key's bytes -- the only sequential
+// part -- with a handful of integer instructions per frame.  (A first version evaluated the comparisons inside the sequential walk:
+// 16 ms for a 10-minute clip, almost all of it exposed latency of three lonely warps.)
+constexpr uint32_t EVF_OFF = 1u, EVF_ON = 2u, EVF_RE = 4u, EVF_DEFER = 8u, EVF_RISE = 16u;
 
-// One CTA, one thread per key (notes <= 96): the state machine of event_metrics_kernel over the F frames of a stitched track,
-// fed through shared-memory tiles of EX_TILE + 2 * EX_HALO frames (coalesced loads; the machine itself is sequential per key).
+__global__ void __launch_bounds__(256) event_flags_kernel(const float* __restrict__ probs, int F, int notes, uint8_t* __restrict__ flags) {
+  const long long total = static_cast<long long>(F) * notes;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int f = static_cast<int>(i / notes);
+    const float* p = probs + i;                       // p[k * notes] = this key, k frames later
+    const float cur = p[0];
+    uint32_t v = 0;
+    if (cur < 0.1f) v |= EVF_OFF;
+    if (cur > 0.5f) v |= EVF_ON;
+    if (cur > 0.4f) v |= EVF_RE;
+    if (f < F - 1 && cur < p[notes]) v |= EVF_DEFER;  // "handle the re-activation in the next frame where the probability is larger"
+    if (f >= 6) {
+      float before = 0.f, after = 0.f;
+      for (int k = -6; k < 0; ++k) before = __fadd_rn(before, p[static_cast<long long>(k) * notes]);
+      before = __fdiv_rn(before, 6.0f);
+      const int n = min(6, F - f);
+      for (int k = 0; k < n; ++k) after = __fadd_rn(after, p[static_cast<long long>(k) * notes]);
+      after = __fdiv_rn(after, 6.0f);
+      if (__fsub_rn(after, before) > 0.1f) v |= EVF_RISE;
+    }
+    flags[i] = static_cast<uint8_t>(v);
+  }
+}
+
+constexpr int EX_TILE = 256;     // frames per shared-memory tile of flag bytes
+constexpr int EX_KEYS = 96;      // >= notes
+constexpr int EX_THREADS = 256;
+constexpr int EX_WORDS = EX_TILE * EX_KEYS / 4;                          // tile capacity in 32-bit words
+constexpr int EX_LD = (EX_WORDS + EX_THREADS - 1) / EX_THREADS;
+
+// One CTA: threads 0 .. notes-1 each walk the flag bytes of their key; all 256 threads move the flags through a double-buffered
+// shared-memory tile (a tile is one contiguous range of the [F, notes] byte array: flat, coalesced word copies whose loads are in
+// flight while the walk runs).  `flags` must be readable up to the next multiple of 4 bytes past F * notes.
 // events[key][k] = (attack, duration) for k < counts[key] <= cap; counts may exceed cap (overflow: the caller re-runs on the host).
-__global__ void __launch_bounds__(EX_THREADS) extract_events_kernel(const float* __restrict__ probs, int F, int notes, uint2* __restrict__ events,
+__global__ void __launch_bounds__(EX_THREADS) extract_events_kernel(const uint8_t* __restrict__ flags, int F, int notes, uint2* __restrict__ events,
                                                                     int* __restrict__ counts, int cap) {
-  __shared__ float tile[EX_TILE + 2 * EX_HALO][EX_THREADS];
-  const int key = threadIdx.x;
+  __shared__ uint32_t tile[2][EX_WORDS];
+  const int tid = threadIdx.x, key = threadIdx.x;
+  const int tile_bytes = EX_TILE * notes;                                // multiple of 4: EX_TILE is
+  const int tile_words = tile_bytes / 4;
+  const long long total_words = (static_cast<long long>(F) * notes + 3) / 4;
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(flags);
+  uint32_t reg[EX_LD];
+  auto gload = [&](int f0) {
+    const long long w0 = static_cast<long long>(f0) * notes / 4;
+#pragma unroll
+    for (int k = 0; k < EX_LD; ++k) {
+      const int idx = tid + k * EX_THREADS;
+      reg[k] = (idx < tile_words && w0 + idx < total_words) ? gw[w0 + idx] : 0u;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < EX_LD; ++k) {
+      const int idx = tid + k * EX_THREADS;
+      if (idx < tile_words) tile[buf][idx] = reg[k];
+    }
+  };
   int started = -1, count = 0;
   auto emit = [&](int start, int dur) {
-    if (key < notes && count < cap) events[static_cast<size_t>(key) * cap + count] = make_uint2(static_cast<uint32_t>(start), static_cast<uint32_t>(dur));
+    if (count < cap) events[static_cast<size_t>(key) * cap + count] = make_uint2(static_cast<uint32_t>(start), static_cast<uint32_t>(dur));
     ++count;
   };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
   for (int f0 = 0; f0 < F; f0 += EX_TILE) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < (EX_TILE + 2 * EX_HALO) * notes; i += EX_THREADS) {
-      const int rr = i / notes, cc = i - rr * notes;
-      const int f = f0 - EX_HALO + rr;
-      tile[rr][cc] = (f >= 0 && f < F) ? probs[static_cast<size_t>(f) * notes + cc] : 0.f;
-    }
-    __syncthreads();
-    if (key >= notes) continue;
-    const int fend = min(f0 + EX_TILE, F);
-    for (int f = f0; f < fend; ++f) {
-      const int r = f - f0 + EX_HALO;
-      const float cur = tile[r][key];
-      if (started < 0) {
-        if (cur > 0.5f) started = f;
-        continue;
-      }
-      if (cur < 0.1f) {
-        emit(started, max(f - started, 1));
-        started = -1;
-        continue;
-      }
-      bool rising = false;
-      if (static_cast<float>(f) - static_cast<float>(started) > 5.0f) {      // f - 6 >= started >= 0, so the look-back is in range
-        float before = 0.f, after = 0.f;
-        for (int i = -6; i < 0; ++i) before = __fadd_rn(before, tile[r + i][key]);
-        before = __fdiv_rn(before, 6.0f);
-        const int n = min(6, F - f);
-        for (int i = 0; i < n; ++i) after = __fadd_rn(after, tile[r + i][key]);
-        after = __fdiv_rn(after, 6.0f);
-        rising = __fsub_rn(after, before) > 0.1f;
-      }
-      if (f < F - 1 && cur < tile[r + 1][key]) continue;
-      if (cur > 0.4f && rising) {
-        emit(started, max(f - 1 - started, 1));
-        started = f;
+    const bool more = f0 + EX_TILE < F;
+    if (more) gload(f0 + EX_TILE);
+    if (key < notes) {
+      const uint8_t* t = reinterpret_cast<const uint8_t*>(tile[buf]) + key;
+      const int fend = min(f0 + EX_TILE, F);
+      for (int f = f0; f < fend; ++f) {
+        const uint32_t v = t[(f - f0) * notes];
+        if (started < 0) {
+          if (v & EVF_ON) started = f;
+        } else if (v & EVF_OFF) {                                        // released (common.rs:81-84)
+          emit(started, max(f - started, 1));
+          started = -1;
+        } else if (!(v & EVF_DEFER) && (v & EVF_RE) && (v & EVF_RISE) && f - started > 5) {   // re-attack (common.rs:88-123)
+          emit(started, max(f - 1 - started, 1));
+          started = f;
+        }
       }
     }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
   }
   if (key < notes) {
     if (started >= 0) emit(started, max(F - started, 1));
