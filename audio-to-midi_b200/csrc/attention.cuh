@@ -126,9 +126,14 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t r[32];
     tmem_ld_x32(tmem_S + t_row + key0, r);
     tmem_ld_wait();
+    if (key0 + 32 <= ATT_T) {          // every chunk but the last one of the upper key half: no padded keys, no per-element test
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (key0 + j < ATT_T) mx = fmaxf(mx, __uint_as_float(r[j]));
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (key0 + j < ATT_T) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
   }
   // the two threads of a row exchange their half-row maxima (keys 0..127 always hold real keys: never -inf)
   sMax[kh * 128 + row] = mx;
@@ -143,10 +148,15 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_ld_x32(tmem_S + t_row + key0, r);
     tmem_ld_wait();
     float p[32];
+    if (key0 + 32 <= ATT_T) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float e = ex2_ftz(fmaf(__uint_as_float(r[j]), kscale, -mxk));
-      p[j] = (key0 + j < ATT_T) ? e : 0.f;  // padded keys 250..255 are masked out
+      for (int j = 0; j < 32; ++j) p[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), kscale, -mxk));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = ex2_ftz(fmaf(__uint_as_float(r[j]), kscale, -mxk));
+        p[j] = (key0 + j < ATT_T) ? e : 0.f;  // padded keys 250..255 are masked out
+      }
     }
     // P (bf16) into the K-major 128B-swizzled A-operand layout: k-block = key / 64
     uint8_t* pb = sP + (key0 >> 6) * (128 * 64 * 2);

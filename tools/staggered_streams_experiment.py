@@ -58,6 +58,47 @@ def run(S, B=64, iters=40, stagger=True):
     print(f"{S} stream(s) x {B} windows, stagger={stagger}: {ms:.3f} ms per step -> {B * 5 / ms * 1e3:.0f} audio-s/s", flush=True)
 
 
+
+
+def run_prio(prios, B=64, iters=40):
+    """ONE handle, len(prios) workspaces, streams with the given CUDA priorities (-1 = high, 0 = default)."""
+    S = len(prios)
+    e = M._Engine(0, model.precision)
+    e.load(model)
+    need = int(e.L.a2m_workspace_bytes(e.h, B, 0))
+    raw = [torch.zeros(need + 1024, dtype=torch.uint8, device="cuda") for _ in range(S)]
+    ws = [(t.data_ptr() + 1023) & ~1023 for t in raw]
+    streams = [torch.cuda.Stream(priority=p) for p in prios]
+    outs = [(torch.empty(B, 250, 90, device="cuda"), torch.empty(B, 250, 90, device="cuda")) for _ in range(S)]
+
+    def f(i):
+        k = i % S
+        x = audio[i % R][:B]
+        rc = e.L.a2m_forward(e.h, x.data_ptr(), B, cos.data_ptr(), sin.data_ptr(), cos.shape[0], outs[k][0].data_ptr(), outs[k][1].data_ptr(),
+                             C.c_void_p(ws[k]), need, C.c_void_p(streams[k].cuda_stream))
+        assert rc == 0, rc
+    for i in range(3 * S):
+        f(i)
+    torch.cuda.synchronize()
+    n = iters * S
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
+    e0.record(main)
+    for s_ in streams:
+        s_.wait_event(e0)
+    for i in range(n):
+        f(i)
+    for s_ in streams:
+        main.wait_stream(s_)
+    e1.record(main)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"priorities {prios}: {ms:.3f} ms per step -> {B * 5 / ms * 1e3:.0f} audio-s/s", flush=True)
+
+
+for pr in ([0, 0], [-1, 0], [-1, -1], [-1, 0, 0], [-2, -1, 0], [0, 0, 0, 0]):
+    run_prio(pr)
+sys.exit(0)
 run(1)
 run(2, stagger=False)
 run(2)
