@@ -314,8 +314,16 @@ def train_roofline(eng):
     total = sum(f["ms"] for f in fam.values())
     name, f = max(fam.items(), key=lambda kv: kv[1]["ms"])
     ach = f["flops"] / (f["ms"] / 1e3) / 1e12
+    traffic = None
+    try:
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_train_traffic.json")))[-1]
+        with open(tf) as fh:
+            traffic = json.load(fh).get(name)
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-            "frac": ach / peaks["tensor_sustained"], "traffic": None, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
+            "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "launches_per_step": f["n"], "kernel_ms_per_step": f["ms"],
             "share_of_serialised_step": f["ms"] / total,
             "hbm": {"achieved": f["bytes"] / (f["ms"] / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": f["bytes"] / (f["ms"] / 1e3) / 1e9 / peaks["hbm"]},
@@ -554,7 +562,7 @@ def run_ours(args):
                         "note": "algorithmic bytes of the kernel / its time; its operands are L2-resident in the steady state"}}
         try:
             import glob
-            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            tf = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")) if "train" not in os.path.basename(f))[-1]
             with open(tf) as fh:
                 roof["traffic"] = json.load(fh).get(name)
             roof["traffic_source"] = os.path.relpath(tf, ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
