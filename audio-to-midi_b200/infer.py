@@ -252,7 +252,8 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
     windows are batch-partitioned over ranks (contiguous blocks; the forward has no collective); each rank runs the batched
     forward on its block, the per-window BCE sum (a2m_window_losses) and the event metrics (a2m_event_metrics) on the device --
     nothing but [n, 6] floats ever returns to the host.  With a process group the per-rank results are gathered in rank order.
-    audio (N, 2, 80000), events (N, 250, 90), numpy.  Returns (lo, hi, losses, [detailed_event_loss dict]): the block bounds
+    audio (N, 2, 80000), events (N, 250, 90): numpy arrays (copied batch by batch), or torch CUDA tensors of a set that is already
+    resident on the device.  Returns (lo, hi, losses, [detailed_event_loss dict]): the block bounds
     of this rank, and losses / dicts of ALL windows when gathered (else of the block)."""
     import ctypes as C
     import torch
@@ -269,11 +270,23 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
     tdev = torch.device(f"cuda:{dev}")
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
     rows = []
-    for i in range(lo, hi, max_batch):
-        j = min(i + max_batch, hi)
-        x = torch.as_tensor(np.ascontiguousarray(audio[i:j], np.float32)).to(tdev)
-        y = torch.as_tensor(np.ascontiguousarray(events[i:j], np.float32)).to(tdev)
-        logits, probs = model.predict(None, x, rope_freqs)
+    on_device = hasattr(audio, "is_cuda") and audio.is_cuda
+    spans = [(i, min(i + max_batch, hi)) for i in range(lo, hi, max_batch)]
+
+    def labels_of(i, j):
+        if hasattr(events, "is_cuda"):
+            return events[i:j].to(tdev, torch.float32).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(events[i:j], np.float32)).to(tdev)
+
+    if on_device:      # the set is already resident (audio / events torch CUDA tensors): consecutive batches overlap on the two lanes
+        outs = model.predict_many(None, [audio[i:j] for i, j in spans], rope_freqs)
+    for n, (i, j) in enumerate(spans):
+        y = labels_of(i, j)
+        if on_device:
+            logits, probs = outs[n]
+        else:
+            x = torch.as_tensor(np.ascontiguousarray(audio[i:j], np.float32)).to(tdev)
+            logits, probs = model.predict(None, x, rope_freqs)
         out = torch.empty(j - i, dtype=torch.float32, device=tdev)
         stream = C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)
         _lib.check(eng.h, eng.L.a2m_window_losses(eng.h, logits.data_ptr(), y.data_ptr(), j - i, out.data_ptr(), stream), "a2m_window_losses", eng.L)
@@ -281,7 +294,8 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
             m = detailed_event_loss_device(model, probs, y)
         else:
             pr = probs.cpu().numpy()
-            m = torch.tensor([[detailed_event_loss(pr[k], events[i + k])[q] for q in _METRIC_KEYS] for k in range(j - i)],
+            ev_host = events[i:j].cpu().numpy() if hasattr(events, "is_cuda") else events[i:j]
+            m = torch.tensor([[detailed_event_loss(pr[k], ev_host[k])[q] for q in _METRIC_KEYS] for k in range(j - i)],
                              dtype=torch.float32, device=tdev)
         rows.append(torch.cat([out[:, None], m], dim=1))
     local = torch.cat(rows) if rows else torch.zeros((0, 6), dtype=torch.float32, device=tdev)

@@ -85,6 +85,8 @@ def test_validation_loss_and_hit_rate():
         for k in range(hi - lo):
             got[lo + k] = (losses[k], details[k])
     host = I.compute_testset_loss(model, audio, labels, max_batch=4, device_metrics=False)      # host eventizer, one process
+    resident = I.compute_testset_loss(model, torch.tensor(audio).cuda(), torch.tensor(labels).cuda(), max_batch=4)   # set already on the device
+    assert np.allclose(resident[2], host[2], rtol=1e-5) and len(resident[3]) == 6
     full = 0
     for k in range(6):
         assert abs(got[k][0] - lref[k]) < 5e-3 * abs(lref[k]) + 1.0, (k, got[k][0], lref[k])
