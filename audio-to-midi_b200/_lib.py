@@ -64,7 +64,12 @@ def lib(precision: str = "bf16") -> C.CDLL:
     if precision in _libs:
         return _libs[precision]
     path = LIBS[precision]
-    if not os.path.exists(path) or os.environ.get("A2M_REBUILD") == "1":
+    override = os.environ.get(f"A2M_LIB_{precision.upper()}")      # A/B experiments (tools/ab_build.sh): an alternative build of this variant
+    if override:
+        if not os.path.exists(override):
+            raise FileNotFoundError(f"A2M_LIB_{precision.upper()}={override} does not exist")
+        path = override
+    elif not os.path.exists(path) or os.environ.get("A2M_REBUILD") == "1":
         path = build(precision=precision)
     else:
         try:

@@ -1099,7 +1099,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
       if (fused_qkv) {
         // attention_norm + q|k|v projection + RoPE in one launch (qkv_fused.cuh)
         CUtensorMap tw, to;
-        if (!make_tmap(h, &tw, dev_ptr<__nv_bfloat16>(h, t.wqkv), 768, kD, kD, 64, 256)) return false;
+        if (!make_tmap(h, &tw, dev_ptr<__nv_bfloat16>(h, t.wqkv), 768, kD, kD, 64, QF_SROWS)) return false;
         if (!make_tmap_t(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, Mt, 768, 768, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
         const float* lw = dev_ptr<float>(h, t.ln1w);
         const float* lb = dev_ptr<float>(h, t.ln1b);

@@ -5,7 +5,7 @@
 //     qkv[:, 512:768] =        LN(x) (Wv Wc)^T
 // Replaces ln_rows_kernel + gemm_tc2<128, ROPE>: the normalised activations never leave shared memory.
 //
-//   warp 0      TMA producer: W [768, 256] streamed as 12 stages of [256 rows x 64 k] (32 KB) through a 2-deep ring
+//   warp 0      TMA producer: W [768, 256] streamed as 24 stages of [128 rows x 64 k] (16 KB) through a 4-deep ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer: 3 column chunks of 256, accumulators ping-pong in 2 x 256 columns
 //   warps 2-17  LayerNorm of the tile (one warp per row) -> bf16 A operand; then per chunk, in two halves of 32 columns per
 //               head: TMEM -> RoPE -> bf16 into a 64B-swizzled staging tile -> TMA store (per-thread global stores of one
@@ -21,14 +21,22 @@ namespace a2m {
 constexpr int QF_THREADS = FF_THREADS;          // 2 + 16 warps
 constexpr int QF_N = 768;
 constexpr int QF_NCHUNK = QF_N / 256;            // 3
-constexpr int QF_NST = 2;                        // the epilogue, not the weight stream, paces this kernel: two stages suffice
+// The weight stream paces the MMAs (in-kernel timeline, tools/ffn_timeline.py): 64 KB of ring is what the shared-memory budget
+// leaves, and with two 32 KB stages the MMA holds half of it while it works, so only one stage is in flight against ~1000
+// cycles of L2 latency.  Stages of 128 W rows (16 KB, UMMA N = 128 into one half of the chunk's accumulator) keep three in
+// flight: 13.9 -> 13.6 us.  (Starting the CTAs at different column chunks, so that they do not all pull the same weight rows
+// at the same moment, was measured SLOWER: simultaneous requests for the same lines are merged in L2.)
+constexpr int QF_SROWS = 128;                    // W rows per ring stage
+constexpr int QF_STAGE = QF_SROWS * 64 * 2;      // 16 KB
+constexpr int QF_NST = 64 * 1024 / QF_STAGE;     // 4
+constexpr int QF_NSUB = 256 / QF_SROWS;          // stages per (chunk, k-block)
 constexpr int QF_ROPE_BYTES = 2 * FF_ROWS * 32 * 4;               // cos then sin, 128 positions x 32 pairs (float4 index XOR row & 7)
 constexpr int QF_OUT_TILE = FF_ROWS * 64;                         // staging tile: 128 rows x 32 bf16, 64B swizzle
 constexpr int QF_OUT_BYTES = 2 * 4 * QF_OUT_TILE;                 // one tile per head of the chunk, double buffered
-constexpr int QF_MAIN_BYTES = FF_A_BYTES + QF_NST * FF_STAGE;     // 128 KB
+constexpr int QF_MAIN_BYTES = FF_A_BYTES + QF_NST * QF_STAGE;     // 128 KB
 constexpr size_t QF_SMEM = 1024 + QF_MAIN_BYTES + QF_OUT_BYTES + QF_ROPE_BYTES + 256;
 
-// tmW: Wqkv [768, 256] bf16, box {64, 256}.  tmO: out [M, 768] bf16, box {32, 128}, 64B swizzle.  X: fp32 [M, 256].
+// tmW: Wqkv [768, 256] bf16, box {64, QF_SROWS}.  tmO: out [M, 768] bf16, box {32, 128}, 64B swizzle.  X: fp32 [M, 256].
 // rope_cos / rope_sin: [>= 256, 32].
 __global__ void __launch_bounds__(QF_THREADS, 1)
 qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const float* X, int M,
@@ -97,16 +105,17 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     if (elect_one()) {
       uint32_t s = 0, ph = 0;
       for (int n = 0; n < QF_NCHUNK; ++n)
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&bar_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&bar_full[s], FF_STAGE);
-          tma_load_2d(sW + s * FF_STAGE, &tmW, &bar_full[s], kb * 64, n * 256);
-          if (++s == QF_NST) { s = 0; ph ^= 1; }
-        }
+        for (int sub = 0; sub < QF_NSUB; ++sub)
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&bar_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&bar_full[s], QF_STAGE);
+            tma_load_2d(sW + s * QF_STAGE, &tmW, &bar_full[s], kb * 64, n * 256 + sub * QF_SROWS);
+            if (++s == QF_NST) { s = 0; ph ^= 1; }
+          }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, QF_SROWS);
       uint32_t s = 0, ph = 0;
       mbar_wait(bar_a, 0);
       tc_fence_after();
@@ -115,18 +124,20 @@ qkv_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         mbar_wait(&bar_dfree[n & 1], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
         FF_STAMP(84 + n * 6);
-        const uint32_t d = tmem_base + (n & 1) * 256;
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&bar_full[s], ph);
-          tc_fence_after();
-          FF_STAMP(84 + n * 6 + 1 + kb);
-          const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * (FF_ROWS * 128)));
-          const uint64_t db = umma_desc_sw128(smem_u32(sW + s * FF_STAGE));
+        for (int sub = 0; sub < QF_NSUB; ++sub) {
+          const uint32_t d = tmem_base + (n & 1) * 256 + sub * QF_SROWS;
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&bar_full[s], ph);
+            tc_fence_after();
+            if (sub == QF_NSUB - 1) FF_STAMP(84 + n * 6 + 1 + kb);
+            const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * (FF_ROWS * 128)));
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + s * QF_STAGE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&bar_empty[s]);
-          if (++s == QF_NST) { s = 0; ph ^= 1; }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, umma_desc_advance_k(da, k * 32), umma_desc_advance_k(db, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&bar_empty[s]);
+            if (++s == QF_NST) { s = 0; ph ^= 1; }
+          }
         }
         umma_commit(&bar_dfull[n & 1]);
       }
