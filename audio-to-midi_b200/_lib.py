@@ -181,7 +181,7 @@ def lib(precision: str = "bf16") -> C.CDLL:
     L.a2m_comm_destroy.restype = C.c_int
     L.a2m_stitch_probs_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, f64, f64, vp, C.c_int64, vp]
     L.a2m_stitch_probs_dev.restype = C.c_int64
-    L.a2m_extract_events_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, i32, vp]
+    L.a2m_extract_events_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp]
     L.a2m_extract_events_dev.restype = C.c_int
     L.a2m_operand_format.argtypes = []
     L.a2m_operand_format.restype = C.c_char_p

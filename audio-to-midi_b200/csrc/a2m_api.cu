@@ -315,7 +315,7 @@ struct A2mHandle {
   TrainState* train = nullptr;   // training path (a2m_train.inc)
   bool train_configured = false; // dynamic-smem opt-in of the training kernels done on this handle's device
   void* clip_stats = nullptr;    // device ClipStats of a2m_prepare_windows
-  uint8_t* evflags_dev = nullptr; // a2m_extract_events_dev: one flag byte per (frame, key)
+  uint8_t* evflags_dev = nullptr; // a2m_extract_events_dev scratch: three bit masks per key, one bit per frame
   size_t evflags_cap = 0;
   long long* row0_dev = nullptr; // a2m_stitch_probs_dev: first stitched row of every window
   size_t row0_cap = 0;
@@ -1760,16 +1760,22 @@ int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windo
 
 // extract_events (common.rs:47-144) on the device: events_dev [notes][cap] of (attack, duration) uint32 pairs, counts_dev [notes].
 // A count above cap means that key overflowed (the caller falls back to a2m_extract_events).  Velocity is the constant 7.
-int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint32_t* events_dev, int32_t* counts_dev,
-                           int32_t cap, void* stream_v) {
+int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint64_t* events_dev, int64_t cap,
+                           int32_t* count_dev, void* stream_v) {
   if (!h) return A2M_EINVAL;
-  if (!probs_dev || !events_dev || !counts_dev || frames <= 0 || frames > 0x7fffffff || notes <= 0 || notes > EX_KEYS || cap <= 0) {
-    h->err = "bad extract_events_dev arguments";
+  if (!probs_dev || !events_dev || !count_dev || frames <= 0 || frames >= (1ll << 24) || notes <= 0 || notes > EX_KEYS || cap <= 0) {
+    h->err = "bad extract_events_dev arguments (frames must be below 2^24, notes at most 96)";
     return A2M_EINVAL;
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const size_t need = static_cast<size_t>(frames) * static_cast<size_t>(notes) + 16;
+  // scratch: three bit masks per key, one bit per frame, as 16-byte vectors of 128 frames: [mask][vector][96 keys]; then the
+  // per-key event lists of the walk
+  const int words = static_cast<int>((frames + 31) / 32);
+  const int Q = (words + 3) / 4;
+  const size_t mask_bytes = 3 * static_cast<size_t>(Q) * EX_KEYS * sizeof(uint4);
+  const long long key_cap = frames / 2 + 2;      // a key closes at most one event every second frame
+  const size_t need = mask_bytes + static_cast<size_t>(notes) * static_cast<size_t>(key_cap) * sizeof(uint64_t);
   if (h->evflags_cap < need) {
     if (h->evflags_dev) cudaFree(h->evflags_dev);
     h->evflags_dev = nullptr;
@@ -1777,12 +1783,13 @@ int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames,
     CUDA_TRY(cudaMalloc(&h->evflags_dev, need));
     h->evflags_cap = need;
   }
-  const long long total = static_cast<long long>(frames) * notes;
-  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16ll));
-  event_flags_kernel<<<grid, 256, 0, stream>>>(probs_dev, static_cast<int>(frames), static_cast<int>(notes), h->evflags_dev);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(h->evflags_dev);
+  if (4 * Q != words) CUDA_TRY(cudaMemsetAsync(masks, 0, mask_bytes, stream));    // the padding words of the last vectors
+  event_masks_kernel<<<words, EVM_THREADS, 0, stream>>>(probs_dev, static_cast<int>(frames), static_cast<int>(notes), Q, masks);
   CUDA_TRY(cudaGetLastError());
-  extract_events_kernel<<<1, EX_THREADS, 0, stream>>>(h->evflags_dev, static_cast<int>(frames), static_cast<int>(notes),
-                                                      reinterpret_cast<uint2*>(events_dev), counts_dev, cap);
+  extract_events_kernel<<<1, EX_KEYS, 0, stream>>>(reinterpret_cast<const uint4*>(masks), static_cast<int>(frames), static_cast<int>(notes), Q,
+                                                   reinterpret_cast<unsigned long long*>(h->evflags_dev + mask_bytes), key_cap,
+                                                   reinterpret_cast<unsigned long long*>(events_dev), cap, count_dev);
   CUDA_TRY(cudaGetLastError());
   return A2M_OK;
 }

@@ -142,104 +142,140 @@ __global__ void __launch_bounds__(256) stitch_probs_kernel(const float* __restri
 // Every comparison the state machine makes is a pure function of the probabilities around a frame, not of the machine's state
 // (common.rs:81-119): p < 0.1, p > 0.5, p > 0.4, p[f] < p[f+1], and the re-attack rise mean(p[f..f+6)) - mean(p[f-6..f)) > 0.1
 // (both sums divided by six, sequential f32 adds starting from 0, as the reference forms them).  Pass 1 evaluates them for all
-// F x notes elements in parallel into one flag byte each; pass 2, one thread per key, walks its key's bytes -- the only sequential
-// part -- with a handful of integer instructions per frame.  (A first version evaluated the comparisons inside the sequential walk:
-// 16 ms for a 10-minute clip, almost all of it exposed latency of three lonely warps.)
-constexpr uint32_t EVF_OFF = 1u, EVF_ON = 2u, EVF_RE = 4u, EVF_DEFER = 8u, EVF_RISE = 16u;
+// F x notes elements in parallel and leaves three BIT MASKS per key, one bit per frame:
+//     on   p > 0.5                                        (an idle key starts a note)
+//     off  p < 0.1                                        (a sounding key is released)
+//     re   p > 0.4, not p[f] < p[f+1], rise > 0.1         (a sounding key is re-attacked, if its note is older than 5 frames)
+// Pass 2, one thread per key, is the machine itself -- the only sequential part -- but it no longer visits frames: an idle key
+// jumps to the next set bit of `on`, a sounding key to the next set bit of `off | re` (find-first-set over 32 frames per word),
+// so its cost is the number of events plus F / 32 words instead of F steps.  History: the comparisons inside one sequential walk
+// per key, 16 ms for a 10-minute clip; a walk over precomputed flag bytes, 2.4 ms; 256-frame segments replayed from each key's
+// latest p < 0.1 frame were SLOWER (5.5 ms) on tracks that rarely fall below 0.1, where every segment replays from frame 0.
+constexpr int EX_KEYS = 96;                 // >= notes
+constexpr int EVM_THREADS = 256;
+constexpr uint32_t EVF_OFF = 1u, EVF_ON = 2u, EVF_RE = 4u;
 
-__global__ void __launch_bounds__(256) event_flags_kernel(const float* __restrict__ probs, int F, int notes, uint8_t* __restrict__ flags) {
-  const long long total = static_cast<long long>(F) * notes;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
-    const int f = static_cast<int>(i / notes);
-    const float* p = probs + i;                       // p[k * notes] = this key, k frames later
-    const float cur = p[0];
+// grid = ceil(F / 32) CTAs; CTA w owns frames 32 w .. 32 w + 31 of every key and writes word w of the three masks of every key:
+// word (w & 3) of the 16-byte vector  masks4[(m * Q + (w >> 2)) * EX_KEYS + key],  m = 0 (on), 1 (off), 2 (re),  Q = ceil(F / 128):
+// a vector holds 128 frames of one key, and the vectors of the keys are adjacent, so that the warp of pass 2 reads 512
+// contiguous bytes per mask and step.  (The words past ceil(F / 32) are zeroed by the caller.)  Frames >= F contribute zero bits.
+__global__ void __launch_bounds__(EVM_THREADS) event_masks_kernel(const float* __restrict__ probs, int F, int notes, int Q,
+                                                                  uint32_t* __restrict__ masks) {
+  __shared__ uint8_t tile[32][EX_KEYS + 4];
+  const int w = blockIdx.x, f0 = w * 32;
+  for (int i = threadIdx.x; i < 32 * notes; i += EVM_THREADS) {     // coalesced over the row-major [frame][key] array
+    const int fr = i / notes, key = i - fr * notes, f = f0 + fr;
     uint32_t v = 0;
-    if (cur < 0.1f) v |= EVF_OFF;
-    if (cur > 0.5f) v |= EVF_ON;
-    if (cur > 0.4f) v |= EVF_RE;
-    if (f < F - 1 && cur < p[notes]) v |= EVF_DEFER;  // "handle the re-activation in the next frame where the probability is larger"
-    if (f >= 6) {
-      float before = 0.f, after = 0.f;
-      for (int k = -6; k < 0; ++k) before = __fadd_rn(before, p[static_cast<long long>(k) * notes]);
-      before = __fdiv_rn(before, 6.0f);
-      const int n = min(6, F - f);
-      for (int k = 0; k < n; ++k) after = __fadd_rn(after, p[static_cast<long long>(k) * notes]);
-      after = __fdiv_rn(after, 6.0f);
-      if (__fsub_rn(after, before) > 0.1f) v |= EVF_RISE;
+    if (f < F) {
+      const float* p = probs + static_cast<long long>(f) * notes + key;    // p[k * notes] = this key, k frames later
+      const float cur = p[0];
+      if (cur < 0.1f) v |= EVF_OFF;
+      if (cur > 0.5f) v |= EVF_ON;
+      const bool defer = f < F - 1 && cur < p[notes];     // "handle the re-activation in the next frame where the probability is larger"
+      if (cur > 0.4f && !defer && f >= 6) {
+        float before = 0.f, after = 0.f;
+        for (int k = -6; k < 0; ++k) before = __fadd_rn(before, p[static_cast<long long>(k) * notes]);
+        before = __fdiv_rn(before, 6.0f);
+        const int n = min(6, F - f);
+        for (int k = 0; k < n; ++k) after = __fadd_rn(after, p[static_cast<long long>(k) * notes]);
+        after = __fdiv_rn(after, 6.0f);
+        if (__fsub_rn(after, before) > 0.1f) v |= EVF_RE;
+      }
     }
-    flags[i] = static_cast<uint8_t>(v);
+    tile[fr][key] = static_cast<uint8_t>(v);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int key = warp; key < notes; key += EVM_THREADS / 32) {      // lane = frame inside the word
+    const uint32_t v = tile[lane][key];
+    const uint32_t on = __ballot_sync(0xffffffffu, v & EVF_ON), off = __ballot_sync(0xffffffffu, v & EVF_OFF),
+                   re = __ballot_sync(0xffffffffu, v & EVF_RE);
+    if (lane < 3) masks[((static_cast<size_t>(lane) * Q + (w >> 2)) * EX_KEYS + key) * 4 + (w & 3)] = lane == 0 ? on : (lane == 1 ? off : re);
   }
 }
 
-constexpr int EX_TILE = 256;     // frames per shared-memory tile of flag bytes
-constexpr int EX_KEYS = 96;      // >= notes
-constexpr int EX_THREADS = 256;
-constexpr int EX_WORDS = EX_TILE * EX_KEYS / 4;                          // tile capacity in 32-bit words
-constexpr int EX_LD = (EX_WORDS + EX_THREADS - 1) / EX_THREADS;
-
-// One CTA: threads 0 .. notes-1 each walk the flag bytes of their key; all 256 threads move the flags through a double-buffered
-// shared-memory tile (a tile is one contiguous range of the [F, notes] byte array: flat, coalesced word copies whose loads are in
-// flight while the walk runs).  `flags` must be readable up to the next multiple of 4 bytes past F * notes.
-// events[key][k] = (attack, duration) for k < counts[key] <= cap; counts may exceed cap (overflow: the caller re-runs on the host).
-__global__ void __launch_bounds__(EX_THREADS) extract_events_kernel(const uint8_t* __restrict__ flags, int F, int notes, uint2* __restrict__ events,
-                                                                    int* __restrict__ counts, int cap) {
-  __shared__ uint32_t tile[2][EX_WORDS];
-  const int tid = threadIdx.x, key = threadIdx.x;
-  const int tile_bytes = EX_TILE * notes;                                // multiple of 4: EX_TILE is
-  const int tile_words = tile_bytes / 4;
-  const long long total_words = (static_cast<long long>(F) * notes + 3) / 4;
-  const uint32_t* gw = reinterpret_cast<const uint32_t*>(flags);
-  uint32_t reg[EX_LD];
-  auto gload = [&](int f0) {
-    const long long w0 = static_cast<long long>(f0) * notes / 4;
-#pragma unroll
-    for (int k = 0; k < EX_LD; ++k) {
-      const int idx = tid + k * EX_THREADS;
-      reg[k] = (idx < tile_words && w0 + idx < total_words) ? gw[w0 + idx] : 0u;
-    }
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int k = 0; k < EX_LD; ++k) {
-      const int idx = tid + k * EX_THREADS;
-      if (idx < tile_words) tile[buf][idx] = reg[k];
-    }
-  };
-  int started = -1, count = 0;
+// One CTA, thread = key.  Each thread appends its key's events to its own list, staging[key * key_cap + i] (key_cap >= F / 2 + 2:
+// a key closes at most one event every second frame); after a prefix sum over the keys the CTA copies the lists, one after the
+// other and coalesced, to events[] as sortable 64-bit words  attack << 32 | key << 24 | duration  (frames < 2^24, checked by
+// the caller), so that the host's ascending sort of the words IS the reference's (attack, key, duration) order (common.rs:142).
+// *total = number of events; words beyond cap are dropped (the caller calls again with a larger buffer).
+// The loop runs over the 128-frame vectors, the same one for every key, so the loads are coalesced, independent of the machine's
+// state and fetched one vector ahead; only the frames a key reacts to inside a vector cost a (divergent) inner trip of ~25
+// instructions on two 64-bit words.  Measured on a 10-minute clip whose keys hover around the thresholds (13 780 events): a scan
+// loop nested inside a per-key event loop 1.2 ms (every outer trip lasted as long as the longest quiet stretch among the warp's
+// 32 keys, each step a dependent L2 round trip).
+__global__ void __launch_bounds__(EX_KEYS) extract_events_kernel(const uint4* __restrict__ masks4, int F, int notes, int Q,
+                                                                 unsigned long long* __restrict__ staging, long long key_cap,
+                                                                 unsigned long long* __restrict__ events, long long cap,
+                                                                 int* __restrict__ total) {
+  __shared__ int cnts[EX_KEYS];
+  __shared__ long long offs[EX_KEYS + 1];
+  const int key = threadIdx.x;
+  const bool live = key < notes;
+  const uint4* m_on = masks4 + key;
+  const uint4* m_off = m_on + static_cast<size_t>(Q) * EX_KEYS;
+  const uint4* m_re = m_off + static_cast<size_t>(Q) * EX_KEYS;
+  unsigned long long* mine = staging + static_cast<size_t>(key) * key_cap;
+  int count = 0;
   auto emit = [&](int start, int dur) {
-    if (count < cap) events[static_cast<size_t>(key) * cap + count] = make_uint2(static_cast<uint32_t>(start), static_cast<uint32_t>(dur));
+    if (count < key_cap)
+      mine[count] = (static_cast<unsigned long long>(start) << 32) | (static_cast<unsigned long long>(key) << 24) |
+                    static_cast<unsigned long long>(dur);
     ++count;
   };
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  int buf = 0;
-  for (int f0 = 0; f0 < F; f0 += EX_TILE) {
-    const bool more = f0 + EX_TILE < F;
-    if (more) gload(f0 + EX_TILE);
-    if (key < notes) {
-      const uint8_t* t = reinterpret_cast<const uint8_t*>(tile[buf]) + key;
-      const int fend = min(f0 + EX_TILE, F);
-      for (int f = f0; f < fend; ++f) {
-        const uint32_t v = t[(f - f0) * notes];
-        if (started < 0) {
-          if (v & EVF_ON) started = f;
-        } else if (v & EVF_OFF) {                                        // released (common.rs:81-84)
-          emit(started, max(f - started, 1));
-          started = -1;
-        } else if (!(v & EVF_DEFER) && (v & EVF_RE) && (v & EVF_RISE) && f - started > 5) {   // re-attack (common.rs:88-123)
-          emit(started, max(f - 1 - started, 1));
-          started = f;
-        }
+  auto u64 = [](uint32_t lo, uint32_t hi) { return static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32); };
+  int started = -1;
+  uint4 non = m_on[0], noff = m_off[0], nre = m_re[0];
+  for (int q = 0; q < Q; ++q) {
+    const uint4 von = non, voff = noff, vre = nre;
+    if (q + 1 < Q) {
+      const size_t o = static_cast<size_t>(q + 1) * EX_KEYS;
+      non = m_on[o]; noff = m_off[o]; nre = m_re[o];
+    }
+    if (!live) continue;
+    const unsigned long long on0 = u64(von.x, von.y), on1 = u64(von.z, von.w), off0 = u64(voff.x, voff.y), off1 = u64(voff.z, voff.w);
+    const unsigned long long sr0 = off0 | u64(vre.x, vre.y), sr1 = off1 | u64(vre.z, vre.w);   // what a sounding key reacts to
+    const int base = q << 7;
+    unsigned long long keep0 = ~0ull, keep1 = ~0ull;        // frames of this vector the machine has not passed yet
+    while (true) {
+      const unsigned long long c0 = (started < 0 ? on0 : sr0) & keep0, c1 = (started < 0 ? on1 : sr1) & keep1;
+      if ((c0 | c1) == 0ull) break;                         // nothing more in this vector (bits of frames >= F are never set)
+      const int bit = c0 ? __ffsll(static_cast<long long>(c0)) - 1 : 64 + __ffsll(static_cast<long long>(c1)) - 1;
+      const int g = base + bit;
+      const bool is_off = (((bit < 64 ? off0 : off1) >> (bit & 63)) & 1ull) != 0ull;
+      if (started < 0) {
+        started = g;                                                             // p > 0.5: the note starts
+      } else if (is_off) {                                                       // released (common.rs:81-84); tested first, as the reference does
+        emit(started, max(g - started, 1));
+        started = -1;
+      } else if (g - started > 5) {                                              // re-attack (common.rs:88-123)
+        emit(started, max(g - 1 - started, 1));
+        started = g;
+      }
+      // the machine moves on to frame g + 1
+      if (bit < 64) {
+        keep0 = bit == 63 ? 0ull : (~0ull << (bit + 1));
+      } else {
+        keep0 = 0ull;
+        keep1 = bit == 127 ? 0ull : (~0ull << (bit - 63));
       }
     }
-    if (more) sstore(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
   }
-  if (key < notes) {
-    if (started >= 0) emit(started, max(F - started, 1));
-    counts[key] = count;
+  if (live && started >= 0) emit(started, max(F - started, 1));                  // still sounding at the end of the track
+  cnts[key] = live ? count : 0;
+  __syncthreads();
+  if (key == 0) {
+    long long run = 0;
+    for (int k = 0; k < EX_KEYS; ++k) { offs[k] = run; run += cnts[k]; }
+    offs[EX_KEYS] = run;
+    *total = static_cast<int>(run < 0x7fffffffll ? run : 0x7fffffffll);
+  }
+  __syncthreads();
+  for (int k = 0; k < notes; ++k) {
+    const unsigned long long* src = staging + static_cast<size_t>(k) * key_cap;
+    const long long o = offs[k];
+    for (int i = key; i < cnts[k]; i += EX_KEYS)
+      if (o + i < cap) events[o + i] = src[i];
   }
 }
 

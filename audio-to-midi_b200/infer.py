@@ -130,10 +130,13 @@ def stitch_probs_device(model, probs, overlap: float, duration_per_frame: float)
     return torch.as_tensor(modelutil.stitch_probs(probs.cpu().numpy(), overlap, duration_per_frame)).to(probs.device)
 
 
-def extract_events_device(model, stitched, cap: int = 4096):
-    """modelutil.extract_events on the device (a2m_extract_events_dev: one thread per key runs the hysteresis state machine over
-    the frames of its key): stitched torch CUDA [F, 90] -> the same sorted list of (attack, key, duration, velocity) tuples.
-    Only the per-key event tables (a few KB) return to the host, which merges and sorts them as common.rs:142 does."""
+def extract_events_device(model, stitched, cap: int = 65536):
+    """modelutil.extract_events on the device (a2m_extract_events_dev: the comparisons of the hysteresis state machine for all
+    (frame, key) pairs in parallel into bit masks, then the machine per key, jumping from set bit to set bit):
+    stitched torch CUDA [F, 90] -> the same sorted list of (attack, key, duration, velocity) tuples.  Only the events
+    return to the host, one 64-bit word each (attack << 32 | key << 24 | duration), whose ascending order is the order
+    common.rs:142 sorts into.  `cap` is the first guess of the event count; the call is repeated with the true count if it
+    was too small."""
     import ctypes as C
     import torch
     from . import _lib
@@ -141,28 +144,42 @@ def extract_events_device(model, stitched, cap: int = 4096):
     eng = model._engine(dev)
     stitched = stitched.to(torch.float32).contiguous()
     F, K = (int(v) for v in stitched.shape)
-    if K > 96:
+    if K > 96 or F >= 1 << 24:
         return modelutil.extract_events(stitched.cpu().numpy())
-    ev = torch.empty((K, cap, 2), dtype=torch.int32, device=stitched.device)
-    cnt = torch.empty(K, dtype=torch.int32, device=stitched.device)
     stream = C.c_void_p(torch.cuda.current_stream(stitched.device).cuda_stream)
-    rc = eng.L.a2m_extract_events_dev(eng.h, stitched.data_ptr(), F, K, ev.data_ptr(), cnt.data_ptr(), cap, stream)
-    _lib.check(eng.h, rc, "a2m_extract_events_dev", eng.L)
-    counts = cnt.cpu().numpy()
-    if int(counts.max(initial=0)) > cap:                       # a key overflowed its table: the host extractor has no limit
-        return modelutil.extract_events(stitched.cpu().numpy())
-    used = int(counts.max(initial=0))
-    if used == 0:
+    cnt = torch.empty(1, dtype=torch.int32, device=stitched.device)
+    while True:
+        words = torch.empty(cap, dtype=torch.int64, device=stitched.device)
+        rc = eng.L.a2m_extract_events_dev(eng.h, stitched.data_ptr(), F, K, words.data_ptr(), cap, cnt.data_ptr(), stream)
+        _lib.check(eng.h, rc, "a2m_extract_events_dev", eng.L)
+        n = int(cnt.item())
+        if n <= cap:
+            break
+        cap = n
+    if n == 0:
         return []
-    table = ev[:, :used].cpu().numpy().view(np.uint32)          # [K, used, 2]
-    keys, slots = np.nonzero(np.arange(used)[None, :] < counts[:, None])
-    attack = table[keys, slots, 0].astype(np.int64)
-    dur = table[keys, slots, 1].astype(np.int64)
-    order = np.lexsort((dur, keys, attack))                     # (attack, key, duration, velocity) ascending; velocity is constant
-    return list(zip(attack[order].tolist(), keys[order].tolist(), dur[order].tolist(), [7] * len(order)))
+    w = np.sort(words[:n].cpu().numpy())
+    return list(zip((w >> 32).tolist(), ((w >> 24) & 0xFF).tolist(), (w & 0xFFFFFF).tolist(), [7] * n))
 
 
-def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 64, rank: int = None, world_size: int = None,
+def balanced_batches(lo: int, hi: int, max_batch: int) -> list:
+    """[(start, stop)] cutting windows lo .. hi into batches of at most max_batch for predict_many's two compute lanes: as few
+    batches as max_batch allows, an EVEN number of them when there is more than one (an odd one leaves a lane idle for a whole
+    step), and of equal size up to one window -- a forward of 6 windows takes almost as long as one of 64 (every kernel is a
+    chain of dependent phases), so a tail batch is the worst cut.  Measured on 134 windows (tools/split_experiment.py):
+    64 + 64 + 6 -> 3.64 ms, 67 + 67 -> 2.67 ms."""
+    n = hi - lo
+    if n <= 0:
+        return []
+    nb = -(-n // max_batch)
+    if nb > 1 and nb % 2:
+        nb += 1
+    nb = min(nb, n)
+    cuts = [lo + (n * i) // nb for i in range(nb + 1)]
+    return [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
+
+
+def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int = 72, rank: int = None, world_size: int = None,
                     gather: bool = True, want_arrays: bool = True):
     """Long-audio transcription (BASELINE config 5; infer.py:339 / audio_to_midi.py:38-53): normalise + slice on the
     device, batched forward of this rank's block of windows, rank-ordered gather of the probabilities, then stitch and
@@ -182,7 +199,7 @@ def transcribe_clip(model, audio_samples, overlap: float = 0.25, max_batch: int 
     n_total = int(windows.shape[0])
     lo, hi = shard_windows(n_total, world_size, rank)
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
-    parts = [windows[i:min(i + max_batch, hi)] for i in range(lo, hi, max_batch)]
+    parts = [windows[a:b] for a, b in balanced_batches(lo, hi, max_batch)]   # max_batch 72: the widest kernels stay one wave of CTAs
     chunks = [p for _lg, p in model.predict_many(None, parts, rope_freqs)]     # consecutive batches overlap on two streams
     local = torch.cat(chunks) if chunks else torch.zeros((0, 250, 90), dtype=torch.float32, device=windows.device)
     if world_size > 1:
@@ -271,7 +288,7 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
     rope_freqs = precompute_frequencies(model_config["attention_size"], 300)
     rows = []
     on_device = hasattr(audio, "is_cuda") and audio.is_cuda
-    spans = [(i, min(i + max_batch, hi)) for i in range(lo, hi, max_batch)]
+    spans = balanced_batches(lo, hi, max_batch)
 
     def labels_of(i, j):
         if hasattr(events, "is_cuda"):

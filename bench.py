@@ -387,7 +387,7 @@ def measure_clip(ctx, model):
     best = statistics.median(times)
     return {"metric": "clip audio-seconds/sec transcribed end to end", "value": 600.0 / best, "unit": "audio-s/s", "seconds_per_clip": best,
             "clip_seconds": 600.0, "windows": n_windows, "windows_per_gpu": -(-n_windows // ctx.world), "stitched_frames": frames, "events": n_events,
-            "h2d_bytes": int(clip.nbytes) * ctx.world, "d2h": "the event list only (per-key tables of (attack, duration), a few KB): stitch_probs and extract_events run on the device",
+            "h2d_bytes": int(clip.nbytes) * ctx.world, "d2h": "the event list only (one 64-bit word per event): stitch_probs and extract_events run on the device",
             "gather": "all_gather of [windows/N, 250, 90] fp32 blocks (NCCL), rank 0 stitches + eventizes on its GPU" if ctx.world > 1 else "none (one rank)",
             "what": "BASELINE.json configs[4]; infer.transcribe_clip; median of 3 after 1 warm-up; every rank uploads and normalises the whole clip "
                     "(the loudness statistics need all of it), then forwards only its block of windows"}

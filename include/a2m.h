@@ -162,14 +162,16 @@ int a2m_debug_round_operand(const float* in_host, uint16_t* out_host, int64_t n)
  * independent per key"), so that the probabilities of a long clip never travel to the host -- only its event list does.
  * a2m_stitch_probs_dev: probs_dev [windows, frames, cats] -> out_dev [out_frames, cats], bit-identical to a2m_stitch_probs;
  * returns out_frames (out_dev = NULL queries it), or A2M_EINVAL (also when overlap >= about half a window, where consecutive
- * cross-fades would chain: use the host function).  a2m_extract_events_dev: probs_dev [frames, notes <= 96] ->
- * events_dev [notes][cap][2] uint32 (attack, duration) in attack order per key and counts_dev [notes]; a count above cap means
- * that key overflowed.  The caller merges the per-key lists and sorts them (attack, key, duration, velocity = 7), as
- * common.rs:142 does. */
+ * cross-fades would chain: use the host function).  a2m_extract_events_dev: probs_dev [frames < 2^24, notes <= 96] ->
+ * events_dev [cap] 64-bit words  attack << 32 | key << 24 | duration  (one per event, in no particular order: sorting the
+ * words ascending IS the (attack, key, duration) order of common.rs:142; velocity is the constant 7) and *count_dev = the
+ * number of events; a count above cap means the words beyond cap were dropped: call again with a larger buffer.  Two
+ * launches: the comparisons of the state machine for every (frame, key) in parallel into three bit masks per key, then the
+ * machine itself, one thread per key, jumping from set bit to set bit (its cost follows the events, not the frames). */
 int64_t a2m_stitch_probs_dev(A2mHandle* h, const float* probs_dev, int64_t windows, int64_t frames, int64_t cats, double overlap,
                              double duration_per_frame, float* out_dev, int64_t out_capacity_frames, void* stream);
-int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint32_t* events_dev,
-                           int32_t* counts_dev, int32_t cap, void* stream);
+int a2m_extract_events_dev(A2mHandle* h, const float* probs_dev, int64_t frames, int64_t notes, uint64_t* events_dev, int64_t cap,
+                           int32_t* count_dev, void* stream);
 
 /* Number of kernels of this library launched by the last a2m_forward on this handle. */
 int32_t a2m_last_launch_count(const A2mHandle* h);

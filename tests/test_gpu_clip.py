@@ -164,7 +164,7 @@ def test_predict_and_stitch_host_windows():
 def test_device_stitch_and_extract_bit_exact(overlap, windows):
     """a2m_stitch_probs_dev / a2m_extract_events_dev against the C++ host functions and the oracle on the same probabilities:
     the stitched track is bit-identical (f64 cross-fade, fractional window step of overlap 0.25 -> 12.5 frames, NaN rows of overlap 0),
-    the event list is identical, and a tiny per-key table capacity falls back to the host extractor."""
+    the event list is identical, also when the first guess of the event count is too small (the call is repeated)."""
     import audio_to_midi_b200 as A
     from audio_to_midi_b200 import infer as I
     from gpu_util import make_model
@@ -184,4 +184,44 @@ def test_device_stitch_and_extract_bit_exact(overlap, windows):
     ev_dev = I.extract_events_device(model, torch.tensor(clean).cuda())
     assert ev_dev == ev_host and len(ev_host) > 50
     assert ev_host == E.extract_events(clean)
-    assert I.extract_events_device(model, torch.tensor(clean).cuda(), cap=2) == ev_host     # overflow -> host fallback
+    assert I.extract_events_device(model, torch.tensor(clean).cuda(), cap=2) == ev_host     # too small a buffer -> repeated with the true count
+
+
+@pytest.mark.parametrize("frames,kind", [(1, "random"), (255, "random"), (256, "random"), (257, "random"), (5000, "random"),
+                                         (3000, "sustained"), (3000, "hover"), (2049, "boundaries"), (1500, "silent")])
+def test_device_eventizer_bit_mask_walk(frames, kind):
+    """a2m_extract_events_dev turns the state machine's comparisons into three bit masks per key (32 frames per word) and lets
+    one thread per key jump from set bit to set bit (event_metrics.cuh).  Probability tracks built to stress exactly that against
+    the C++ host extractor: tracks shorter than / equal to / one longer than a multiple of the word and tile sizes, keys that never
+    fall below 0.1, keys hovering around all four thresholds (re-attack candidates younger than 6 frames must be skipped), notes
+    that start or end on word boundaries or sound at the last frame, and an all-silent track."""
+    import audio_to_midi_b200 as A
+    from audio_to_midi_b200 import infer as I
+    from gpu_util import make_model
+    model, _ = make_model(1)
+    rng = np.random.Generator(np.random.PCG64(frames * 7 + len(kind)))
+    if kind == "random":
+        p = rng.random((frames, 90)).astype(np.float32)
+    elif kind == "sustained":            # never below 0.1; re-attacks (rises > 0.1 over six frames) and long holds spanning segments
+        p = (0.3 + 0.6 * rng.random((frames, 90))).astype(np.float32)
+        p[:, ::3] = np.clip(0.75 + 0.2 * np.sin(np.arange(frames)[:, None] / rng.uniform(3, 40, size=30)[None, :]), 0.11, 1).astype(np.float32)
+    elif kind == "hover":                # small steps around 0.1 / 0.4 / 0.5
+        centre = rng.choice(np.float32([0.1, 0.4, 0.5]), size=(1, 90))
+        p = (centre + rng.normal(0, 0.03, size=(frames, 90))).clip(0, 1).astype(np.float32)
+        p[::97] = 0.99
+    elif kind == "boundaries":
+        p = np.full((frames, 90), 0.02, dtype=np.float32)
+        for k in range(90):
+            start = 256 * (1 + k % 7) + (k % 5) - 2            # attacks at seg - 2 .. seg + 2
+            stop = 256 * (2 + k % 6) + (k % 3) - 1             # releases at seg - 1 .. seg + 1
+            p[start:max(stop, start + 1), k] = 0.9
+            p[frames - 1 - (k % 2), k] = 0.95                  # still sounding at the end of the track
+    else:
+        p = np.full((frames, 90), 0.05, dtype=np.float32)
+    want = A.modelutil.extract_events(p)
+    got = I.extract_events_device(model, torch.tensor(p).cuda(), cap=16)
+    assert got == want
+    if kind in ("random", "sustained", "hover", "boundaries") and frames > 256:
+        assert len(want) > 50
+    if kind == "silent":
+        assert want == []

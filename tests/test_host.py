@@ -388,3 +388,19 @@ def test_change_fp_precision_selects_the_operand_variant():
     assert A.change_fp_precision(m, np.float32).precision == "f16"
     with pytest.raises(ValueError):
         A.change_fp_precision(m, np.int8)
+
+
+def test_balanced_batches_cover_the_range_evenly():
+    """infer.balanced_batches: the cut of a rank's windows for the two compute lanes -- contiguous, complete, at most max_batch
+    per batch, an even number of batches when more than one, sizes equal up to one window."""
+    from audio_to_midi_b200.infer import balanced_batches
+    assert balanced_batches(0, 134, 72) == [(0, 67), (67, 134)]
+    assert balanced_batches(0, 134, 64) == [(0, 33), (33, 67), (67, 100), (100, 134)]
+    assert balanced_batches(5, 5, 64) == [] and balanced_batches(3, 4, 64) == [(3, 4)]
+    for lo, n, mb in [(0, 1, 1), (7, 64, 64), (0, 65, 64), (10, 512, 64), (0, 3, 1), (0, 200, 72), (0, 17, 72), (2, 129, 64)]:
+        spans = balanced_batches(lo, lo + n, mb)
+        assert spans[0][0] == lo and spans[-1][1] == lo + n
+        assert all(b == c for (_a, b), (c, _d) in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) <= mb and max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+        assert len(spans) == 1 or len(spans) % 2 == 0 or len(spans) == n

@@ -19,7 +19,7 @@ for it in range(4):
         torch.cuda.synchronize(); t.append(time.perf_counter())
     d = pin.to(dev, non_blocking=True); mark()
     w = I.prepare_windows_device(model, d, 0.5); mark()
-    parts = [w[i:i + 64] for i in range(0, w.shape[0], 64)]
+    parts = [w[a:b] for a, b in I.balanced_batches(0, int(w.shape[0]), 72)]
     out = model.predict_many(None, parts, rope); mark()
     probs = torch.cat([p for _, p in out]); mark()
     st = I.stitch_probs_device(model, probs, 0.5, 0.02); mark()
