@@ -376,7 +376,7 @@ def measure_clip(ctx, model):
         _barrier(ctx)
         t0 = time.perf_counter()
         dev_clip = pin.to(ctx.dev, non_blocking=True)
-        events, _st, _pr = I.transcribe_clip(model, dev_clip, overlap=0.5, max_batch=64, want_arrays=False)
+        events, _st, _pr = I.transcribe_clip(model, dev_clip, overlap=0.5, want_arrays=False)
         torch.cuda.synchronize()
         dt = _max_over_ranks(ctx, time.perf_counter() - t0)
         if it > 0:
