@@ -133,17 +133,31 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       // depthwise conv of the 8 tokens of the pass, then their LayerNorm statistics jointly (warp_sum8_all)
       float y[TPP][PER];
       const int l_first = (tile0 + r0) % L;   // one runtime modulo per pass instead of one per token (~22 instructions each)
+      if (l_first >= 3 && l_first + TPP + 3 <= L) {
+        // the pass and its halo lie inside one window (all but 2 of a window's 62 passes): 28 fused multiply-adds per token and
+        // lane, no per-tap boundary test (the tests were a fifth of this phase's instructions; the kernel is issue-bound)
 #pragma unroll
-      for (int i = 0; i < TPP; ++i) {
-        const int l = l_first + i - ((l_first + i >= L) ? L : 0);
+        for (int i = 0; i < TPP; ++i) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
+          for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
-          const int ll = l + t - 3;
-          if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary (warp-uniform)
+          for (int t = 0; t < 7; ++t)
 #pragma unroll
             for (int j = 0; j < PER; ++j) y[i][j] = fmaf(w[t][j], rows[i + t][j], y[i][j]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TPP; ++i) {
+          const int l = l_first + i - ((l_first + i >= L) ? L : 0);
+#pragma unroll
+          for (int j = 0; j < PER; ++j) y[i][j] = bias[j];
+#pragma unroll
+          for (int t = 0; t < 7; ++t) {
+            const int ll = l + t - 3;
+            if (ll >= 0 && ll < L) {  // zero "SAME" padding at the window boundary (warp-uniform)
+#pragma unroll
+              for (int j = 0; j < PER; ++j) y[i][j] = fmaf(w[t][j], rows[i + t][j], y[i][j]);
+            }
           }
         }
       }
@@ -302,9 +316,10 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   // (9 % of the kernel's stall samples sat on the add that consumes them) hides behind the tensor core
   constexpr int NW5 = FB_THREADS / 32;
   constexpr int RPW5 = FB_TOK / NW5;  // 16 rows per warp, in two batches of 8
-  float xpre[RPW5 / 2][PER];
+  constexpr int NPRE = RPW5 / 2;   // (prefetching all 16 rows was measured: no faster, and the registers spill)
+  float xpre[NPRE][PER];
 #pragma unroll
-  for (int i = 0; i < RPW5 / 2; ++i) {
+  for (int i = 0; i < NPRE; ++i) {
     const int tok = tile0 + warp + i * NW5;
     if (tok < M) RM::load(X + static_cast<size_t>(tok) * C, lane, xpre[i]);
   }
@@ -342,9 +357,9 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
 #pragma unroll
       for (int i = 0; i < RPW / 2; ++i) {
         const int tok = tile0 + warp + (half * (RPW / 2) + i) * NW;
-        if (half == 0) {
+        if (half * (RPW / 2) + i < NPRE) {
 #pragma unroll
-          for (int j = 0; j < PER; ++j) xv[i][j] = xpre[i][j];
+          for (int j = 0; j < PER; ++j) xv[i][j] = xpre[half * (RPW / 2) + i][j];
         } else if (tok < M) {
           RM::load(X + static_cast<size_t>(tok) * C, lane, xv[i]);
         }
