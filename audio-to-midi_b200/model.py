@@ -443,6 +443,12 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         if (len(shape) not in (2, 3)) or shape[-2:] != (2, 80000):
             raise ValueError(f"samples must be (2, 80000) or (B, 2, 80000), got {shape}")
         B = 1 if single else shape[0]
+        if B == 0:      # an empty batch maps to empty outputs, as jax.vmap over a zero-length axis does; no launch, no device needed
+            if is_torch:
+                import torch
+                z = torch.empty((0, 250, 90), dtype=torch.float32, device=samples.device)
+                return z, z.clone()
+            return np.empty((0, 250, 90), np.float32), np.empty((0, 250, 90), np.float32)
         if is_torch:
             import torch
             if not samples.is_cuda:
@@ -506,7 +512,7 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
             sin = torch.as_tensor(np.ascontiguousarray(rope_freqs.sin_freq, np.float32)).to(x0.device)
             hit = self._rope_cache[dev] = (cos, sin, rope_freqs)
         cos, sin, _ = hit
-        max_b = max(int(x.shape[0]) for x in xs)
+        max_b = max(1, max(int(x.shape[0]) for x in xs))
         key = (dev, self.precision)
         st = self._lanes.get(key)
         if st is None or st["eng"] is not eng or st["cap"] < max_b or len(st["streams"]) < lanes:
@@ -528,8 +534,11 @@ class OutputSequenceGenerator(Module):   # model.py:673-773
         fork.record(main)
         for s in st["streams"][:lanes]:
             s.wait_event(fork)
-        for i, (x, (lg, pr)) in enumerate(zip(xs, outs)):
-            lane = i % lanes
+        lane = -1
+        for x, (lg, pr) in zip(xs, outs):
+            if int(x.shape[0]) == 0:      # an empty batch: empty views, no launch
+                continue
+            lane = (lane + 1) % lanes
             rc = eng.L.a2m_forward(eng.h, x.data_ptr(), int(x.shape[0]), cos.data_ptr(), sin.data_ptr(), cos.shape[0], lg.data_ptr(),
                                    pr.data_ptr(), C.c_void_p(st["ws"][lane]), st["bytes"], C.c_void_p(st["streams"][lane].cuda_stream))
             _lib.check(eng.h, rc, "a2m_forward", eng.L)

@@ -253,3 +253,38 @@ def test_predict_many_overlaps_batches_bitwise():
             assert torch.equal(lg, rl) and torch.equal(pr, rp)
     one = model.predict_many(None, [wins[:3]], rope)
     assert torch.equal(one[0][1], model.predict(None, wins[:3], rope)[1])
+
+
+@pytest.mark.gpu
+def test_empty_batches_on_the_device():
+    """A zero-length batch gives zero-length outputs on the device path too, alone and inside predict_many (a rank whose block of a
+    short clip is empty), without disturbing its neighbours."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model
+    from oracle import synth
+    model, _ = make_model(4321, **ACTIVE)
+    rope = A.precompute_frequencies(64, 300)
+    wins = torch.tensor(synth.make_windows_fast(5, 9)).cuda()
+    lg, pr = model.predict(None, wins[:0], rope)
+    assert tuple(lg.shape) == tuple(pr.shape) == (0, 250, 90) and pr.is_cuda
+    got = model.predict_many(None, [wins[:2], wins[:0], wins[2:5]], rope)
+    assert tuple(got[1][1].shape) == (0, 250, 90)
+    assert torch.equal(got[0][1], model.predict(None, wins[:2], rope)[1])
+    assert torch.equal(got[2][1], model.predict(None, wins[2:5], rope)[1])
+
+
+@pytest.mark.gpu
+def test_large_batch_matches_small_batches_bitwise():
+    """260 windows in one call: every kernel runs several waves of CTAs (stage 5: 1016 tiles on 296 slots) and the workspace is
+    four times the bench's.  Its probabilities equal, bit for bit, those of the same windows sent in batches of 64 / 64 / 64 / 68."""
+    import audio_to_midi_b200 as A
+    from gpu_util import make_model
+    from oracle import synth
+    model, _ = make_model(4321, **ACTIVE)
+    rope = A.precompute_frequencies(64, 300)
+    base = torch.tensor(synth.make_windows_fast(65, 21)).cuda()
+    audio = torch.cat([base * g for g in (1.0, 0.83, 1.21, 0.67)])           # 260 distinct windows
+    _, pr = model.predict(None, audio, rope)
+    parts = torch.cat([model.predict(None, audio[a:b], rope)[1] for a, b in ((0, 64), (64, 128), (128, 192), (192, 260))])
+    assert torch.equal(pr, parts)
+    assert bool(torch.isfinite(pr).all()) and float(pr.std()) > 1e-3

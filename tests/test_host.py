@@ -404,3 +404,15 @@ def test_balanced_batches_cover_the_range_evenly():
         sizes = [b - a for a, b in spans]
         assert max(sizes) <= mb and max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
         assert len(spans) == 1 or len(spans) % 2 == 0 or len(spans) == n
+
+
+def test_empty_batch_maps_to_empty_outputs_without_a_device():
+    """jax.vmap(model.predict) over a zero-length batch returns zero-length outputs (infer.py:40); the mirror does the same before
+    it ever asks for a GPU, so the edge case is covered on the CPU runner too."""
+    import audio_to_midi_b200 as A
+    model = A.OutputSequenceGenerator(A.model_config, key=3)
+    rope = A.precompute_frequencies(64, 300)
+    logits, probs = model.predict(None, np.zeros((0, 2, 80000), np.float32), rope)
+    assert logits.shape == probs.shape == (0, 250, 90) and logits.dtype == np.float32
+    with pytest.raises(ValueError):
+        model.predict(None, np.zeros((0, 2, 1000), np.float32), rope)
