@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(SB_TOK) block_small_kernel(const float* Xin, f
 // The three Blocks of a narrow stage (C in {4, 8}: a 128-token tile is 2-4 KB, every launch is a latency-bound chain
 // of load -> barrier -> ~300 instructions per token -> store) in ONE launch: the tile is loaded once with a halo of 9
 // tokens, Block k is evaluated by one thread per token for the rows the next Block still needs (halo shrinking by 3 per
-// Block, ping-pong between two shared-memory buffers), the third Block's 128 rows are stored.  One third of the global
+// Block, ping-pong between two shared-memory buffers), the third Block's SS_TOK rows are stored.  One third of the global
 // traffic and of the launches of three block_small_kernel calls; the arithmetic per token is identical (same device
 // function), so are the results.
 template <int C>
@@ -330,8 +330,121 @@ __device__ __forceinline__ void small_block_token(const float* __restrict__ sp, 
   for (int c = 0; c < C; ++c) out[c] = fmaf(sp[Lay::GAMMA + c], o[c], xr[c]);
 }
 
-constexpr int SS_TOK = 128;              // output tokens per CTA
-constexpr int SS_THREADS = 160;          // >= SS_TOK + 12 (rows evaluated by the first Block)
+// Two ADJACENT tokens (buffer rows r and r + 1) per thread: every weight vector fetched from shared memory feeds both tokens and
+// the 8 input rows of the two depthwise windows are read once instead of 2 x 7 -- these kernels spend as many issue slots on
+// LDS as on arithmetic.  Each token's operations are those of small_block_token, in the same order: results are bit-identical.
+// rows = row of (token 0) - 3; `two` = false: only token 0 exists (its partner's results are garbage the caller ignores).
+template <int C>
+__device__ __forceinline__ void small_block_pair(const float* __restrict__ sp, const float* rows, int RS, int l0, int l1, int L, bool two,
+                                                 float* out0 /* [C] */, float* out1 /* [C] */) {
+  using Lay = SmallBlockLayout<C>;
+  constexpr int H = Lay::H, V = C / 4;
+  float y0[C], y1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) y0[c] = y1[c] = sp[Lay::DWB + c];
+  float xa[C], xb[C];                      // rows t and t + 1 of the 8-row window
+#pragma unroll
+  for (int q = 0; q < V; ++q) {
+    const float4 v = reinterpret_cast<const float4*>(rows)[q];
+    xa[4 * q] = v.x; xa[4 * q + 1] = v.y; xa[4 * q + 2] = v.z; xa[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    if (t < 6 || two) {
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 v = reinterpret_cast<const float4*>(rows + (t + 1) * RS)[q];
+        xb[4 * q] = v.x; xb[4 * q + 1] = v.y; xb[4 * q + 2] = v.z; xb[4 * q + 3] = v.w;
+      }
+    }
+    float w[C];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 v = reinterpret_cast<const float4*>(sp + Lay::DW + t * C)[q];
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+    const int ll0 = l0 + t - 3, ll1 = l1 + t - 3;   // zero "SAME" padding at the WINDOW boundary
+    if (ll0 >= 0 && ll0 < L) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) y0[c] = fmaf(w[c], xa[c], y0[c]);
+    }
+    if (ll1 >= 0 && ll1 < L) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) y1[c] = fmaf(w[c], xb[c], y1[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) xa[c] = xb[c];
+  }
+  auto layer_norm = [&](float* y) {
+    float mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) mean += y[c];
+    mean *= (1.0f / C);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) var += (y[c] - mean) * (y[c] - mean);
+    const float inv = rsqrtf(var * (1.0f / C) + kLnEps);
+#pragma unroll
+    for (int c = 0; c < C; ++c) y[c] = (y[c] - mean) * inv * sp[Lay::LNW + c] + sp[Lay::LNB + c];
+  };
+  layer_norm(y0);
+  layer_norm(y1);
+  float o0[C], o1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) o0[c] = o1[c] = sp[Lay::B2 + c];
+#pragma unroll 2
+  for (int h = 0; h < H; ++h) {
+    float a0 = sp[Lay::B1 + h], a1 = a0;
+    const float4* w1 = reinterpret_cast<const float4*>(sp + Lay::W1 + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w1[q];
+      a0 = fmaf(w.x, y0[4 * q], a0);
+      a0 = fmaf(w.y, y0[4 * q + 1], a0);
+      a0 = fmaf(w.z, y0[4 * q + 2], a0);
+      a0 = fmaf(w.w, y0[4 * q + 3], a0);
+      a1 = fmaf(w.x, y1[4 * q], a1);
+      a1 = fmaf(w.y, y1[4 * q + 1], a1);
+      a1 = fmaf(w.z, y1[4 * q + 2], a1);
+      a1 = fmaf(w.w, y1[4 * q + 3], a1);
+    }
+    const float g0 = gelu_tanh_cc(a0), g1 = gelu_tanh_cc(a1);
+    const float4* w2 = reinterpret_cast<const float4*>(sp + Lay::W2T + h * C);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float4 w = w2[q];
+      o0[4 * q] = fmaf(w.x, g0, o0[4 * q]);
+      o0[4 * q + 1] = fmaf(w.y, g0, o0[4 * q + 1]);
+      o0[4 * q + 2] = fmaf(w.z, g0, o0[4 * q + 2]);
+      o0[4 * q + 3] = fmaf(w.w, g0, o0[4 * q + 3]);
+      o1[4 * q] = fmaf(w.x, g1, o1[4 * q]);
+      o1[4 * q + 1] = fmaf(w.y, g1, o1[4 * q + 1]);
+      o1[4 * q + 2] = fmaf(w.z, g1, o1[4 * q + 2]);
+      o1[4 * q + 3] = fmaf(w.w, g1, o1[4 * q + 3]);
+    }
+  }
+  const float* xr0 = rows + 3 * RS;   // layer scale + residual
+  const float* xr1 = rows + 4 * RS;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float g = sp[Lay::GAMMA + c];
+    out0[c] = fmaf(g, o0[c], xr0[c]);
+    out1[c] = fmaf(g, o1[c], xr1[c]);
+  }
+}
+
+#ifndef A2M_SS_PAIR
+#define A2M_SS_PAIR 1                    // two adjacent tokens per thread (small_block_pair): 0.107 -> 0.091 ms per step for the two stages
+#endif
+#ifndef A2M_SS_TOK
+#define A2M_SS_TOK (A2M_SS_PAIR ? 256 : 128)
+#endif
+#ifndef A2M_SS_THREADS
+#define A2M_SS_THREADS 160
+#endif
+constexpr int SS_TOK = A2M_SS_TOK;              // output tokens per CTA
+constexpr int SS_THREADS = A2M_SS_THREADS;      // >= the rows (or row pairs) evaluated by the first Block: SS_TOK + 12
+static_assert(SS_THREADS * (A2M_SS_PAIR ? 2 : 1) >= SS_TOK + 12, "one thread per row (pair) of the first Block");
 template <int C>
 struct SmallStageCfg {
   static constexpr int RS = (C == 4) ? 4 : C + 4;
@@ -384,6 +497,46 @@ __global__ void __launch_bounds__(SS_THREADS) stage_small_kernel(const float* Xi
 #pragma unroll 1
   for (int k = 0; k < 3; ++k) {
     const int first = 3 * (k + 1), count = Cfg::ROWS - 6 * (k + 1);
+#if A2M_SS_PAIR
+    if (2 * static_cast<int>(threadIdx.x) < count) {
+      const int r = first + 2 * threadIdx.x;
+      const int tok = tile0 - 9 + r;
+      const bool two = 2 * static_cast<int>(threadIdx.x) + 1 < count;
+      const bool v0 = tok >= 0 && tok < M, v1 = two && tok + 1 >= 0 && tok + 1 < M;
+      float o0[C], o1[C];
+      if (v0 || v1) {
+        const int l0 = v0 ? tok % L : 0, l1 = v1 ? (tok + 1) % L : 0;
+        small_block_pair<C>(sp + k * Cfg::P, src + (r - 3) * RS, RS, l0, l1, L, two, o0, o1);
+      }
+      if (!v0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) o0[c] = 0.f;
+      }
+      if (!v1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) o1[c] = 0.f;
+      }
+      if (k < 2) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(dst + r * RS)[q] = make_float4(o0[4 * q], o0[4 * q + 1], o0[4 * q + 2], o0[4 * q + 3]);
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(dst + (r + 1) * RS)[q] = make_float4(o1[4 * q], o1[4 * q + 1], o1[4 * q + 2], o1[4 * q + 3]);
+        }
+      } else {
+        if (v0) {
+          float* g = Xout + static_cast<size_t>(tok) * C;
+#pragma unroll
+          for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(g)[q] = make_float4(o0[4 * q], o0[4 * q + 1], o0[4 * q + 2], o0[4 * q + 3]);
+        }
+        if (v1) {
+          float* g = Xout + static_cast<size_t>(tok + 1) * C;
+#pragma unroll
+          for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(g)[q] = make_float4(o1[4 * q], o1[4 * q + 1], o1[4 * q + 2], o1[4 * q + 3]);
+        }
+      }
+    }
+#else
     if (static_cast<int>(threadIdx.x) < count) {
       const int r = first + threadIdx.x;
       const int tok = tile0 - 9 + r;
@@ -403,6 +556,7 @@ __global__ void __launch_bounds__(SS_THREADS) stage_small_kernel(const float* Xi
         for (int q = 0; q < V; ++q) reinterpret_cast<float4*>(g)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
     }
+#endif
     __syncthreads();
     float* t = src; src = dst; dst = t;
   }
