@@ -61,7 +61,8 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sSum + 2 * 128);
   uint64_t* bar_s = bar_load + 1;
   uint64_t* bar_o = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar_v = bar_load + 3;       // V on its own barrier: the S MMAs start as soon as Q and K have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
 
   const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +77,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_v, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<AG_TMEM_COLS>(tmem_slot);
@@ -89,10 +91,11 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   AT_STAMP(65);
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_load, AG_SQ + AG_SK + AG_SV);
+    mbar_arrive_expect_tx(bar_load, AG_SQ + AG_SK);
     tma_load_2d(sQ, &tmQ, bar_load, h * ATT_HD, b * ATT_TP + mt * 128);
     tma_load_2d(sK, &tmK, bar_load, h * ATT_HD, b * ATT_TP);
-    tma_load_2d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, b * ATT_TP);
+    mbar_arrive_expect_tx(bar_v, AG_SV);
+    tma_load_2d(sV, &tmV, bar_v, v_col0 + h * ATT_HD, b * ATT_TP);
     mbar_wait(bar_load, 0);
     tc_fence_after();
     AT_STAMP(66);
@@ -191,6 +194,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
 
   if (threadIdx.x == 0) {
+    mbar_wait(bar_v, 0);
     tc_fence_after();
     constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);  // B = V[key][d]: MN-major
 #pragma unroll
@@ -287,7 +291,8 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + AL_SP);
   uint64_t* bar_s = bar_load + 1;
   uint64_t* bar_o = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar_v = bar_load + 3;       // V on its own barrier: the S MMAs start as soon as Q and K have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
 
   const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -301,6 +306,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_v, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<AL_TMEM_COLS>(tmem_slot);
@@ -314,11 +320,12 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   AT_STAMP(73);
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_load, AL_SQ + AL_SK + AL_SV);
+    mbar_arrive_expect_tx(bar_load, AL_SQ + AL_SK);
     // padded row j <-> token j - 3; rows outside [0, 250) are zero-filled by the TMA unit
     tma_load_3d(sQ, &tmQ, bar_load, h * ATT_HD, mt * 128 - 3, b);
     tma_load_3d(sK, &tmK, bar_load, h * ATT_HD, mt * 128 - 8 - 3, b);
-    tma_load_3d(sV, &tmV, bar_load, v_col0 + h * ATT_HD, mt * 128 - 8 - 3, b);
+    mbar_arrive_expect_tx(bar_v, AL_SV);
+    tma_load_3d(sV, &tmV, bar_v, v_col0 + h * ATT_HD, mt * 128 - 8 - 3, b);
     mbar_wait(bar_load, 0);
     tc_fence_after();
     AT_STAMP(74);
@@ -464,6 +471,7 @@ attn_local_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
 
   if (threadIdx.x == 0) {
+    mbar_wait(bar_v, 0);
     tc_fence_after();
     constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
     const uint64_t dv = umma_desc_sw128(smem_u32(sV));
