@@ -18,6 +18,10 @@
 
 namespace a2m {
 
+#ifndef A2M_PA_TMA_STORE
+#define A2M_PA_TMA_STORE 1
+#endif
+
 constexpr int PA_AUX_BYTES = (2 * FF_F + FF_D) * 4 + 2 * FF_D * 4 + 2 * FF_ROWS * 4 * 4 + 256;   // b1, b2 | lnw, lnb | row stats | barriers
 constexpr size_t PA_SMEM = 1024 + FF_MAIN_BYTES + PA_AUX_BYTES;
 
@@ -329,6 +333,33 @@ postattn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_cons
     // (c) D2 (= x' + FFN) + b2 -> staging (all operand bytes are dead once bar_done fires), then coalesced store
     mbar_wait(bar_done, 0);
     tc_fence_after();
+#if A2M_PA_TMA_STORE
+    // eight [128 rows x 32 fp32] boxes in tmX's 128B-swizzled layout (the layout the x stages arrived in), handed back to global
+    // memory by eight TMA stores: 256 LDS + 256 STG warp instructions per CTA less (the store loop was throttled by the LSU)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = cq * 64 + c * 32;
+      uint32_t r[32];
+      tmem_ld_x32(tmem_d2 + t_row + col0, r);
+      tmem_ld_wait();
+      uint8_t* brow = smem + (col0 >> 5) * 16384 + row * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(brow + ((static_cast<uint32_t>(q) ^ (row & 7)) << 4)) =
+            make_float4(__uint_as_float(r[4 * q]) + sB2[col0 + 4 * q], __uint_as_float(r[4 * q + 1]) + sB2[col0 + 4 * q + 1],
+                        __uint_as_float(r[4 * q + 2]) + sB2[col0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + sB2[col0 + 4 * q + 3]);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, FF_CTHREADS);
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int bx = 0; bx < 8; ++bx) tma_store_2d(&tmX, smem + bx * 16384, bx * 32, tile0);
+      bulk_commit();
+      bulk_wait_all<0>();   // the stores must have landed before the grid counts as complete
+    }
+  }
+
+#else
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col0 = cq * 64 + c * 32;
@@ -354,6 +385,7 @@ postattn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_cons
     }
   }
 
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
