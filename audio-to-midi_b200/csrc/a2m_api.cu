@@ -71,7 +71,7 @@ struct Err {
     }                                                                                               \
   } while (0)
 
-uint16_t f32_to_bf16(float f) {
+[[maybe_unused]] uint16_t f32_to_bf16(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);  // NaN
@@ -79,7 +79,7 @@ uint16_t f32_to_bf16(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 // IEEE binary16, round to nearest even, overflow to infinity, gradual underflow (what cvt.rn.f16.f32 does on the device)
-uint16_t f32_to_f16(float f) {
+[[maybe_unused]] uint16_t f32_to_f16(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
   const uint32_t sign = (u >> 16) & 0x8000u;
@@ -1080,7 +1080,7 @@ bool build_plan(A2mHandle* h, Plan* p, int B, uint8_t* ws_base) {
     const bool local = (i % 2 == 0);
     const TLayerW& t = w.tl[i];
     float* xt = ws.Xt;
-    __nv_bfloat16 *a16 = ws.A16, *qc = ws.QC16, *kv = ws.KV16, *vt = ws.Vt16, *o16 = ws.O16, *h16 = ws.H16;
+    __nv_bfloat16 *a16 = ws.A16, *qc = ws.QC16, *kv = ws.KV16, *o16 = ws.O16, *h16 = ws.H16;
     const bool fused_qkv = w.folded_kv && g_fuse_qkv;
     if (!fused_qkv) {
       const float* lw = dev_ptr<float>(h, t.ln1w);

@@ -51,7 +51,9 @@ postattn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sH = sA + FF_A_BYTES;
   uint8_t* sW = sH + 2 * FF_H_BYTES;
+#if !A2M_PA_TMA_STORE
   float* sStage = reinterpret_cast<float*>(smem);   // aliases everything above once the last MMA has completed
+#endif
   float* sB1 = reinterpret_cast<float*>(smem + FF_MAIN_BYTES);
   float* sB2 = sB1 + 2 * FF_F;
   float* sLnW = sB2 + FF_D;

@@ -335,9 +335,9 @@ __global__ void __launch_bounds__(DwBwd<C>::THREADS) dwconv_ln_bwd_kernel(const 
   using RM = RowMap<C>;
   using D = DwBwd<C>;
   constexpr int PER = RM::PER, TOK = D::TOK, XR = D::XR, AR = D::AR, DWB_THREADS = D::THREADS;
-  extern __shared__ __align__(128) float smem_f[];
-  float* stage0 = smem_f;
-  float* sg = smem_f + 2 * D::STAGE_FLOATS;              // g rows tile0-3 .. tile0+TOK+2
+  extern __shared__ __align__(128) float smem_dwb[];   // own name: the other kernels of this unit declare smem_f with 16-byte alignment
+  float* stage0 = smem_dwb;
+  float* sg = smem_dwb + 2 * D::STAGE_FLOATS;              // g rows tile0-3 .. tile0+TOK+2
   uint64_t* bars = reinterpret_cast<uint64_t*>(sg + AR * C);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
