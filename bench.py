@@ -560,7 +560,9 @@ def run_ours(args):
     roof = None
     if rank == 0:
         peaks = _peaks()
-        prof = model.profile_steps(B, repeats=5, device=local)
+        # three passes, per-launch median: one pass (5 repeats per launch) occasionally carries an outlier of 5-10 % on a family
+        passes = [model.profile_steps(B, repeats=5, device=local) for _ in range(3)]
+        prof = [(p0[0], statistics.median(q[i][1] for q in passes), p0[2], p0[3]) for i, p0 in enumerate(passes[0])]
         fam = {}
         for k, pms, fl, by in prof:
             f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
