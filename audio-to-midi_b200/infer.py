@@ -358,7 +358,11 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
 
     if on_device:      # the set is already resident (audio / events torch CUDA tensors): consecutive batches overlap on the two lanes
         outs = model.predict_many(None, [audio[i:j] for i, j in spans], rope_freqs)
-    elif spans:
+    elif spans and dworld == 1 and torch.get_num_threads() >= 4:
+        # staging through page-locked memory pays with torch's multi-threaded CPU copy and the host to itself (one process:
+        # 10 k -> 27 k windows/s).  Several ranks on one host share its memory bandwidth and run with OMP_NUM_THREADS=1 under
+        # torchrun; measured at 2 ranks the staged path was slower than the driver's own pageable copies (8 k against 15-19 k
+        # windows/s), so multi-rank processes keep the plain path below
         shapes = [audio.shape[1:], events.shape[1:]] if host_labels else [audio.shape[1:]]
         feeder = _HostFeeder(model, tdev, max(j - i for i, j in spans), shapes)
         feeder.stage(0, host_batch(*spans[0]))
@@ -366,6 +370,10 @@ def compute_testset_loss(model, audio, events, rank: int = None, world_size: int
         if on_device:
             y = labels_of(i, j)
             logits, probs = outs[n]
+        elif feeder is None:
+            y = labels_of(i, j)
+            x = torch.as_tensor(np.ascontiguousarray(audio[i:j], np.float32)).to(tdev)
+            logits, probs = model.predict(None, x, rope_freqs)
         else:
             got = feeder.take(n)                                 # the compute stream waits for batch n's upload
             x = got[0]
