@@ -256,3 +256,77 @@ def test_autograd_of_twin_matches_fp64_finite_differences():
                 checked += 1
     assert checked >= 80
     print(f"finite differences: {checked} entries, worst relative error {worst:.2e}")
+
+
+def _events_by_bit_masks(probs):
+    """numpy restatement of the DEVICE eventizer's algorithm (csrc/event_metrics.cuh): every comparison of the state machine is a
+    pure function of the probabilities around a frame, so three masks per key (p > 0.5; p < 0.1; re-attack candidate = p > 0.4,
+    not p[f] < p[f + 1], rise of the six-frame means > 0.1) decide everything, and the machine only has to jump from set bit to
+    set bit: an idle key to the next `on`, a sounding key to the next `off | re`."""
+    p = np.asarray(probs, np.float32)
+    F, K = p.shape
+    on, off = p > np.float32(0.5), p < np.float32(0.1)
+    defer = np.zeros((F, K), bool)
+    defer[:-1] = p[:-1] < p[1:]
+    rise = np.zeros((F, K), bool)
+    for f in range(6, F):
+        before = np.zeros(K, np.float32)
+        for i in range(f - 6, f):
+            before = (before + p[i]).astype(np.float32)          # sequential f32 adds, as the reference forms the mean
+        after = np.zeros(K, np.float32)
+        for i in range(f, min(f + 6, F)):
+            after = (after + p[i]).astype(np.float32)
+        rise[f] = (after / np.float32(6.0) - before / np.float32(6.0)).astype(np.float32) > np.float32(0.1)
+    re = (p > np.float32(0.4)) & ~defer & rise
+    events = []
+    for key in range(K):
+        on_idx = np.flatnonzero(on[:, key])
+        sr_idx = np.flatnonzero(off[:, key] | re[:, key])
+        f, started = 0, -1
+        while f < F:
+            if started < 0:
+                i = np.searchsorted(on_idx, f)
+                if i == len(on_idx):
+                    break
+                started = int(on_idx[i])
+                f = started + 1
+            else:
+                i = np.searchsorted(sr_idx, f)
+                if i == len(sr_idx):
+                    break
+                g = int(sr_idx[i])
+                if off[g, key]:
+                    events.append((started, key, max(g - started, 1), 7))
+                    started = -1
+                elif g - started > 5:
+                    events.append((started, key, max(g - 1 - started, 1), 7))
+                    started = g
+                f = g + 1
+        if started >= 0:
+            events.append((started, key, max(F - started, 1), 7))
+    return sorted(events)
+
+
+@pytest.mark.parametrize("frames,kind", [(1, "random"), (7, "random"), (300, "random"), (400, "hover"), (350, "sustained"), (260, "silent")])
+def test_bit_mask_walk_equals_the_state_machine(frames, kind):
+    """The restructuring the device eventizer rests on (masks + jumps instead of a frame-by-frame state machine) gives the same
+    event list as the restatement of common.rs:47-144 -- on the CPU runner, independent of the CUDA code (which
+    tests/test_gpu_clip.py holds against the C++ extractor)."""
+    from oracle import events as E
+    rng = np.random.Generator(np.random.PCG64(frames * 3 + len(kind)))
+    K = 24
+    if kind == "random":
+        p = rng.random((frames, K)).astype(np.float32)
+    elif kind == "hover":
+        centre = rng.choice(np.float32([0.1, 0.4, 0.5]), size=(1, K))
+        p = (centre + rng.normal(0, 0.03, size=(frames, K))).clip(0, 1).astype(np.float32)
+        p[::53] = 0.99
+    elif kind == "sustained":
+        p = (0.3 + 0.6 * rng.random((frames, K))).astype(np.float32)
+        p[:, ::3] = np.clip(0.75 + 0.2 * np.sin(np.arange(frames)[:, None] / rng.uniform(3, 40, size=(1, 8))), 0.11, 1).astype(np.float32)
+    else:
+        p = np.full((frames, K), 0.05, np.float32)
+    want = E.extract_events(p)
+    assert _events_by_bit_masks(p) == want
+    if kind in ("random", "hover", "sustained") and frames >= 300:
+        assert len(want) > 20
